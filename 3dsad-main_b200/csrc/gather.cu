@@ -1,0 +1,150 @@
+// a2 gather_operation, a5 grouping_operation (forward + backward) -- SURVEY.md 8(a).
+// (No reference file exists to cite: /root/reference is README.md:1-2 only.)
+//
+// HBM-bound copies.  Channel-first public layout: out[b,c,j,s] = f[b,c,idx[b,j,s]].
+// One thread owns FOUR consecutive (j,s) positions: it loads their indices once
+// (one 128-bit load), then walks a chunk of channels issuing 4 independent 4-byte
+// gathers (the source row f[b,c,:] is L1/L2 resident) and ONE 128-bit streaming store
+// per channel, so every store instruction of a warp writes 512 contiguous bytes.
+// gather_operation is grouping_operation with nsample == 1.
+#include "sad_common.cuh"
+
+namespace {
+
+constexpr int GR_T = 256;
+constexpr int GR_CCH = 16;   // channels per thread (grid.y splits the rest)
+
+template <bool VEC>
+__global__ void __launch_bounds__(GR_T)
+group_fwd_kernel(int C, int N, long long PS, const float* __restrict__ features,
+                 const int32_t* __restrict__ idx, float* __restrict__ out) {
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * GR_CCH;
+  const int cn = min(GR_CCH, C - c0);
+  const long long t = (long long)blockIdx.x * GR_T + threadIdx.x;
+  const float* f = features + ((size_t)b * C + c0) * N;
+  if (VEC) {
+    if (t * 4 >= PS) return;
+    const int4 id = __ldg(reinterpret_cast<const int4*>(idx + (size_t)b * PS) + t);
+    float* o = out + ((size_t)b * C + c0) * PS + t * 4;
+    int c = 0;
+    for (; c + 4 <= cn; c += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* fu = f + (size_t)(c + u) * N;
+        v[u] = make_float4(__ldg(fu + id.x), __ldg(fu + id.y), __ldg(fu + id.z), __ldg(fu + id.w));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) __stcs(reinterpret_cast<float4*>(o + (size_t)(c + u) * PS), v[u]);
+    }
+    for (; c < cn; ++c) {
+      const float* fu = f + (size_t)c * N;
+      __stcs(reinterpret_cast<float4*>(o + (size_t)c * PS),
+             make_float4(__ldg(fu + id.x), __ldg(fu + id.y), __ldg(fu + id.z), __ldg(fu + id.w)));
+    }
+  } else {
+    if (t >= PS) return;
+    const int id = __ldg(idx + (size_t)b * PS + t);
+    float* o = out + ((size_t)b * C + c0) * PS + t;
+#pragma unroll 4
+    for (int c = 0; c < cn; ++c) __stcs(o + (size_t)c * PS, __ldg(f + (size_t)c * N + id));
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(GR_T)
+group_bwd_kernel(int C, int N, long long PS, const float* __restrict__ grad_out,
+                 const int32_t* __restrict__ idx, float* __restrict__ grad_features) {
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * GR_CCH;
+  const int cn = min(GR_CCH, C - c0);
+  const long long t = (long long)blockIdx.x * GR_T + threadIdx.x;
+  float* g = grad_features + ((size_t)b * C + c0) * N;
+  if (VEC) {
+    if (t * 4 >= PS) return;
+    const int4 id = __ldg(reinterpret_cast<const int4*>(idx + (size_t)b * PS) + t);
+    const float* go = grad_out + ((size_t)b * C + c0) * PS + t * 4;
+#pragma unroll 4
+    for (int c = 0; c < cn; ++c) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(go + (size_t)c * PS));
+      float* gc = g + (size_t)c * N;
+      atomicAdd(gc + id.x, v.x);
+      atomicAdd(gc + id.y, v.y);
+      atomicAdd(gc + id.z, v.z);
+      atomicAdd(gc + id.w, v.w);
+    }
+  } else {
+    if (t >= PS) return;
+    const int id = __ldg(idx + (size_t)b * PS + t);
+    const float* go = grad_out + ((size_t)b * C + c0) * PS + t;
+#pragma unroll 4
+    for (int c = 0; c < cn; ++c) atomicAdd(g + (size_t)c * N + id, __ldcs(go + (size_t)c * PS));
+  }
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int group_fwd(const char* name, int B, int C, int N, long long PS, const float* features, const int32_t* idx,
+              float* out, cudaStream_t stream) {
+  SAD_REQUIRE(B >= 0 && C >= 0 && N >= 1 && PS >= 0, "%s: bad sizes B=%d C=%d N=%d PS=%lld", name, B, C, N, PS);
+  if (B == 0 || C == 0 || PS == 0) return SAD_OK;
+  SAD_REQUIRE(features && idx && out, "%s: null pointer", name);
+  SAD_REQUIRE(B <= 65535 && sad_ceil_div(C, GR_CCH) <= 65535, "%s: B/C exceed grid limits", name);
+  const bool vec = (PS % 4 == 0) && aligned16(idx) && aligned16(out);
+  dim3 grid((unsigned)sad_ceil_div(vec ? PS / 4 : PS, GR_T), (unsigned)sad_ceil_div(C, GR_CCH), (unsigned)B);
+  if (vec)
+    group_fwd_kernel<true><<<grid, GR_T, 0, stream>>>(C, N, PS, features, idx, out);
+  else
+    group_fwd_kernel<false><<<grid, GR_T, 0, stream>>>(C, N, PS, features, idx, out);
+  SAD_LAUNCH_CHECK(name);
+  return SAD_OK;
+}
+
+int group_bwd(const char* name, int B, int C, int N, long long PS, const float* grad_out, const int32_t* idx,
+              float* grad_features, cudaStream_t stream) {
+  SAD_REQUIRE(B >= 0 && C >= 0 && N >= 1 && PS >= 0, "%s: bad sizes B=%d C=%d N=%d PS=%lld", name, B, C, N, PS);
+  if (B == 0 || C == 0) return SAD_OK;
+  SAD_REQUIRE(grad_features, "%s: null pointer", name);
+  SAD_CUDA_OK(cudaMemsetAsync(grad_features, 0, (size_t)B * C * N * sizeof(float), stream));
+  if (PS == 0) return SAD_OK;
+  SAD_REQUIRE(grad_out && idx, "%s: null pointer", name);
+  SAD_REQUIRE(B <= 65535 && sad_ceil_div(C, GR_CCH) <= 65535, "%s: B/C exceed grid limits", name);
+  const bool vec = (PS % 4 == 0) && aligned16(idx) && aligned16(grad_out);
+  dim3 grid((unsigned)sad_ceil_div(vec ? PS / 4 : PS, GR_T), (unsigned)sad_ceil_div(C, GR_CCH), (unsigned)B);
+  if (vec)
+    group_bwd_kernel<true><<<grid, GR_T, 0, stream>>>(C, N, PS, grad_out, idx, grad_features);
+  else
+    group_bwd_kernel<false><<<grid, GR_T, 0, stream>>>(C, N, PS, grad_out, idx, grad_features);
+  SAD_LAUNCH_CHECK(name);
+  return SAD_OK;
+}
+
+}  // namespace
+
+extern "C" int sad_grouping_operation_fwd(int B, int C, int N, int npoint, int nsample, const float* features,
+                                          const int32_t* idx, float* out, sad_stream_t stream) {
+  SAD_REQUIRE(npoint >= 0 && nsample >= 0, "grouping_operation: bad npoint/nsample");
+  return group_fwd("grouping_operation", B, C, N, (long long)npoint * nsample, features, idx, out,
+                   (cudaStream_t)stream);
+}
+
+extern "C" int sad_grouping_operation_bwd(int B, int C, int N, int npoint, int nsample, const float* grad_out,
+                                          const int32_t* idx, float* grad_features, sad_stream_t stream) {
+  SAD_REQUIRE(npoint >= 0 && nsample >= 0, "grouping_operation_bwd: bad npoint/nsample");
+  return group_bwd("grouping_operation_bwd", B, C, N, (long long)npoint * nsample, grad_out, idx, grad_features,
+                   (cudaStream_t)stream);
+}
+
+extern "C" int sad_gather_operation_fwd(int B, int C, int N, int npoint, const float* features,
+                                        const int32_t* idx, float* out, sad_stream_t stream) {
+  SAD_REQUIRE(npoint >= 0, "gather_operation: bad npoint");
+  return group_fwd("gather_operation", B, C, N, (long long)npoint, features, idx, out, (cudaStream_t)stream);
+}
+
+extern "C" int sad_gather_operation_bwd(int B, int C, int N, int npoint, const float* grad_out,
+                                        const int32_t* idx, float* grad_features, sad_stream_t stream) {
+  SAD_REQUIRE(npoint >= 0, "gather_operation_bwd: bad npoint");
+  return group_bwd("gather_operation_bwd", B, C, N, (long long)npoint, grad_out, idx, grad_features,
+                   (cudaStream_t)stream);
+}

@@ -1,0 +1,275 @@
+"""PointNet++-lineage operator surface over libsad_b200.so.
+
+Seven ``torch.autograd.Function`` subclasses exposed as callables with the lineage
+argument orders (the mounted reference holds no code to cite -- README.md:1-2 only;
+the rows cited are SURVEY.md section 8(a) a1..a9):
+
+    furthest_point_sample(xyz, npoint)                    -> idx  (B,npoint)          i32
+    gather_operation(features, idx)                       -> (B,C,npoint)             f32
+    ball_query(radius, nsample, xyz, new_xyz)             -> idx  (B,npoint,nsample)  i32
+    ball_query_adaptive(radius_t, nsample, xyz, new_xyz)  -> idx  (B,npoint,nsample)  i32
+    grouping_operation(features, idx)                     -> (B,C,npoint,nsample)     f32
+    three_nn(unknown, known)                              -> dist (B,n,3) f32, idx (B,n,3) i32
+    three_interpolate(features, idx, weight)              -> (B,C,n)                  f32
+
+Index outputs are int32 and non-differentiable.  Inputs must be CUDA, contiguous and
+fp32 / int32; anything else raises (no CPU fallback, no silent copies).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+
+def _stream(t: torch.Tensor):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _p(t: torch.Tensor):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _req(t, name, dtype, ndim, last=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: CUDA tensor required (libsad_b200 has no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if t.dim() != ndim:
+        raise ValueError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
+    if last is not None and t.shape[-1] != last:
+        raise ValueError(f"{name}: last dim must be {last}, got shape {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous (call .contiguous() first)")
+    return t
+
+
+def _same_dev(*ts):
+    d = ts[0].device
+    for t in ts[1:]:
+        if t.device != d:
+            raise RuntimeError("all tensors must live on the same CUDA device")
+    return d
+
+
+class FurthestPointSampling(Function):
+    """a1.  xyz (B,N,3) f32 -> (B,npoint) i32; sel[0]=0, ties to the lowest index."""
+
+    @staticmethod
+    def forward(ctx, xyz, npoint):
+        _req(xyz, "xyz", torch.float32, 3, 3)
+        B, N, _ = xyz.shape
+        npoint = int(npoint)
+        if npoint < 1 or N < 1:
+            raise ValueError("furthest_point_sample: need N >= 1 and npoint >= 1")
+        out = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+        with torch.cuda.device(xyz.device):
+            _lib.check(_lib.load().sad_furthest_point_sample_fwd(B, N, npoint, _p(xyz), _p(out), _stream(xyz)),
+                       "furthest_point_sample")
+        ctx.mark_non_differentiable(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad=None):
+        return None, None
+
+
+class GatherOperation(Function):
+    """a2.  features (B,C,N) f32, idx (B,npoint) i32 -> (B,C,npoint)."""
+
+    @staticmethod
+    def forward(ctx, features, idx):
+        _req(features, "features", torch.float32, 3)
+        _req(idx, "idx", torch.int32, 2)
+        _same_dev(features, idx)
+        B, C, N = features.shape
+        if idx.shape[0] != B:
+            raise ValueError("gather_operation: batch mismatch")
+        npoint = idx.shape[1]
+        out = torch.empty((B, C, npoint), dtype=torch.float32, device=features.device)
+        with torch.cuda.device(features.device):
+            _lib.check(_lib.load().sad_gather_operation_fwd(B, C, N, npoint, _p(features), _p(idx), _p(out),
+                                                            _stream(features)), "gather_operation")
+        ctx.save_for_backward(idx)
+        ctx.N = N
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        B, C, npoint = grad_out.shape
+        g = torch.empty((B, C, ctx.N), dtype=torch.float32, device=grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            _lib.check(_lib.load().sad_gather_operation_bwd(B, C, ctx.N, npoint, _p(grad_out), _p(idx), _p(g),
+                                                            _stream(grad_out)), "gather_operation_bwd")
+        return g, None
+
+
+class BallQuery(Function):
+    """a3.  (radius, nsample, xyz (B,N,3), new_xyz (B,npoint,3)) -> idx (B,npoint,nsample) i32."""
+
+    @staticmethod
+    def forward(ctx, radius, nsample, xyz, new_xyz):
+        _req(xyz, "xyz", torch.float32, 3, 3)
+        _req(new_xyz, "new_xyz", torch.float32, 3, 3)
+        _same_dev(xyz, new_xyz)
+        B, N, _ = xyz.shape
+        if new_xyz.shape[0] != B:
+            raise ValueError("ball_query: batch mismatch")
+        npoint, nsample = new_xyz.shape[1], int(nsample)
+        if nsample < 1:
+            raise ValueError("ball_query: nsample must be >= 1")
+        out = torch.empty((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
+        with torch.cuda.device(xyz.device):
+            _lib.check(_lib.load().sad_ball_query_fwd(B, N, npoint, float(radius), nsample, _p(xyz), _p(new_xyz),
+                                                      _p(out), _stream(xyz)), "ball_query")
+        ctx.mark_non_differentiable(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad=None):
+        return None, None, None, None
+
+
+class BallQueryAdaptive(Function):
+    """a4 (3DSAD).  radius_t (B,npoint) f32: per-cluster radius from predicted object size."""
+
+    @staticmethod
+    def forward(ctx, radius_t, nsample, xyz, new_xyz):
+        _req(xyz, "xyz", torch.float32, 3, 3)
+        _req(new_xyz, "new_xyz", torch.float32, 3, 3)
+        _req(radius_t, "radius_t", torch.float32, 2)
+        _same_dev(xyz, new_xyz, radius_t)
+        B, N, _ = xyz.shape
+        npoint, nsample = new_xyz.shape[1], int(nsample)
+        if new_xyz.shape[0] != B or tuple(radius_t.shape) != (B, npoint):
+            raise ValueError("ball_query_adaptive: radius_t must have shape (B, npoint)")
+        if nsample < 1:
+            raise ValueError("ball_query_adaptive: nsample must be >= 1")
+        out = torch.empty((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
+        with torch.cuda.device(xyz.device):
+            _lib.check(_lib.load().sad_ball_query_adaptive_fwd(B, N, npoint, _p(radius_t), nsample, _p(xyz),
+                                                               _p(new_xyz), _p(out), _stream(xyz)),
+                       "ball_query_adaptive")
+        ctx.mark_non_differentiable(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad=None):
+        return None, None, None, None
+
+
+class GroupingOperation(Function):
+    """a5.  features (B,C,N) f32, idx (B,npoint,nsample) i32 -> (B,C,npoint,nsample)."""
+
+    @staticmethod
+    def forward(ctx, features, idx):
+        _req(features, "features", torch.float32, 3)
+        _req(idx, "idx", torch.int32, 3)
+        _same_dev(features, idx)
+        B, C, N = features.shape
+        if idx.shape[0] != B:
+            raise ValueError("grouping_operation: batch mismatch")
+        _, npoint, nsample = idx.shape
+        out = torch.empty((B, C, npoint, nsample), dtype=torch.float32, device=features.device)
+        with torch.cuda.device(features.device):
+            _lib.check(_lib.load().sad_grouping_operation_fwd(B, C, N, npoint, nsample, _p(features), _p(idx),
+                                                              _p(out), _stream(features)), "grouping_operation")
+        ctx.save_for_backward(idx)
+        ctx.N = N
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        B, C, npoint, nsample = grad_out.shape
+        g = torch.empty((B, C, ctx.N), dtype=torch.float32, device=grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            _lib.check(_lib.load().sad_grouping_operation_bwd(B, C, ctx.N, npoint, nsample, _p(grad_out), _p(idx),
+                                                              _p(g), _stream(grad_out)), "grouping_operation_bwd")
+        return g, None
+
+
+class ThreeNN(Function):
+    """a8.  unknown (B,n,3), known (B,m,3), m >= 3 -> dist (B,n,3) f32, idx (B,n,3) i32."""
+
+    @staticmethod
+    def forward(ctx, unknown, known):
+        _req(unknown, "unknown", torch.float32, 3, 3)
+        _req(known, "known", torch.float32, 3, 3)
+        _same_dev(unknown, known)
+        B, n, _ = unknown.shape
+        m = known.shape[1]
+        if known.shape[0] != B:
+            raise ValueError("three_nn: batch mismatch")
+        if m < 3:
+            raise ValueError("three_nn requires m >= 3 known points")
+        dist = torch.empty((B, n, 3), dtype=torch.float32, device=unknown.device)
+        idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknown.device)
+        with torch.cuda.device(unknown.device):
+            _lib.check(_lib.load().sad_three_nn_fwd(B, n, m, _p(unknown), _p(known), _p(dist), _p(idx),
+                                                    _stream(unknown)), "three_nn")
+        ctx.mark_non_differentiable(dist, idx)
+        return dist, idx
+
+    @staticmethod
+    def backward(ctx, a=None, b=None):
+        return None, None
+
+
+class ThreeInterpolate(Function):
+    """a9.  features (B,C,m) f32, idx (B,n,3) i32, weight (B,n,3) f32 -> (B,C,n)."""
+
+    @staticmethod
+    def forward(ctx, features, idx, weight):
+        _req(features, "features", torch.float32, 3)
+        _req(idx, "idx", torch.int32, 3, 3)
+        _req(weight, "weight", torch.float32, 3, 3)
+        _same_dev(features, idx, weight)
+        B, C, m = features.shape
+        n = idx.shape[1]
+        if idx.shape[0] != B or tuple(weight.shape) != tuple(idx.shape):
+            raise ValueError("three_interpolate: idx / weight must both be (B,n,3)")
+        out = torch.empty((B, C, n), dtype=torch.float32, device=features.device)
+        with torch.cuda.device(features.device):
+            _lib.check(_lib.load().sad_three_interpolate_fwd(B, C, m, n, _p(features), _p(idx), _p(weight),
+                                                             _p(out), _stream(features)), "three_interpolate")
+        ctx.save_for_backward(idx, weight)
+        ctx.m = m
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, weight = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        B, C, n = grad_out.shape
+        g = torch.empty((B, C, ctx.m), dtype=torch.float32, device=grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            _lib.check(_lib.load().sad_three_interpolate_bwd(B, C, n, ctx.m, _p(grad_out), _p(idx), _p(weight),
+                                                             _p(g), _stream(grad_out)), "three_interpolate_bwd")
+        return g, None, None
+
+
+furthest_point_sample = FurthestPointSampling.apply
+gather_operation = GatherOperation.apply
+ball_query = BallQuery.apply
+ball_query_adaptive = BallQueryAdaptive.apply
+grouping_operation = GroupingOperation.apply
+three_nn = ThreeNN.apply
+three_interpolate = ThreeInterpolate.apply
+
+
+def size_to_radius(size: torch.Tensor, alpha: float = 1.0, r_min: float = 0.1, r_max: float = 1.2):
+    """Predicted box size (B,K,3) -> per-cluster radius (B,K):
+    r = clamp(alpha * 0.5 * ||size||_2, r_min, r_max)   [SURVEY a4, DECISION: formula unpinned]."""
+    s = size.float()
+    n2 = (s[..., 0] * s[..., 0] + s[..., 1] * s[..., 1]) + s[..., 2] * s[..., 2]
+    r = (alpha * 0.5) * torch.sqrt(n2)
+    return r.clamp(min=r_min, max=r_max).contiguous()
