@@ -19,6 +19,7 @@ SIGNATURES = {
     "sad_version": [],
     "sad_last_error_string": [],
     "sad_fps_force_cluster_size": [_c_int],
+    "sad_launch_count": [],
     "sad_furthest_point_sample_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
     "sad_gather_operation_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_gather_operation_bwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
@@ -30,7 +31,8 @@ SIGNATURES = {
     "sad_three_interpolate_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_three_interpolate_bwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
 }
-_RESTYPES = {"sad_last_error_string": ctypes.c_char_p, "sad_fps_force_cluster_size": None}
+_RESTYPES = {"sad_last_error_string": ctypes.c_char_p, "sad_fps_force_cluster_size": None,
+             "sad_launch_count": ctypes.c_ulonglong}
 
 _lib = None
 _lock = threading.Lock()
@@ -67,3 +69,56 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = load().sad_last_error_string()
         raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+class CallProfiler:
+    """Context manager: CUDA-event timing of every C-ABI call made inside it (used by
+    bench.py / tools for the per-kernel view; never active on the timed path).
+
+        with CallProfiler() as prof: model(...)
+        prof.summary() -> {entry_point: {"calls": n, "ms": total_device_ms}}
+    """
+
+    def __init__(self):
+        self.records = []
+        self._saved = {}
+
+    def __enter__(self):
+        import torch
+        lib = load()
+        for name in SIGNATURES:
+            if not (name.endswith("_fwd") or name.endswith("_bwd")):
+                continue
+            fn = getattr(lib, name)
+            self._saved[name] = fn
+
+            def wrapped(*args, _fn=fn, _name=name):
+                a = torch.cuda.Event(enable_timing=True)
+                b = torch.cuda.Event(enable_timing=True)
+                a.record()
+                rc = _fn(*args)
+                b.record()
+                self.records.append((_name, args, a, b))
+                return rc
+
+            setattr(lib, name, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        lib = load()
+        for name, fn in self._saved.items():
+            setattr(lib, name, fn)
+        torch.cuda.synchronize()
+        return False
+
+    def rows(self):
+        return [(name, args, a.elapsed_time(b)) for (name, args, a, b) in self.records]
+
+    def summary(self):
+        out = {}
+        for name, _, ms in self.rows():
+            d = out.setdefault(name, {"calls": 0, "ms": 0.0})
+            d["calls"] += 1
+            d["ms"] += ms
+        return out

@@ -3,37 +3,49 @@
 //
 // B200 design.  FPS is `npoint` strictly serial iterations, each a full pass over the
 // scene plus an argmax; the bound is per-iteration LATENCY, not HBM.  So:
-//   * every point (x,y,z,min-dist) lives in REGISTERS for the whole kernel: thread t
-//     of CTA r owns points k = (p*CS + r)*T + t, p < P  (P compile-time, unrolled);
-//   * small scenes (N <= 4096): one CTA per scene, one __syncthreads per iteration;
-//   * large scenes: one thread-block CLUSTER (up to 16 CTAs = 16 SMs) per scene.  The
-//     per-CTA winner record {dist,idx,x,y,z} is pushed into every peer's shared memory
-//     with st.shared::cluster (DSMEM) and one barrier.cluster per iteration publishes
-//     it -- no global memory on the critical path at all;
-//   * argmax with ties -> lowest index: redux.sync.max on the (non-negative) distance
-//     bits, then redux.sync.min on the index among the maxima (H2).
-// Slots past N are given min-dist 0 and an index >= N, so they can only ever tie at 0
-// and then lose to a real point on the index rule.
+//   * every point (x,y,z,min-dist) lives in REGISTERS for the whole kernel.  Warp g
+//     (g = cta_rank*NW + warp) owns the contiguous index range [g*P*32, (g+1)*P*32),
+//     thread `lane` the points k = (g*P + p)*32 + lane, p < P (compile-time, unrolled);
+//   * small scenes: one CTA per scene; large scenes: one thread-block CLUSTER (up to 16
+//     CTAs = 16 SMs) per scene;
+//   * per iteration each warp reduces its own points with redux.sync (max on the
+//     non-negative distance bits, then min on the index among the maxima: ties -> lowest
+//     index, H2) and pushes ONE 16-byte record {dist, x, y, z} straight into slot g of
+//     every peer CTA's shared memory with st.async (DSMEM) -- the store itself signals
+//     the peer's mbarrier (complete_tx), so there is no cluster barrier, no CTA barrier
+//     and no global memory on the critical path;
+//   * every warp then reduces the CS*NW records.  Because warps own ascending index
+//     ranges, "lowest slot among equal distances" == "lowest index", so the index never
+//     travels: the winning warp alone writes it to the output.
+// Slots past N get min-dist 0 and an index >= N: they can only ever tie at 0 and then
+// lose to a real point on the index rule.
 #include "sad_common.cuh"
 
 namespace {
 
 using namespace sad;
 
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, float a, float b, float c, float d, uint32_t rbar) {
+  asm volatile(
+      "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+          raddr),
+      "f"(a), "f"(b), "f"(c), "f"(d), "r"(rbar)
+      : "memory");
+}
+
 template <int T, int P, int CS>
 __global__ void __launch_bounds__(T, 1)
 fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict__ out) {
   constexpr int NW = T / 32;
-  extern __shared__ __align__(16) float s_pts[];          // [3][P*T] SoA copy for winner lookup
-  __shared__ uint2 s_w[2][NW];                             // per-warp (dist bits, idx)
-  __shared__ __align__(16) uint32_t s_rec[2][CS][8];       // per-CTA records (cluster variant)
-
-  float* sx = s_pts;
-  float* sy = s_pts + P * T;
-  float* sz = s_pts + 2 * P * T;
+  constexpr int NSLOT = CS * NW;
+  constexpr int RPL = (NSLOT + 31) / 32;                 // records per lane in the final reduce
+  extern __shared__ __align__(16) float4 s_pts[];         // [P*T] (x,y,z,-) copy for winner lookup
+  __shared__ __align__(16) float4 s_rec[2][NSLOT];        // {dist bits, x, y, z} per warp of the cluster
+  __shared__ __align__(8) uint64_t s_bar[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = (CS > 1) ? cluster_ctarank() : 0u;
+  const int g = (int)rank * NW + warp;                    // slot id == ascending index range id
   const int b = blockIdx.x / CS;
   const float* pts = xyz + (size_t)b * N * 3;
   int32_t* o = out + (size_t)b * npoint;
@@ -41,7 +53,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict
   float px[P], py[P], pz[P], md[P];
 #pragma unroll
   for (int p = 0; p < P; ++p) {
-    const int k = (p * CS + (int)rank) * T + tid;
+    const int k = (g * P + p) * 32 + lane;
     if (k < N) {
       px[p] = __ldg(pts + 3 * (size_t)k);
       py[p] = __ldg(pts + 3 * (size_t)k + 1);
@@ -51,85 +63,90 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict
       px[p] = py[p] = pz[p] = 0.f;
       md[p] = 0.f;
     }
-    sx[p * T + tid] = px[p];
-    sy[p * T + tid] = py[p];
-    sz[p * T + tid] = pz[p];
+    s_pts[p * T + tid] = make_float4(px[p], py[p], pz[p], 0.f);
   }
   float qx = __ldg(pts), qy = __ldg(pts + 1), qz = __ldg(pts + 2);
   if (rank == 0 && tid == 0) o[0] = 0;
+
+  uint32_t r_rec[2] = {0, 0}, r_bar[2] = {0, 0};          // DSMEM addresses in peer CTA `lane`
+  if (CS > 1) {
+    if (tid == 0) {
+      mbar_init(&s_bar[0], 1);
+      mbar_init(&s_bar[1], 1);
+      mbar_fence_init();
+    }
+    const uint32_t dst = (uint32_t)(lane % CS);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      r_rec[u] = mapa(smem_u32(&s_rec[u][g]), dst);
+      r_bar[u] = mapa(smem_u32(&s_bar[u]), dst);
+    }
+  }
   __syncthreads();
-  if (CS > 1) cluster_sync_all();   // every peer CTA is resident before any DSMEM store
+  if (CS > 1) cluster_sync_all();   // peers resident + mbarrier inits visible before any DSMEM store
 
   for (int j = 1; j < npoint; ++j) {
     const int buf = j & 1;
-    // ---- local pass over the P register-resident points
-    float bv = 0.f;
-    int bp = 0;
+    if (CS > 1 && tid == 0) mbar_arrive_expect_tx(&s_bar[buf], NSLOT * 16);
+
+    // ---- local pass over the P register-resident points (two independent best-chains)
+    float bv0 = -1.f, bv1 = -1.f;
+    int bp0 = 0, bp1 = 1;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
       const float d = sqdist(px[p], py[p], pz[p], qx, qy, qz);
       const float m = fminf(md[p], d);
       md[p] = m;
-      if (p == 0) {
-        bv = m;
-      } else if (m > bv) {   // strict: ascending p == ascending index inside a thread
-        bv = m;
-        bp = p;
+      if (p & 1) {
+        if (m > bv1) { bv1 = m; bp1 = p; }   // strict: ascending p == ascending index in a thread
+      } else {
+        if (m > bv0) { bv0 = m; bp0 = p; }
       }
     }
+    float bv = bv0;
+    int bp = bp0;
+    if (P > 1 && (bv1 > bv0 || (bv1 == bv0 && bp1 < bp0))) { bv = bv1; bp = bp1; }
+
     const uint32_t vb = __float_as_uint(bv);
-    const uint32_t bk = (uint32_t)((bp * CS + (int)rank) * T + tid);
+    const uint32_t bk = (uint32_t)((g * P + bp) * 32 + lane);
     const uint32_t wmax = __reduce_max_sync(FULL, vb);
     const uint32_t wk = __reduce_min_sync(FULL, vb == wmax ? bk : 0xFFFFFFFFu);
-    if (lane == 0) s_w[buf][warp] = make_uint2(wmax, wk);
+    const int lp = (int)(wk >> 5) - g * P;
+    const float4 c = s_pts[lp * T + warp * 32 + (int)(wk & 31u)];
 
     if (CS == 1) {
+      if (lane == 0) s_rec[buf][warp] = make_float4(__uint_as_float(wmax), c.x, c.y, c.z);
       __syncthreads();
-      const uint2 e = (lane < NW) ? s_w[buf][lane] : make_uint2(0u, 0xFFFFFFFFu);
-      const uint32_t cmax = __reduce_max_sync(FULL, e.x);
-      const uint32_t ck = __reduce_min_sync(FULL, e.x == cmax ? e.y : 0xFFFFFFFFu);
-      qx = sx[ck];   // CS == 1: slot index == point index
-      qy = sy[ck];
-      qz = sz[ck];
-      if (tid == 0) o[j] = (int32_t)ck;
     } else {
-      if (warp != 0) {
-        named_bar_arrive(1, T);
-      } else {
-        named_bar_sync(1, T);
-        const uint2 e = (lane < NW) ? s_w[buf][lane] : make_uint2(0u, 0xFFFFFFFFu);
-        const uint32_t cmax = __reduce_max_sync(FULL, e.x);
-        const uint32_t ck = __reduce_min_sync(FULL, e.x == cmax ? e.y : 0xFFFFFFFFu);
-        const uint32_t slot = ((ck / T) / CS) * T + (ck % T);
-        const float cx = sx[slot], cy = sy[slot], cz = sz[slot];
-        if (lane < CS) {
-          st_cluster_v4(mapa(smem_u32(&s_rec[buf][rank][0]), (uint32_t)lane), cmax, ck,
-                        __float_as_uint(cx), __float_as_uint(cy));
-        } else if (lane < 2 * CS) {
-          st_cluster_b32(mapa(smem_u32(&s_rec[buf][rank][4]), (uint32_t)(lane - CS)),
-                         __float_as_uint(cz));
-        }
-      }
-      cluster_arrive_release();
-      cluster_wait_acquire();
-      const uint2 e = (lane < CS) ? *reinterpret_cast<const uint2*>(&s_rec[buf][lane][0])
-                                  : make_uint2(0u, 0xFFFFFFFFu);
-      const uint32_t gmax = __reduce_max_sync(FULL, e.x);
-      const uint32_t gk = __reduce_min_sync(FULL, e.x == gmax ? e.y : 0xFFFFFFFFu);
-      const uint32_t who = __ballot_sync(FULL, lane < CS && e.x == gmax && e.y == gk);
-      const int w = __ffs(who) - 1;
-      qx = __uint_as_float(s_rec[buf][w][2]);
-      qy = __uint_as_float(s_rec[buf][w][3]);
-      qz = __uint_as_float(s_rec[buf][w][4]);
-      if (rank == 0 && tid == 0) o[j] = (int32_t)gk;
+      if (lane < CS) st_async_v4(r_rec[buf], __uint_as_float(wmax), c.x, c.y, c.z, r_bar[buf]);
+      mbar_wait(&s_bar[buf], (uint32_t)((j >> 1) & 1));
     }
+
+    // ---- every warp reduces the NSLOT records: max dist, ties -> lowest slot (== lowest index)
+    uint32_t v = 0u, slot = 0xFFFFFFFFu;
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+      const int s = lane + 32 * r;
+      if (s < NSLOT) {
+        const uint32_t x = __float_as_uint(s_rec[buf][s].x);
+        if (slot == 0xFFFFFFFFu || x > v) { v = x; slot = (uint32_t)s; }
+      }
+    }
+    const uint32_t gmax = __reduce_max_sync(FULL, v);
+    const uint32_t gslot = __reduce_min_sync(FULL, v == gmax ? slot : 0xFFFFFFFFu);
+    const float4 w = s_rec[buf][gslot];
+    qx = w.y;
+    qy = w.z;
+    qz = w.w;
+    if ((int)gslot == g && lane == 0) o[j] = (int32_t)wk;
   }
+  if (CS > 1) cluster_sync_all();   // no CTA retires while a peer's st.async may still target it
 }
 
 template <int T, int P, int CS>
 int launch_fps(int B, int N, int npoint, const float* xyz, int32_t* idx, cudaStream_t stream) {
   auto kern = fps_kernel<T, P, CS>;
-  const size_t smem = (size_t)3 * P * T * sizeof(float);
+  const size_t smem = (size_t)P * T * sizeof(float4);
   static thread_local int configured_dev = -1;   // per (T,P,CS) instantiation and thread
   int dev = 0;
   SAD_CUDA_OK(cudaGetDevice(&dev));
@@ -151,7 +168,16 @@ int launch_fps(int B, int N, int npoint, const float* xyz, int32_t* idx, cudaStr
   cfg.attrs = attr;
   cfg.numAttrs = (CS > 1) ? 1 : 0;
   SAD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, xyz, N, npoint, idx));
+  sad_count_launch(1);
   return SAD_OK;
+}
+
+constexpr int kPs[] = {1, 2, 3, 4, 6, 8, 10, 12, 16, 20, 24, 32, 40, 48};
+
+int round_p(int p) {
+  for (int a : kPs)
+    if (p <= a) return a;
+  return -1;
 }
 
 template <int T, int CS>
@@ -164,25 +190,36 @@ int dispatch_p(int P, int B, int N, int npoint, const float* xyz, int32_t* idx, 
     SAD_FPS_CASE(2)
     SAD_FPS_CASE(3)
     SAD_FPS_CASE(4)
-    SAD_FPS_CASE(5)
     SAD_FPS_CASE(6)
     SAD_FPS_CASE(8)
     SAD_FPS_CASE(10)
-    SAD_FPS_CASE(13)
+    SAD_FPS_CASE(12)
     SAD_FPS_CASE(16)
     SAD_FPS_CASE(20)
-    SAD_FPS_CASE(25)
+    SAD_FPS_CASE(24)
+    SAD_FPS_CASE(32)
+    SAD_FPS_CASE(40)
+    SAD_FPS_CASE(48)
 #undef SAD_FPS_CASE
   }
   sad_set_error("fps: no kernel for P=%d", P);
   return SAD_EUNSUPPORTED;
 }
 
-int round_p(int p) {
-  static const int allowed[] = {1, 2, 3, 4, 5, 6, 8, 10, 13, 16, 20, 25};
-  for (int a : allowed)
-    if (p <= a) return a;
-  return -1;
+// Large scenes only: wider CTAs at the maximum cluster size.
+int dispatch_big(int T, int P, int B, int N, int npoint, const float* xyz, int32_t* idx, cudaStream_t s) {
+  if (T == 256) {
+    switch (P) {
+      case 24: return launch_fps<256, 24, 16>(B, N, npoint, xyz, idx, s);
+      case 32: return launch_fps<256, 32, 16>(B, N, npoint, xyz, idx, s);
+      case 40: return launch_fps<256, 40, 16>(B, N, npoint, xyz, idx, s);
+      case 48: return launch_fps<256, 48, 16>(B, N, npoint, xyz, idx, s);
+    }
+  } else if (T == 512 && P == 25) {
+    return launch_fps<512, 25, 16>(B, N, npoint, xyz, idx, s);
+  }
+  sad_set_error("fps: no large-scene kernel for T=%d P=%d", T, P);
+  return SAD_EUNSUPPORTED;
 }
 
 }  // namespace
@@ -198,27 +235,30 @@ extern "C" int sad_furthest_point_sample_fwd(int B, int N, int npoint, const flo
               npoint);
   if (B == 0) return SAD_OK;
   SAD_REQUIRE(xyz && idx, "furthest_point_sample: null pointer");
-  constexpr int T = 512;
+  constexpr int T = 128, PMAX = 48;
+  if ((long long)N > 16LL * 512 * 25) {
+    sad_set_error("furthest_point_sample: N=%d exceeds the register-resident capacity (%d)", N, 16 * 512 * 25);
+    return SAD_EUNSUPPORTED;
+  }
+  if ((long long)N > 16LL * T * PMAX) {   // > 98304 points: wider CTAs, cluster of 16
+    if ((long long)N <= 16LL * 256 * PMAX) {
+      return dispatch_big(256, round_p(sad_ceil_div(N, 16 * 256)) < 24 ? 24 : round_p(sad_ceil_div(N, 16 * 256)), B,
+                          N, npoint, xyz, idx, stream);
+    }
+    return dispatch_big(512, 25, B, N, npoint, xyz, idx, stream);
+  }
   int cs = g_force_cs;
   if (cs == 0) {
-    if (N <= 4096) {
+    if (N <= 3072) {
       cs = 1;
     } else {
       // largest cluster that still lets every scene of the batch run in one wave
       cs = 16;
-      while (cs > 2 && (long long)B * cs > 144) cs >>= 1;
+      while (cs > 2 && (long long)B * cs > 148) cs >>= 1;
     }
   }
   SAD_REQUIRE(cs == 1 || cs == 2 || cs == 4 || cs == 8 || cs == 16, "fps: bad cluster size %d", cs);
-  while (cs < 16 && (long long)cs * T * 25 < N) cs <<= 1;   // capacity: P <= 25 points / thread
-  if ((long long)cs * T * 25 < N) {
-    sad_set_error("furthest_point_sample: N=%d exceeds the register-resident capacity (%d)", N, 16 * T * 25);
-    return SAD_EUNSUPPORTED;
-  }
-  if (cs == 1 && N <= 1024) {
-    const int P = round_p(sad_ceil_div(N, 256));
-    return dispatch_p<256, 1>(P, B, N, npoint, xyz, idx, stream);
-  }
+  while (cs < 16 && (long long)cs * T * PMAX < N) cs <<= 1;   // capacity: P <= 48 points / thread
   const int P = round_p(sad_ceil_div(N, (long long)cs * T));
   switch (cs) {
     case 1: return dispatch_p<T, 1>(P, B, N, npoint, xyz, idx, stream);

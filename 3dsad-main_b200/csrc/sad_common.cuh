@@ -12,6 +12,7 @@
 
 // ---------------------------------------------------------------- host side
 void sad_set_error(const char* fmt, ...);
+void sad_count_launch(int n);
 
 #define SAD_REQUIRE(cond, ...)          \
   do {                                  \
@@ -38,6 +39,7 @@ void sad_set_error(const char* fmt, ...);
       sad_set_error("launch of %s failed: %s", name, cudaGetErrorString(e_));    \
       return SAD_ECUDA;                                                          \
     }                                                                            \
+    sad_count_launch(1);                                                         \
   } while (0)
 
 static inline int sad_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

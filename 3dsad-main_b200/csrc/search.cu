@@ -193,13 +193,14 @@ constexpr int NN_TILE = 2048;
 
 __device__ __forceinline__ void nn_insert(float d, int k, float& b0, float& b1, float& b2, int& i0, int& i1,
                                           int& i2) {
-  if (d < b0) {
-    b2 = b1; i2 = i1; b1 = b0; i1 = i0; b0 = d; i0 = k;
-  } else if (d < b1) {
-    b2 = b1; i2 = i1; b1 = d; i1 = k;
-  } else if (d < b2) {
-    b2 = d; i2 = k;
-  }
+  // branch-free strict-'<' insertion into the sorted triple (selects only: no divergence)
+  const bool c0 = d < b0, c1 = d < b1, c2 = d < b2;
+  b2 = c1 ? b1 : (c2 ? d : b2);
+  i2 = c1 ? i1 : (c2 ? k : i2);
+  b1 = c0 ? b0 : (c1 ? d : b1);
+  i1 = c0 ? i0 : (c1 ? k : i1);
+  b0 = c0 ? d : b0;
+  i0 = c0 ? k : i0;
 }
 
 // One warp per unknown point; lanes stride the known points (ascending per lane, strict

@@ -1,0 +1,278 @@
+"""SA / FP / voting / size-adaptive vote-aggregation modules and the backbone built from
+the operator surface in ops.py (SURVEY.md section 3 call stacks 1-3, section 8(b)).
+
+Module signatures follow the PointNet++ / VoteNet lineage that BASELINE.json's
+north_star names (the mounted reference has no code to cite, README.md:1-2 only):
+
+    PointnetSAModuleVotes(npoint, radius, nsample, mlp, use_xyz=True, normalize_xyz=True)
+        forward(xyz (B,N,3), features (B,C,N), inds=None, radius_t=None)
+            -> new_xyz (B,npoint,3), new_features (B,C_out,npoint), inds (B,npoint)
+    PointnetFPModule(mlp)
+        forward(unknown (B,n,3), known (B,m,3), unknow_feats (B,C1,n), known_feats (B,C2,m))
+            -> (B,C_out,n)
+
+Two execution paths, same results within the bf16 tolerance:
+  * eval (inference, the timed path): BN folded into the 1x1 convs, the shared MLP runs
+    through sad_b200.mlp (hand-written tcgen05 kernels);
+  * train: plain torch Conv2d/BatchNorm2d/ReLU so autograd + DDP work; the point ops'
+    backward kernels (scatter-add) come from ops.py.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from . import mlp as _mlp
+from .config import LAYER_CFG, mlp_channels
+
+
+class SharedMLP(nn.Module):
+    """Stack of 1x1 Conv2d (+BatchNorm2d) + ReLU over (B,C,P,S) [LINEAGE pt_utils.SharedMLP]."""
+
+    def __init__(self, channels: Sequence[int], bn: bool = True, last_relu: bool = True):
+        super().__init__()
+        self.channels = list(channels)
+        self.last_relu = last_relu
+        self.convs = nn.ModuleList()
+        self.bns = nn.ModuleList()
+        for cin, cout in zip(channels[:-1], channels[1:]):
+            self.convs.append(nn.Conv2d(cin, cout, kernel_size=1, bias=not bn))
+            self.bns.append(nn.BatchNorm2d(cout) if bn else nn.Identity())
+        self._folded = None
+
+    def train(self, mode: bool = True):
+        self._folded = None
+        return super().train(mode)
+
+    @torch.no_grad()
+    def load_folded(self, layers):
+        """Install [(W (Cout,Cin), b (Cout,)), ...] (numpy or tensors) as conv weights with identity BN."""
+        for conv, bn, (W, b) in zip(self.convs, self.bns, layers):
+            W = torch.as_tensor(W, dtype=torch.float32)
+            b = torch.as_tensor(b, dtype=torch.float32)
+            conv.weight.copy_(W.view(*W.shape, 1, 1))
+            if isinstance(bn, nn.BatchNorm2d):
+                bn.running_mean.zero_()
+                bn.running_var.fill_(1.0)
+                bn.weight.fill_(float((1.0 + bn.eps) ** 0.5))
+                bn.bias.copy_(b)
+            else:
+                conv.bias.copy_(b)
+        self._folded = None
+
+    @torch.no_grad()
+    def folded(self) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+        """Eval-mode BN folded into (W, b) per layer (cached until train()/load_folded())."""
+        if self._folded is None:
+            out = []
+            for conv, bn in zip(self.convs, self.bns):
+                W = conv.weight.detach().flatten(1).float()
+                b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(W.shape[0], device=W.device)
+                if isinstance(bn, nn.BatchNorm2d):
+                    s = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+                    W = W * s[:, None]
+                    b = (b - bn.running_mean) * s + bn.bias.detach()
+                out.append((W.contiguous(), b.contiguous()))
+            self._folded = _mlp.prepare_layers(out)
+        return self._folded
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        n = len(self.convs)
+        for i, (conv, bn) in enumerate(zip(self.convs, self.bns)):
+            x = bn(conv(x))
+            if i < n - 1 or self.last_relu:
+                x = torch.relu(x)
+        return x
+
+
+def _gather_xyz(xyz: torch.Tensor, inds: torch.Tensor) -> torch.Tensor:
+    """new_xyz (B,npoint,3) = xyz[b, inds[b]] through gather_operation (lineage idiom)."""
+    flipped = xyz.transpose(1, 2).contiguous()
+    return ops.gather_operation(flipped, inds).transpose(1, 2).contiguous()
+
+
+def query_and_group(xyz, new_xyz, features, idx, radius, use_xyz=True, normalize_xyz=True):
+    """[LINEAGE QueryAndGroup] -> (B, 3+C, npoint, nsample); radius scalar or (B,npoint)."""
+    grouped_xyz = ops.grouping_operation(xyz.transpose(1, 2).contiguous(), idx)
+    grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
+    if normalize_xyz:
+        if torch.is_tensor(radius):
+            grouped_xyz = grouped_xyz / radius[:, None, :, None]
+        else:
+            grouped_xyz = grouped_xyz / float(radius)
+    if features is None:
+        return grouped_xyz
+    grouped = ops.grouping_operation(features, idx)
+    return torch.cat([grouped_xyz, grouped], dim=1) if use_xyz else grouped
+
+
+class PointnetSAModuleVotes(nn.Module):
+    """Set abstraction: FPS -> (adaptive) ball query -> group -> shared MLP -> max-pool."""
+
+    def __init__(self, npoint: int, radius: Optional[float], nsample: int, mlp: Sequence[int],
+                 use_xyz: bool = True, normalize_xyz: bool = True, bn: bool = True):
+        super().__init__()
+        self.npoint, self.radius, self.nsample = npoint, radius, nsample
+        self.use_xyz, self.normalize_xyz = use_xyz, normalize_xyz
+        ch = list(mlp)
+        if use_xyz:
+            ch[0] += 3
+        self.mlp_module = SharedMLP(ch, bn=bn)
+
+    def forward(self, xyz, features=None, inds=None, radius_t=None):
+        if inds is None:
+            inds = ops.furthest_point_sample(xyz, self.npoint)
+        new_xyz = _gather_xyz(xyz, inds)
+        if radius_t is not None:
+            idx = ops.ball_query_adaptive(radius_t, self.nsample, xyz, new_xyz)
+            rad = radius_t
+        else:
+            idx = ops.ball_query(self.radius, self.nsample, xyz, new_xyz)
+            rad = self.radius
+        if not self.training and not torch.is_grad_enabled():
+            new_features = _mlp.sa_group_mlp(xyz, new_xyz, features, idx, rad, self.mlp_module.folded(),
+                                             use_xyz=self.use_xyz, normalize_xyz=self.normalize_xyz)
+        else:
+            grouped = query_and_group(xyz, new_xyz, features, idx, rad, self.use_xyz, self.normalize_xyz)
+            new_features = self.mlp_module(grouped).max(dim=3)[0]
+        return new_xyz, new_features, inds
+
+
+class PointnetFPModule(nn.Module):
+    """Feature propagation: three_nn -> inverse-distance weights -> three_interpolate -> MLP."""
+
+    def __init__(self, mlp: Sequence[int], bn: bool = True):
+        super().__init__()
+        self.mlp = SharedMLP(list(mlp), bn=bn)
+
+    def forward(self, unknown, known, unknow_feats, known_feats):
+        if known is not None:
+            dist, idx = ops.three_nn(unknown, known)
+            dist_recip = 1.0 / (dist + 1e-8)
+            norm = (dist_recip[..., 0] + dist_recip[..., 1]) + dist_recip[..., 2]
+            weight = (dist_recip / norm.unsqueeze(-1)).contiguous()
+            interpolated = ops.three_interpolate(known_feats.contiguous(), idx, weight)
+        else:
+            interpolated = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
+        new_features = interpolated if unknow_feats is None else torch.cat([interpolated, unknow_feats], dim=1)
+        if not self.training and not torch.is_grad_enabled():
+            return _mlp.pointwise_mlp(new_features, self.mlp.folded(), last_relu=True)
+        return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
+
+
+class Pointnet2Backbone(nn.Module):
+    """4 SA + 2 FP backbone (SURVEY section 8 layer table) -> 1024 seeds x 256 features."""
+
+    def __init__(self, input_feature_dim: int = 1, bn: bool = True):
+        super().__init__()
+        ch = mlp_channels(input_feature_dim)
+        c = LAYER_CFG
+        self.sa1 = PointnetSAModuleVotes(*c["sa1"], mlp=[input_feature_dim] + ch["sa1"][1:], bn=bn)
+        self.sa2 = PointnetSAModuleVotes(*c["sa2"], mlp=[128] + ch["sa2"][1:], bn=bn)
+        self.sa3 = PointnetSAModuleVotes(*c["sa3"], mlp=[256] + ch["sa3"][1:], bn=bn)
+        self.sa4 = PointnetSAModuleVotes(*c["sa4"], mlp=[256] + ch["sa4"][1:], bn=bn)
+        self.fp1 = PointnetFPModule(ch["fp1"], bn=bn)
+        self.fp2 = PointnetFPModule(ch["fp2"], bn=bn)
+
+    def forward(self, xyz, features):
+        end = {}
+        x, f = xyz, features
+        for name in ("sa1", "sa2", "sa3", "sa4"):
+            x, f, inds = getattr(self, name)(x, f)
+            end[name + "_xyz"], end[name + "_features"], end[name + "_inds"] = x, f, inds
+        f = self.fp1(end["sa3_xyz"], end["sa4_xyz"], end["sa3_features"], end["sa4_features"])
+        f = self.fp2(end["sa2_xyz"], end["sa3_xyz"], end["sa2_features"], f)
+        end["fp2_features"] = f
+        end["fp2_xyz"] = end["sa2_xyz"]
+        end["fp2_inds"] = end["sa1_inds"][:, : end["sa2_xyz"].shape[1]]
+        return end
+
+
+class VotingModule(nn.Module):
+    """Seed -> vote glue [LINEAGE]: 3-layer 1x1 MLP, last layer linear; vote = seed + offset."""
+
+    def __init__(self, seed_feature_dim: int = 256, bn: bool = True):
+        super().__init__()
+        c = seed_feature_dim
+        self.mlp = SharedMLP([c, c, c, 3 + c], bn=bn, last_relu=False)
+        self.mlp.bns[-1] = nn.Identity()          # last conv is a plain linear layer with bias
+        self.mlp.convs[-1] = nn.Conv2d(c, 3 + c, kernel_size=1, bias=True)
+
+    def forward(self, seed_xyz, seed_features):
+        if not self.training and not torch.is_grad_enabled():
+            y = _mlp.pointwise_mlp(seed_features, self.mlp.folded(), last_relu=False)
+        else:
+            y = self.mlp(seed_features.unsqueeze(-1)).squeeze(-1)
+        vote_xyz = (seed_xyz + y[:, :3, :].transpose(1, 2)).contiguous()
+        vote_features = (seed_features + y[:, 3:, :]).contiguous()
+        return vote_xyz, vote_features
+
+
+class SizeAdaptiveAggregation(nn.Module):
+    """3DSAD vote aggregation (a7): FPS over votes -> cluster centres -> per-cluster radius from
+    the predicted object size -> adaptive ball query -> group -> MLP + max-pool."""
+
+    def __init__(self, npoint: int = 256, nsample: int = 16, seed_feature_dim: int = 256,
+                 mlp: Sequence[int] = (128, 128, 128), alpha: float = 1.0, r_min: float = 0.1,
+                 r_max: float = 1.2, bn: bool = True):
+        super().__init__()
+        self.alpha, self.r_min, self.r_max = alpha, r_min, r_max
+        self.sa = PointnetSAModuleVotes(npoint, None, nsample, [seed_feature_dim] + list(mlp), bn=bn)
+
+    def forward(self, vote_xyz, vote_features, size):
+        radius_t = ops.size_to_radius(size, self.alpha, self.r_min, self.r_max)
+        cxyz, cfeat, cinds = self.sa(vote_xyz, vote_features, radius_t=radius_t)
+        return cxyz, cfeat, cinds, radius_t
+
+
+class SADHotPath(nn.Module):
+    """The timed unit 'scene' (SURVEY call stack 3): backbone -> voting -> size-adaptive
+    vote aggregation.  `size` (B,256,3) is the predicted box size per cluster."""
+
+    def __init__(self, input_feature_dim: int = 1, bn: bool = True):
+        super().__init__()
+        self.backbone = Pointnet2Backbone(input_feature_dim, bn=bn)
+        self.vgen = VotingModule(256, bn=bn)
+        c = LAYER_CFG
+        self.agg = SizeAdaptiveAggregation(c["agg"][0], c["agg"][2], 256, alpha=c["alpha"],
+                                           r_min=c["r_min"], r_max=c["r_max"], bn=bn)
+
+    @torch.no_grad()
+    def load_params(self, params):
+        """params: dict from config.make_params (BN folded)."""
+        bb = self.backbone
+        for name in ("sa1", "sa2", "sa3", "sa4"):
+            getattr(bb, name).mlp_module.load_folded(params[name])
+        bb.fp1.mlp.load_folded(params["fp1"])
+        bb.fp2.mlp.load_folded(params["fp2"])
+        self.vgen.mlp.load_folded(params["vote"])
+        self.agg.sa.mlp_module.load_folded(params["agg"])
+        return self
+
+    def forward(self, xyz, features, size):
+        end = self.backbone(xyz, features)
+        vxyz, vfeat = self.vgen(end["fp2_xyz"], end["fp2_features"])
+        cxyz, cfeat, cinds, radius_t = self.agg(vxyz, vfeat, size)
+        end.update(vote_xyz=vxyz, vote_features=vfeat, cluster_xyz=cxyz, cluster_features=cfeat,
+                   cluster_inds=cinds, cluster_radius=radius_t)
+        return end
+
+    @torch.no_grad()
+    def forward_host(self, xyz_host, feat_host, size_host, out_host=None):
+        """End-to-end call with HOST (pinned) buffers: H2D copies, forward, D2H of the cluster
+        features / centres.  Returns (cluster_xyz_host, cluster_features_host)."""
+        dev = next(self.parameters()).device
+        xyz = xyz_host.to(dev, non_blocking=True)
+        feat = feat_host.to(dev, non_blocking=True)
+        size = size_host.to(dev, non_blocking=True)
+        end = self.forward(xyz, feat, size)
+        if out_host is None:
+            out_host = (torch.empty(end["cluster_xyz"].shape, dtype=torch.float32, pin_memory=True),
+                        torch.empty(end["cluster_features"].shape, dtype=torch.float32, pin_memory=True))
+        out_host[0].copy_(end["cluster_xyz"], non_blocking=True)
+        out_host[1].copy_(end["cluster_features"], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out_host

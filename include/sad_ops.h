@@ -99,6 +99,9 @@ SAD_API int sad_three_interpolate_bwd(int B, int C, int n, int m, const float* g
                               const int32_t* idx, const float* weight, float* grad_features,
                               sad_stream_t stream);
 
+/* Number of kernels this library has launched in this process (all threads, monotonic). */
+SAD_API unsigned long long sad_launch_count(void);
+
 /* Test / benchmark hook: force the FPS thread-block-cluster size for subsequent calls on
  * this thread (1,2,4,8,16; 0 = built-in heuristic).  Results never depend on it. */
 SAD_API void sad_fps_force_cluster_size(int cluster_size);

@@ -17,6 +17,8 @@ which is what makes this file the spec.
 """
 from __future__ import annotations
 
+import sys
+
 import numpy as np
 
 __all__ = [
@@ -254,7 +256,13 @@ def shared_mlp(x, layers, pool=True, last_relu=True, emulate_bf16=False):
 
 
 # ---------------------------------------------------------------- modules (a7)
-def query_and_group(xyz, new_xyz, features, idx, radius, use_xyz=True, normalize_xyz=True):
+def _impl(impl):
+    """Op provider for the module-level compositions: this file (NumPy) by default, or
+    oracle.c_port (same results bit for bit, multi-threaded) for full-size / timed runs."""
+    return impl if impl is not None else sys.modules[__name__]
+
+
+def query_and_group(xyz, new_xyz, features, idx, radius, use_xyz=True, normalize_xyz=True, impl=None):
     """QueryAndGroup [LINEAGE]: grouped_xyz = xyz[idx] - new_xyz (/ radius if
     normalising; radius scalar or (B,npoint)); concat with grouped features on the
     channel axis -> (B, 3+C, npoint, nsample)."""
@@ -272,36 +280,38 @@ def query_and_group(xyz, new_xyz, features, idx, radius, use_xyz=True, normalize
     g = np.ascontiguousarray(g.transpose(0, 3, 1, 2)).astype(np.float32)
     if features is None:
         return g
-    gf = grouping_operation(_f32c(features), idx)
+    gf = _impl(impl).grouping_operation(_f32c(features), idx)
     return np.concatenate([g, gf], axis=1) if use_xyz else gf
 
 
 def sa_module(xyz, features, npoint, radius, nsample, layers, use_xyz=True,
-              normalize_xyz=True, radius_t=None, inds=None, emulate_bf16=False):
+              normalize_xyz=True, radius_t=None, inds=None, emulate_bf16=False, impl=None):
     """Set-abstraction module (SURVEY section 3 call stack 1).  radius_t (B,npoint)
     switches to the adaptive ball query and per-cluster normalisation.
     -> (new_xyz (B,npoint,3), new_features (B,Cout,npoint), inds (B,npoint))."""
     xyz = _f32c(xyz)
     B = xyz.shape[0]
+    I = _impl(impl)
     if inds is None:
-        inds = furthest_point_sample(xyz, npoint)
+        inds = I.furthest_point_sample(xyz, npoint)
     new_xyz = np.stack([xyz[b][inds[b]] for b in range(B)], axis=0)
     if radius_t is not None:
-        idx = ball_query_adaptive(radius_t, nsample, xyz, new_xyz)
+        idx = I.ball_query_adaptive(radius_t, nsample, xyz, new_xyz)
         rr = _f32c(radius_t)
     else:
-        idx = ball_query(radius, nsample, xyz, new_xyz)
+        idx = I.ball_query(radius, nsample, xyz, new_xyz)
         rr = F32(radius)
-    x = query_and_group(xyz, new_xyz, features, idx, rr, use_xyz, normalize_xyz)
+    x = query_and_group(xyz, new_xyz, features, idx, rr, use_xyz, normalize_xyz, impl=impl)
     out = shared_mlp(x, layers, pool=True, emulate_bf16=emulate_bf16)
     return new_xyz, out, inds
 
 
-def fp_module(unknown, known, unknown_feats, known_feats, layers, emulate_bf16=False):
+def fp_module(unknown, known, unknown_feats, known_feats, layers, emulate_bf16=False, impl=None):
     """Feature-propagation module (call stack 2) -> (B,Cout,n)."""
-    dist, idx = three_nn(unknown, known)
+    I = _impl(impl)
+    dist, idx = I.three_nn(unknown, known)
     w = interpolation_weights(dist)
-    interp = three_interpolate(known_feats, idx, w)
+    interp = I.three_interpolate(known_feats, idx, w)
     x = interp if unknown_feats is None else np.concatenate([interp, _f32c(unknown_feats)], axis=1)
     y = shared_mlp(x[..., None], layers, pool=False, emulate_bf16=emulate_bf16)
     return y[..., 0]
@@ -319,41 +329,42 @@ def voting_module(seed_xyz, seed_features, layers, emulate_bf16=False):
 
 
 def vote_aggregation(vote_xyz, vote_features, size, npoint, nsample, layers,
-                     alpha=1.0, r_min=0.1, r_max=1.2, emulate_bf16=False):
+                     alpha=1.0, r_min=0.1, r_max=1.2, emulate_bf16=False, impl=None):
     """a7: FPS over votes -> cluster centres -> per-cluster radius from predicted size
     (B,npoint,3) -> adaptive ball query -> group -> MLP + max-pool."""
     radius_t = size_to_radius(size, alpha, r_min, r_max)
     return sa_module(vote_xyz, vote_features, npoint, None, nsample, layers,
-                     radius_t=radius_t, emulate_bf16=emulate_bf16) + (radius_t,)
+                     radius_t=radius_t, emulate_bf16=emulate_bf16, impl=impl) + (radius_t,)
 
 
-def backbone_forward(xyz, features, params, cfg, emulate_bf16=False):
+def backbone_forward(xyz, features, params, cfg, emulate_bf16=False, impl=None):
     """4 SA + 2 FP backbone (call stack 3, SURVEY section 8 layer table).
     params: dict name -> layers; cfg: dict name -> (npoint, radius, nsample)."""
     end = {}
     x, f = _f32c(xyz), features
     for name in ("sa1", "sa2", "sa3", "sa4"):
         npoint, radius, nsample = cfg[name]
-        x, f, inds = sa_module(x, f, npoint, radius, nsample, params[name], emulate_bf16=emulate_bf16)
+        x, f, inds = sa_module(x, f, npoint, radius, nsample, params[name], emulate_bf16=emulate_bf16,
+                               impl=impl)
         end[name + "_xyz"], end[name + "_features"], end[name + "_inds"] = x, f, inds
     f = fp_module(end["sa3_xyz"], end["sa4_xyz"], end["sa3_features"], end["sa4_features"],
-                  params["fp1"], emulate_bf16)
-    f = fp_module(end["sa2_xyz"], end["sa3_xyz"], end["sa2_features"], f, params["fp2"], emulate_bf16)
+                  params["fp1"], emulate_bf16, impl)
+    f = fp_module(end["sa2_xyz"], end["sa3_xyz"], end["sa2_features"], f, params["fp2"], emulate_bf16, impl)
     end["fp2_features"] = f
     end["fp2_xyz"] = end["sa2_xyz"]
     end["fp2_inds"] = end["sa1_inds"][:, : end["sa2_xyz"].shape[1]]
     return end
 
 
-def detector_hot_path(xyz, features, size, params, cfg, emulate_bf16=False):
+def detector_hot_path(xyz, features, size, params, cfg, emulate_bf16=False, impl=None):
     """The timed unit 'scene': backbone -> voting -> size-adaptive vote aggregation."""
-    end = backbone_forward(xyz, features, params, cfg, emulate_bf16)
+    end = backbone_forward(xyz, features, params, cfg, emulate_bf16, impl)
     vxyz, vfeat = voting_module(end["fp2_xyz"], end["fp2_features"], params["vote"], emulate_bf16)
     npoint, _, nsample = cfg["agg"]
     cxyz, cfeat, cinds, radius_t = vote_aggregation(
         vxyz, vfeat, size, npoint, nsample, params["agg"],
         alpha=cfg.get("alpha", 1.0), r_min=cfg.get("r_min", 0.1), r_max=cfg.get("r_max", 1.2),
-        emulate_bf16=emulate_bf16)
+        emulate_bf16=emulate_bf16, impl=impl)
     end.update(vote_xyz=vxyz, vote_features=vfeat, cluster_xyz=cxyz, cluster_features=cfeat,
                cluster_inds=cinds, cluster_radius=radius_t)
     return end
