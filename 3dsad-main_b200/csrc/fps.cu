@@ -119,7 +119,8 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict
       __syncthreads();
     } else {
       if (lane < CS) st_async_v4(r_rec[buf], __uint_as_float(wmax), c.x, c.y, c.z, r_bar[buf]);
-      mbar_wait(&s_bar[buf], (uint32_t)((j >> 1) & 1));
+      // use u of s_bar[buf] is iteration j = 2u + 1 (buf 1) or 2u + 2 (buf 0): u = (j-1)/2
+      mbar_wait(&s_bar[buf], (uint32_t)(((j - 1) >> 1) & 1));
     }
 
     // ---- every warp reduces the NSLOT records: max dist, ties -> lowest slot (== lowest index)

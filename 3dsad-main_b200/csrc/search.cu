@@ -19,6 +19,8 @@ constexpr int BQ_TILE = 2048;        // candidates per stage (24 KB)
 constexpr int BQ_STAGES = 2;
 
 // Cooperative tile load: bulk-TMA for the 16-byte-aligned body, plain loads for the tail.
+// The tile is padded to a multiple of 32 points with +inf coordinates (d2 = +inf is never
+// < r*r), so the scan loop needs no per-lane bounds check.
 __device__ __forceinline__ void load_tile(float* dst, const float* src, int npts, bool bulk_ok,
                                           uint64_t* bar, int tid, int nthreads) {
   const uint32_t bytes = (uint32_t)npts * 12u;
@@ -33,6 +35,9 @@ __device__ __forceinline__ void load_tile(float* dst, const float* src, int npts
   } else {
     for (int i = tid; i < npts * 3; i += nthreads) dst[i] = __ldg(src + i);
   }
+  const int pad_end = ((npts + 31) & ~31) * 3;
+  const int i = npts * 3 + tid - 64;
+  if (tid >= 64 && i < pad_end) dst[i] = __int_as_float(0x7f800000);
 }
 
 template <int QPW>
@@ -67,8 +72,8 @@ ball_query_kernel(int N, int npoint, float radius, const float* __restrict__ rad
       out[q] = idx + ((size_t)b * npoint + j) * nsample;
     } else {
       qx[q] = qy[q] = qz[q] = 0.f;
-      r2[q] = 0.f;
-      cnt[q] = nsample;     // inactive query: already "full"
+      r2[q] = -1.f;         // inactive query: nothing is ever < -1
+      cnt[q] = nsample;     // ... and it counts as already "full"
       out[q] = nullptr;
     }
   }
@@ -93,36 +98,41 @@ ball_query_kernel(int N, int npoint, float radius, const float* __restrict__ rad
   for (; t < ntiles; ++t) {
     const int stage = t % BQ_STAGES;
     const uint32_t parity = (uint32_t)((t / BQ_STAGES) & 1);
-    const float* tile = s_tile + stage * BQ_TILE * 3;
-    const int npts = min(BQ_TILE, N - t * BQ_TILE);
+    const float* tp = s_tile + stage * BQ_TILE * 3 + lane * 3;
+    const int nchunks = (min(BQ_TILE, N - t * BQ_TILE) + 31) >> 5;
     bool warp_done = true;
 #pragma unroll
     for (int q = 0; q < QPW; ++q) warp_done = warp_done && (cnt[q] >= nsample);
 
     if (bulk_ok) mbar_wait(&s_full[stage], parity);
     if (!warp_done) {
-      for (int base = 0; base < npts; base += 32) {
-        const int c = base + lane;
-        const bool valid = c < npts;
-        const int cc = valid ? c : 0;
-        const float x = tile[3 * cc], y = tile[3 * cc + 1], z = tile[3 * cc + 2];
-        bool all_full = true;
+      int cbase = t * BQ_TILE + lane;        // candidate index of this lane in the current chunk
+      for (int ch = 0; ch < nchunks; ++ch, tp += 96, cbase += 32) {
+        const float x = tp[0], y = tp[1], z = tp[2];
+        bool hit[QPW];
+        bool anyhit = false;
 #pragma unroll
         for (int q = 0; q < QPW; ++q) {
-          const float d2 = sqdist(x, y, z, qx[q], qy[q], qz[q]);
-          const bool hit = valid && (d2 < r2[q]) && (cnt[q] < nsample);
-          const uint32_t m = __ballot_sync(FULL, hit);
-          if (m) {
-            const int pos = cnt[q] + __popc(m & lt_mask);
-            if (hit && pos < nsample) out[q][pos] = t * BQ_TILE + c;
-            if (cnt[q] == 0) first[q] = t * BQ_TILE + base + __ffs(m) - 1;
-            cnt[q] += __popc(m);
-          }
-          all_full = all_full && (cnt[q] >= nsample);
+          hit[q] = sqdist(x, y, z, qx[q], qy[q], qz[q]) < r2[q];
+          anyhit = anyhit || hit[q];
         }
-        if (all_full) {
-          warp_done = true;
-          break;
+        if (__any_sync(FULL, anyhit)) {      // rare path: ordered compaction with ballot + popc
+          bool all_full = true;
+#pragma unroll
+          for (int q = 0; q < QPW; ++q) {
+            const uint32_t m = __ballot_sync(FULL, hit[q]);
+            if (m != 0u && cnt[q] < nsample) {
+              const int pos = cnt[q] + __popc(m & lt_mask);
+              if (hit[q] && pos < nsample) out[q][pos] = cbase;
+              if (cnt[q] == 0) first[q] = cbase - lane + __ffs(m) - 1;
+              cnt[q] += __popc(m);
+            }
+            all_full = all_full && (cnt[q] >= nsample);
+          }
+          if (all_full) {
+            warp_done = true;
+            break;
+          }
         }
       }
     }
@@ -162,7 +172,8 @@ int launch_ball_query(int B, int N, int npoint, float radius, const float* radiu
   const size_t smem = (size_t)BQ_STAGES * BQ_TILE * 3 * sizeof(float);
   const long long total_q = (long long)B * npoint;
   const int wpb = BQ_T / 32;
-  int qpw = 4;
+  int qpw = 8;
+  if (total_q / (wpb * 8) < 296) qpw = 4;
   if (total_q / (wpb * 4) < 296) qpw = 2;
   if (total_q / (wpb * 2) < 296) qpw = 1;
 #define SAD_BQ_LAUNCH(Q)                                                                            \
@@ -179,7 +190,8 @@ int launch_ball_query(int B, int N, int npoint, float radius, const float* radiu
     ball_query_kernel<Q><<<grid, BQ_T, smem, stream>>>(N, npoint, radius, radius_t, nsample, xyz,   \
                                                        new_xyz, idx);                               \
   }
-  if (qpw == 4) SAD_BQ_LAUNCH(4)
+  if (qpw == 8) SAD_BQ_LAUNCH(8)
+  else if (qpw == 4) SAD_BQ_LAUNCH(4)
   else if (qpw == 2) SAD_BQ_LAUNCH(2)
   else SAD_BQ_LAUNCH(1)
 #undef SAD_BQ_LAUNCH

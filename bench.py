@@ -111,46 +111,53 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Samples SM clock + throttle reasons through NVML every ~5 ms on a side thread
+    (the recipe's nvidia-smi line, without its start-up latency)."""
 
     def __init__(self, index):
-        self.rows, self.proc, self.th = [], None, None
+        self.rows, self.ok, self._stop = [], False, False
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.rows.append((time.perf_counter(), ln.strip()))
+    def _poll(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.rows.append((time.perf_counter(), sm, rs))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.004)
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for (t, ln) in self.rows:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                smax = float(f[1])
-                if t0 - 0.05 <= t <= t1 + 0.05:
-                    sm.append(float(f[0]))
-                    for nm, v in zip(names, f[3:7]):
-                        if v.lower().startswith("active"):
-                            reasons.add(nm)
-            except ValueError:
-                continue
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self._stop = True
+        self.th.join(timeout=1.0)
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        sm, reasons = [], set()
+        for (t, c, rs) in self.rows:
+            if t0 <= t <= t1:
+                sm.append(c)
+                for name, bit in bits.items():
+                    if rs & bit:
+                        reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(reasons),
                 "samples": len(sm)}
 
 
