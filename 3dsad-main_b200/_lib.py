@@ -30,9 +30,15 @@ SIGNATURES = {
     "sad_three_nn_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_three_interpolate_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_three_interpolate_bwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
+    "sad_mlp_weight_image_bytes": [_c_int, _c_int, _c_int],
+    "sad_mlp_pack_weights": [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp],
+    "sad_shared_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _c_float, _vp,
+                           _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _vp],
+    "sad_three_interpolate_cl_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
+    "sad_cf_to_cl_bf16": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
 }
 _RESTYPES = {"sad_last_error_string": ctypes.c_char_p, "sad_fps_force_cluster_size": None,
-             "sad_launch_count": ctypes.c_ulonglong}
+             "sad_launch_count": ctypes.c_ulonglong, "sad_mlp_weight_image_bytes": ctypes.c_longlong}
 
 _lib = None
 _lock = threading.Lock()
@@ -87,7 +93,7 @@ class CallProfiler:
         import torch
         lib = load()
         for name in SIGNATURES:
-            if not (name.endswith("_fwd") or name.endswith("_bwd")):
+            if not (name.endswith("_fwd") or name.endswith("_bwd") or name == "sad_cf_to_cl_bf16"):
                 continue
             fn = getattr(lib, name)
             self._saved[name] = fn

@@ -1,51 +1,257 @@
 """Shared point-wise MLP (+ max-pool) host side -- SURVEY.md section 8(a) row a6.
 
-INTERIM (round-1 bring-up): the contraction below still runs through torch.matmul in
-bf16 (cuBLAS) on top of this repo's own grouping kernels; the hand-written tcgen05
-kernel (csrc/mlp.cu) replaces `_chain` once it is parity-green.  Storage precision is
-already the final one: bf16 inputs / weights / inter-layer activations, fp32 accumulate,
-fp32 bias + ReLU, fp32 output (tolerance 2e-2 vs the fp32 oracle, BASELINE north_star)."""
+Inference path: ONE launch of the hand-written tcgen05 kernel (csrc/mlp.cu) per SA / FP /
+voting stage: neighbourhood gather -> 2-3 layer MLP on the tensor cores -> max-pool, with
+the grouped tensor never materialised.  Features travel between stages channel-last in
+bf16 ("cl"); the public, lineage-shaped (B,C,N) fp32 tensors ("cf") are still produced for
+the caller, and carry their cl twin in the `_sad_cl` attribute so the next stage can skip
+the layout bridge.  Storage precision: bf16 operands, fp32 accumulate / bias / ReLU / max
+(2e-2 vs the fp32 oracle, BASELINE north_star).
+
+Shapes the kernel does not cover (hidden widths not a multiple of 64 or > 256, more than 3
+layers, nsample not a power of two) take `composed_*`: the same math composed from this
+repo's grouping kernels and torch matmuls -- still GPU-only, used by odd-shaped user
+modules and by the training path, never by the benchmarked detector configuration.
+"""
 from __future__ import annotations
 
-from typing import List, Tuple
+import ctypes
+from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
+
+_VP = ctypes.c_void_p
 
 
-class PreparedLayer:
-    __slots__ = ("W", "b", "W_bf16", "cin", "cout")
-
-    def __init__(self, W: torch.Tensor, b: torch.Tensor):
-        self.W = W.contiguous()
-        self.b = b.contiguous()
-        self.W_bf16 = W.to(torch.bfloat16).contiguous()
-        self.cout, self.cin = W.shape
+def _ptr(t: Optional[torch.Tensor]):
+    return _VP(t.data_ptr()) if t is not None else _VP(0)
 
 
-def prepare_layers(layers: List[Tuple[torch.Tensor, torch.Tensor]]) -> List[PreparedLayer]:
-    return [PreparedLayer(W, b) for (W, b) in layers]
+def _stream(t: torch.Tensor):
+    return _VP(torch.cuda.current_stream(t.device).cuda_stream)
 
 
-def _chain(rows: torch.Tensor, layers: List[PreparedLayer], last_relu: bool) -> torch.Tensor:
-    """rows (R,Cin) -> (R,Cout) fp32; bf16 storage between layers, fp32 accumulate."""
+def _round64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+class Layout:
+    """Where the columns of the first layer's weight matrix come from (K order of the kernel):
+    [feat_cl (c0) | feat2_cl (c1) | special chunk: xyz(3), extras (e)]."""
+
+    def __init__(self, c0=0, c0_cols=(), c1=0, c1_cols=(), xyz_cols=None, extra_cols=()):
+        self.c0, self.c1 = c0, c1                       # padded widths (multiples of 64)
+        self.c0_cols, self.c1_cols = list(c0_cols), list(c1_cols)
+        self.xyz_cols = list(xyz_cols) if xyz_cols is not None else None
+        self.extra_cols = list(extra_cols)
+
+    @property
+    def has_special(self):
+        return self.xyz_cols is not None or len(self.extra_cols) > 0
+
+    def perm(self):
+        p = np.full(self.c0 + self.c1 + (64 if self.has_special else 0), -1, dtype=np.int32)
+        p[: len(self.c0_cols)] = self.c0_cols
+        p[self.c0: self.c0 + len(self.c1_cols)] = self.c1_cols
+        if self.has_special:
+            s = self.c0 + self.c1
+            if self.xyz_cols is not None:
+                p[s: s + 3] = self.xyz_cols
+            p[s + 3: s + 3 + len(self.extra_cols)] = self.extra_cols
+        return p
+
+    def key(self):
+        return (self.c0, tuple(self.c0_cols), self.c1, tuple(self.c1_cols),
+                tuple(self.xyz_cols) if self.xyz_cols is not None else None, tuple(self.extra_cols))
+
+
+def sa_layout(c_feat: int, use_xyz: bool) -> Layout:
+    """SA stage: original columns are [xyz(3) if use_xyz, features(c_feat)]."""
+    off = 3 if use_xyz else 0
+    xyz = [0, 1, 2] if use_xyz else None
+    if 0 < c_feat <= 13:
+        return Layout(xyz_cols=xyz, extra_cols=range(off, off + c_feat))
+    return Layout(c0=_round64(c_feat), c0_cols=range(off, off + c_feat), xyz_cols=xyz)
+
+
+def fp_layout(c_interp: int, c_skip: int) -> Layout:
+    return Layout(c0=_round64(c_interp), c0_cols=range(c_interp),
+                  c1=_round64(c_skip), c1_cols=range(c_interp, c_interp + c_skip))
+
+
+class PreparedMLP:
+    """BN-folded layers [(W (Cout,Cin) f32, b (Cout,) f32), ...] plus, lazily per layout, the
+    packed bf16 weight images the tcgen05 kernel streams."""
+
+    def __init__(self, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]]):
+        self.layers = [(W.contiguous(), b.contiguous()) for (W, b) in layers]
+        self.c_out = [int(W.shape[0]) for (W, _) in self.layers]
+        self.c_in = int(self.layers[0][0].shape[1])
+        self.W_bf16 = [W.to(torch.bfloat16) for (W, _) in self.layers]
+        self._packed = {}
+
+    def __len__(self):
+        return len(self.layers)
+
+    def __iter__(self):
+        return iter(self.layers)
+
+    def fusable(self, S: int) -> bool:
+        n = len(self.layers)
+        hidden_ok = all(c % 64 == 0 and c <= 256 for c in self.c_out[:-1])
+        return 2 <= n <= 3 and hidden_ok and S in (1, 2, 4, 8, 16, 32, 64, 128)
+
+    def packed(self, layout: Layout):
+        key = layout.key()
+        if key not in self._packed:
+            lib = _lib.load()
+            dev = self.layers[0][0].device
+            imgs, biases = [], []
+            n = len(self.layers)
+            for li, (W, b) in enumerate(self.layers):
+                Wn = np.ascontiguousarray(W.detach().cpu().numpy(), dtype=np.float32)
+                cout, cin = Wn.shape
+                perm = layout.perm() if li == 0 else np.arange(_round64(cin), dtype=np.int32)
+                if li > 0:
+                    perm[cin:] = -1
+                kpad = int(perm.shape[0])
+                is_last = int(li == n - 1)
+                nbytes = lib.sad_mlp_weight_image_bytes(cout, kpad, is_last)
+                if nbytes <= 0:
+                    raise RuntimeError("sad_mlp_weight_image_bytes rejected the layer shape")
+                img = np.zeros(nbytes, dtype=np.uint8)
+                _lib.check(lib.sad_mlp_pack_weights(_VP(Wn.ctypes.data), cout, cin, _VP(perm.ctypes.data), kpad,
+                                                    is_last, _VP(img.ctypes.data)), "mlp_pack_weights")
+                imgs.append(torch.from_numpy(img).to(dev))
+                biases.append(b.detach().float().contiguous().to(dev))
+            self._packed[key] = (imgs, biases,
+                                 (_VP * n)(*[t.data_ptr() for t in imgs]),
+                                 (_VP * n)(*[t.data_ptr() for t in biases]),
+                                 (ctypes.c_int * n)(*self.c_out))
+        return self._packed[key]
+
+
+def prepare_layers(layers) -> PreparedMLP:
+    return PreparedMLP(layers)
+
+
+# ----------------------------------------------------------------------------- layout bridge
+def to_cl_bf16(features_cf: torch.Tensor, pad_to: Optional[int] = None) -> torch.Tensor:
+    """(B,C,N) f32 -> (B,N,Cpad) bf16 channel-last; reuses the `_sad_cl` twin when present."""
+    B, C, N = features_cf.shape
+    cpad = pad_to or C
+    twin = getattr(features_cf, "_sad_cl", None)
+    if twin is not None and tuple(twin.shape) == (B, N, cpad):
+        return twin
+    x = features_cf.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    if cpad == C:
+        out = torch.empty((B, N, C), dtype=torch.bfloat16, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sad_cf_to_cl_bf16(B, C, N, _ptr(x), _ptr(out), _stream(x)), "cf_to_cl_bf16")
+        return out
+    out = torch.zeros((B, N, cpad), dtype=torch.bfloat16, device=x.device)
+    out[:, :, :C] = to_cl_bf16(x)
+    return out
+
+
+def _attach(cf: Optional[torch.Tensor], cl: Optional[torch.Tensor]):
+    if cf is not None and cl is not None:
+        cf._sad_cl = cl
+    return cf
+
+
+def fused_mlp(mlp: PreparedMLP, layout: Layout, B, N, P, S, feat_cl=None, feat2_cl=None, xyz=None, new_xyz=None,
+              idx=None, radius=0.0, radius_t=None, normalize_xyz=False, extra=None, last_relu=True,
+              want_cf=True, want_cl=True):
+    """Raw launcher of sad_shared_mlp_fwd -> (out_cf (B,Clast,P) f32 | None, out_cl (B,P,Clast) bf16 | None)."""
+    imgs, biases, w_ptrs, b_ptrs, c_arr = mlp.packed(layout)
+    dev = imgs[0].device
+    c_last = mlp.c_out[-1]
+    out_cf = torch.empty((B, c_last, P), dtype=torch.float32, device=dev) if want_cf else None
+    out_cl = torch.empty((B, P, c_last), dtype=torch.bfloat16, device=dev) if want_cl else None
+    E = len(layout.extra_cols)
+    with torch.cuda.device(dev):
+        rc = _lib.load().sad_shared_mlp_fwd(
+            B, N, P, S, _ptr(feat_cl), layout.c0, _ptr(feat2_cl), layout.c1, _ptr(xyz), _ptr(new_xyz), _ptr(idx),
+            float(radius), _ptr(radius_t), int(bool(normalize_xyz)), _ptr(extra), E, len(mlp), w_ptrs, b_ptrs, c_arr,
+            int(bool(last_relu)), _ptr(out_cl), _ptr(out_cf), _VP(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "shared_mlp")
+    return out_cf, out_cl
+
+
+# ----------------------------------------------------------------------------- stage entry points
+def sa_group_mlp(xyz, new_xyz, features, idx, radius, mlp: PreparedMLP, use_xyz=True, normalize_xyz=True):
+    """Group (relative, optionally radius-normalised xyz ++ features) -> MLP -> max over nsample.
+    xyz (B,N,3), new_xyz (B,P,3), features (B,C,N) f32 | None, idx (B,P,S) i32 -> (B,Cout,P) f32."""
+    B, P, S = idx.shape
+    N = xyz.shape[1]
+    c_feat = 0 if features is None else features.shape[1]
+    if not mlp.fusable(S) or (c_feat == 0 and not use_xyz):
+        return composed_sa(xyz, new_xyz, features, idx, radius, mlp, use_xyz, normalize_xyz)
+    layout = sa_layout(c_feat, use_xyz or c_feat == 0)
+    feat_cl, extra = None, None
+    if layout.c0:
+        feat_cl = to_cl_bf16(features, pad_to=layout.c0)
+    elif c_feat:
+        extra = features.contiguous() if c_feat == 1 else features.transpose(1, 2).contiguous()
+    radius_t = radius if torch.is_tensor(radius) else None
+    out_cf, out_cl = fused_mlp(mlp, layout, B, N, P, S, feat_cl=feat_cl, xyz=xyz if layout.xyz_cols else None,
+                               new_xyz=new_xyz, idx=idx, radius=0.0 if radius_t is not None else float(radius),
+                               radius_t=radius_t, normalize_xyz=normalize_xyz, extra=extra)
+    return _attach(out_cf, out_cl)
+
+
+def fp_interp_mlp(known_feats, unknow_feats, idx, weight, mlp: PreparedMLP):
+    """three_interpolate -> concat skip -> MLP.  known_feats (B,C2,m), unknow_feats (B,C1,n) | None,
+    idx/weight (B,n,3) -> (B,Cout,n) f32."""
+    B, C2, m = known_feats.shape
+    n = idx.shape[1]
+    c_skip = 0 if unknow_feats is None else unknow_feats.shape[1]
+    if not mlp.fusable(1):
+        interp = ops.three_interpolate(known_feats.contiguous(), idx, weight)
+        x = interp if unknow_feats is None else torch.cat([interp, unknow_feats], dim=1)
+        return composed_pointwise(x, mlp, last_relu=True)
+    layout = fp_layout(C2, c_skip)
+    known_cl = to_cl_bf16(known_feats, pad_to=layout.c0)
+    interp_cl = torch.empty((B, n, layout.c0), dtype=torch.bfloat16, device=known_cl.device)
+    with torch.cuda.device(known_cl.device):
+        _lib.check(_lib.load().sad_three_interpolate_cl_fwd(B, layout.c0, m, n, _ptr(known_cl), _ptr(idx), _ptr(weight),
+                                                            _ptr(interp_cl), _stream(known_cl)), "three_interpolate_cl")
+    skip_cl = to_cl_bf16(unknow_feats, pad_to=layout.c1) if c_skip else None
+    out_cf, out_cl = fused_mlp(mlp, layout, B, n, n, 1, feat_cl=interp_cl, feat2_cl=skip_cl)
+    return _attach(out_cf, out_cl)
+
+
+def pointwise_mlp(x: torch.Tensor, mlp: PreparedMLP, last_relu: bool = True) -> torch.Tensor:
+    """x (B,C,n) -> (B,Cout,n) f32 (voting and other per-point stacks)."""
+    B, C, n = x.shape
+    if not mlp.fusable(1):
+        return composed_pointwise(x, mlp, last_relu)
+    layout = Layout(c0=_round64(C), c0_cols=range(C))
+    out_cf, out_cl = fused_mlp(mlp, layout, B, n, n, 1, feat_cl=to_cl_bf16(x, pad_to=layout.c0), last_relu=last_relu)
+    return _attach(out_cf, out_cl)
+
+
+# ----------------------------------------------------------------------------- composed (general-shape) path
+def _chain(rows: torch.Tensor, mlp: PreparedMLP, last_relu: bool) -> torch.Tensor:
     h = rows.to(torch.bfloat16)
-    n = len(layers)
-    for i, L in enumerate(layers):
-        y = (h @ L.W_bf16.t()).float() + L.b
+    n = len(mlp)
+    for i, ((W, b), Wb) in enumerate(zip(mlp.layers, mlp.W_bf16)):
+        y = (h @ Wb.t()).float() + b
         if i < n - 1 or last_relu:
             y = torch.relu(y)
         h = y.to(torch.bfloat16) if i < n - 1 else y
     return h
 
 
-def sa_group_mlp(xyz, new_xyz, features, idx, radius, layers: List[PreparedLayer],
-                 use_xyz: bool = True, normalize_xyz: bool = True) -> torch.Tensor:
-    """Group (relative, optionally radius-normalised xyz ++ features) -> MLP -> max over nsample.
-    xyz (B,N,3), new_xyz (B,P,3), features (B,C,N) | None, idx (B,P,S) -> (B,Cout,P) fp32."""
+def composed_sa(xyz, new_xyz, features, idx, radius, mlp, use_xyz=True, normalize_xyz=True):
     B, P, S = idx.shape
-    g = ops.grouping_operation(xyz.transpose(1, 2).contiguous(), idx)          # (B,3,P,S)
+    g = ops.grouping_operation(xyz.transpose(1, 2).contiguous(), idx)
     g = g - new_xyz.transpose(1, 2).unsqueeze(-1)
     if normalize_xyz:
         g = g / (radius[:, None, :, None] if torch.is_tensor(radius) else float(radius))
@@ -53,13 +259,12 @@ def sa_group_mlp(xyz, new_xyz, features, idx, radius, layers: List[PreparedLayer
         gf = ops.grouping_operation(features.contiguous(), idx)
         g = torch.cat([g, gf], dim=1) if use_xyz else gf
     rows = g.permute(0, 2, 3, 1).reshape(B * P * S, g.shape[1])
-    y = _chain(rows, layers, last_relu=True)
+    y = _chain(rows, mlp, last_relu=True)
     return y.view(B, P, S, -1).max(dim=2)[0].transpose(1, 2).contiguous()
 
 
-def pointwise_mlp(x: torch.Tensor, layers: List[PreparedLayer], last_relu: bool = True) -> torch.Tensor:
-    """x (B,C,n) -> (B,Cout,n) fp32 (FP modules, voting)."""
+def composed_pointwise(x, mlp, last_relu=True):
     B, C, n = x.shape
     rows = x.transpose(1, 2).reshape(B * n, C)
-    y = _chain(rows, layers, last_relu)
+    y = _chain(rows, mlp, last_relu)
     return y.view(B, n, -1).transpose(1, 2).contiguous()

@@ -149,11 +149,14 @@ class PointnetFPModule(nn.Module):
         self.mlp = SharedMLP(list(mlp), bn=bn)
 
     def forward(self, unknown, known, unknow_feats, known_feats):
+        fast = not self.training and not torch.is_grad_enabled()
         if known is not None:
             dist, idx = ops.three_nn(unknown, known)
             dist_recip = 1.0 / (dist + 1e-8)
             norm = (dist_recip[..., 0] + dist_recip[..., 1]) + dist_recip[..., 2]
             weight = (dist_recip / norm.unsqueeze(-1)).contiguous()
+            if fast:
+                return _mlp.fp_interp_mlp(known_feats, unknow_feats, idx, weight, self.mlp.folded())
             interpolated = ops.three_interpolate(known_feats.contiguous(), idx, weight)
         else:
             interpolated = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))

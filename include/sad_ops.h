@@ -99,6 +99,49 @@ SAD_API int sad_three_interpolate_bwd(int B, int C, int n, int m, const float* g
                               const int32_t* idx, const float* weight, float* grad_features,
                               sad_stream_t stream);
 
+/* ---- a6  shared point-wise MLP (+ max-pool), fused with the neighbourhood gather ------------
+ *
+ * Weights travel as pre-packed bf16 "images" (the exact tcgen05 K-major SWIZZLE_128B
+ * shared-memory byte layout, so the TMA engine can stream them with plain bulk copies).
+ * sad_mlp_weight_image_bytes / sad_mlp_pack_weights are HOST functions (no CUDA call):
+ *   W      (cout x cin) fp32 row-major (BN already folded),
+ *   perm   kpad int32: perm[k] = column of W feeding packed K index k, -1 = zero column
+ *          (layer 1 K order: [feat_cl C0 | feat2_cl C1in | special chunk of 64: dx,dy,dz,
+ *          extras..., zeros]; later layers: identity over the previous layer's outputs),
+ *   kpad   K rounded up to a multiple of 64,  is_last = 1 for the final layer of the stack.
+ * Returns bytes (or -1) / SAD_OK. */
+SAD_API long long sad_mlp_weight_image_bytes(int cout, int kpad, int is_last);
+SAD_API int sad_mlp_pack_weights(const float* W, int cout, int cin, const int32_t* perm, int kpad,
+                                 int is_last, void* out_image_host);
+
+/* One launch = gather + 2..3 layer MLP (bias, ReLU; last ReLU optional) + max over S.
+ *   rows           r = (b, j, s), b<B, j<P, s<S;   S power of two <= 128 (1 = no pooling)
+ *   feat_cl        (B,N,C0) bf16 channel-last, row picked by idx (C0 % 64 == 0; NULL if C0 == 0)
+ *   feat2_cl       (B,P,C1in) bf16 channel-last, row-aligned second source (needs S == 1)
+ *   xyz,new_xyz    (B,N,3),(B,P,3) f32: adds (xyz[idx]-new_xyz[j]) (/ radius if normalize_xyz)
+ *   idx            (B,P,S) i32, or NULL = identity (needs S == 1 and N == P)
+ *   radius_t       (B,P) f32 per-cluster radius (overrides `radius`) or NULL
+ *   extra          (B,N,E) f32 scalar features appended after xyz in the special chunk (E <= 13)
+ *   w_img, bias    n_layers device pointers (packed images / f32 biases), c_out widths;
+ *                  hidden widths % 64 == 0 and <= 256
+ *   out_cl_bf16    (B,P,c_last) bf16 channel-last and/or out_cf_f32 (B,c_last,P) f32 (either may be NULL)
+ * bf16 operands, fp32 accumulate/bias/ReLU/max (tolerance 2e-2 vs the fp32 oracle). */
+SAD_API int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_cl, int C0,
+                               const void* feat2_cl, int C1in, const float* xyz, const float* new_xyz,
+                               const int32_t* idx, float radius, const float* radius_t,
+                               int normalize_xyz, const float* extra, int E, int n_layers,
+                               const void* const* w_img, const float* const* bias, const int* c_out,
+                               int last_relu, void* out_cl_bf16, float* out_cf_f32, sad_stream_t stream);
+
+/* a9 on the internal layout: features (B,m,C) bf16 channel-last -> out (B,n,C) bf16 (C % 8 == 0). */
+SAD_API int sad_three_interpolate_cl_fwd(int B, int C, int m, int n, const void* feat_cl_bf16,
+                                         const int32_t* idx, const float* weight, void* out_cl_bf16,
+                                         sad_stream_t stream);
+
+/* Layout bridge for the drop-in surface: (B,C,N) f32 channel-first -> (B,N,C) bf16 channel-last. */
+SAD_API int sad_cf_to_cl_bf16(int B, int C, int N, const float* in_cf, void* out_cl_bf16,
+                              sad_stream_t stream);
+
 /* Number of kernels this library has launched in this process (all threads, monotonic). */
 SAD_API unsigned long long sad_launch_count(void);
 
