@@ -1,0 +1,41 @@
+"""Smallest program that runs the benchmarked step (B=8 x 40k hot path) -- the command
+profiled under ncu (launch list / --set full captures).  Not a benchmark: prints nothing
+but a checksum.
+
+    python tools/profile_step.py [--warmup 2] [--steps 1] [--B 8] [--N 40000]
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import sad_b200  # noqa: E402,F401
+from sad_b200.config import LAYER_CFG, make_params  # noqa: E402
+from sad_b200.modules import SADHotPath  # noqa: E402
+from sad_b200.scenes import make_scenes, make_sizes  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--B", type=int, default=8)
+    ap.add_argument("--N", type=int, default=40000)
+    a = ap.parse_args()
+    dev = "cuda:0"
+    model = SADHotPath(1).load_params(make_params(0)).to(dev).eval()
+    xyz, feat = make_scenes(a.B, a.N, "surface")
+    size = make_sizes(a.B, LAYER_CFG["agg"][0])
+    x, f, s = (torch.from_numpy(t).to(dev) for t in (xyz, feat, size))
+    with torch.no_grad():
+        for _ in range(a.warmup + a.steps):
+            end = model(x, f, s)
+    torch.cuda.synchronize()
+    print("checksum", float(end["cluster_features"].sum()))
+
+
+if __name__ == "__main__":
+    main()
