@@ -19,8 +19,13 @@ def main():
     with open(src) as f:
         lines = [ln for ln in f if not ln.startswith("==")]
     rows = list(csv.DictReader(lines))
-    per = (len(rows) - tail) // passes
-    step = rows[len(rows) - tail - per: len(rows) - tail]
+    # a pass starts at each launch of the step's first kernel (the first pass also carries
+    # one-time weight folding / packing launches, so passes are not equally long)
+    first = rows[0]["Kernel Name"]
+    starts = [i for i, r in enumerate(rows) if r["Kernel Name"] == first]
+    assert len(starts) == passes, f"expected {passes} passes, found {len(starts)}"
+    step = rows[starts[-1]: len(rows) - tail]
+    per = len(step)
     agg, tot = collections.OrderedDict(), 0.0
     for row in step:
         v = float(row["Metric Value"].replace(",", ""))
