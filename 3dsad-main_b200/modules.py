@@ -122,10 +122,11 @@ class PointnetSAModuleVotes(nn.Module):
             ch[0] += 3
         self.mlp_module = SharedMLP(ch, bn=bn)
 
-    def forward(self, xyz, features=None, inds=None, radius_t=None):
+    def forward(self, xyz, features=None, inds=None, radius_t=None, new_xyz=None):
         if inds is None:
             inds = ops.furthest_point_sample(xyz, self.npoint)
-        new_xyz = _gather_xyz(xyz, inds)
+        if new_xyz is None:
+            new_xyz = _gather_xyz(xyz, inds)
         if radius_t is not None:
             idx = ops.ball_query_adaptive(radius_t, self.nsample, xyz, new_xyz)
             rad = radius_t
@@ -148,13 +149,18 @@ class PointnetFPModule(nn.Module):
         super().__init__()
         self.mlp = SharedMLP(list(mlp), bn=bn)
 
-    def forward(self, unknown, known, unknow_feats, known_feats):
+    @staticmethod
+    def interpolation_plan(unknown, known):
+        """three_nn + inverse-distance weights (depends on coordinates only) -> (idx, weight)."""
+        dist, idx = ops.three_nn(unknown, known)
+        dist_recip = 1.0 / (dist + 1e-8)
+        norm = (dist_recip[..., 0] + dist_recip[..., 1]) + dist_recip[..., 2]
+        return idx, (dist_recip / norm.unsqueeze(-1)).contiguous()
+
+    def forward(self, unknown, known, unknow_feats, known_feats, plan=None):
         fast = not self.training and not torch.is_grad_enabled()
         if known is not None:
-            dist, idx = ops.three_nn(unknown, known)
-            dist_recip = 1.0 / (dist + 1e-8)
-            norm = (dist_recip[..., 0] + dist_recip[..., 1]) + dist_recip[..., 2]
-            weight = (dist_recip / norm.unsqueeze(-1)).contiguous()
+            idx, weight = plan if plan is not None else self.interpolation_plan(unknown, known)
             if fast:
                 return _mlp.fp_interp_mlp(known_feats, unknow_feats, idx, weight, self.mlp.folded())
             interpolated = ops.three_interpolate(known_feats.contiguous(), idx, weight)
@@ -180,14 +186,61 @@ class Pointnet2Backbone(nn.Module):
         self.fp1 = PointnetFPModule(ch["fp1"], bn=bn)
         self.fp2 = PointnetFPModule(ch["fp2"], bn=bn)
 
+    overlap_geometry = True     # run the coordinate-only chain (FPS, three_nn) on a side stream
+
+    def _geometry_chain(self, xyz):
+        """Everything that depends on coordinates only -- the four dependent FPS passes, the
+        sampled coordinates and the two interpolation plans -- issued on a side stream so the
+        serial FPS latency overlaps the ball queries / MLPs of the earlier stages."""
+        main = torch.cuda.current_stream(xyz.device)
+        geo = getattr(self, "_geo_stream", None)
+        if geo is None or geo.device != xyz.device:
+            geo = self._geo_stream = torch.cuda.Stream(device=xyz.device)
+        geo.wait_stream(main)
+        plan = {}
+        with torch.cuda.stream(geo):
+            x = xyz
+            for name in ("sa1", "sa2", "sa3", "sa4"):
+                inds = ops.furthest_point_sample(x, getattr(self, name).npoint)
+                x = _gather_xyz(x, inds)
+                ev = torch.cuda.Event()
+                ev.record(geo)
+                plan[name] = (inds, x, ev)
+            p1 = PointnetFPModule.interpolation_plan(plan["sa3"][1], plan["sa4"][1])
+            p2 = PointnetFPModule.interpolation_plan(plan["sa2"][1], plan["sa3"][1])
+            ev = torch.cuda.Event()
+            ev.record(geo)
+            plan["fp"] = (p1, p2, ev)
+        for v in plan.values():           # tensors born on `geo`, consumed on `main`
+            for t in v:
+                if torch.is_tensor(t):
+                    t.record_stream(main)
+                elif isinstance(t, tuple):
+                    for u in t:
+                        u.record_stream(main)
+        return plan, main
+
     def forward(self, xyz, features):
         end = {}
         x, f = xyz, features
+        fast = (self.overlap_geometry and not self.training and not torch.is_grad_enabled() and xyz.is_cuda)
+        plan = None
+        if fast:
+            plan, main = self._geometry_chain(xyz)
         for name in ("sa1", "sa2", "sa3", "sa4"):
-            x, f, inds = getattr(self, name)(x, f)
+            if plan is not None:
+                inds, new_xyz, ev = plan[name]
+                main.wait_event(ev)
+                x, f, inds = getattr(self, name)(x, f, inds=inds, new_xyz=new_xyz)
+            else:
+                x, f, inds = getattr(self, name)(x, f)
             end[name + "_xyz"], end[name + "_features"], end[name + "_inds"] = x, f, inds
-        f = self.fp1(end["sa3_xyz"], end["sa4_xyz"], end["sa3_features"], end["sa4_features"])
-        f = self.fp2(end["sa2_xyz"], end["sa3_xyz"], end["sa2_features"], f)
+        p1 = p2 = None
+        if plan is not None:
+            p1, p2, ev = plan["fp"]
+            main.wait_event(ev)
+        f = self.fp1(end["sa3_xyz"], end["sa4_xyz"], end["sa3_features"], end["sa4_features"], plan=p1)
+        f = self.fp2(end["sa2_xyz"], end["sa3_xyz"], end["sa2_features"], f, plan=p2)
         end["fp2_features"] = f
         end["fp2_xyz"] = end["sa2_xyz"]
         end["fp2_inds"] = end["sa1_inds"][:, : end["sa2_xyz"].shape[1]]
