@@ -1,29 +1,38 @@
 // a1  furthest_point_sample -- SURVEY.md section 8(a) row a1, hard part H3.
 // (No reference file exists to cite: /root/reference is README.md:1-2 only.)
 //
-// B200 design.  FPS is `npoint` strictly serial iterations, each a full pass over the
-// scene plus an argmax; the bound is per-iteration LATENCY, not HBM.  So:
+// B200 design.  FPS is `npoint` strictly serial picks, each a full pass over the scene plus
+// an argmax; the bound is the per-pick LATENCY chain, not HBM.  So:
 //   * every point (x,y,z,min-dist) lives in REGISTERS for the whole kernel.  Warp g
 //     (g = cta_rank*NW + warp) owns the contiguous index range [g*P*32, (g+1)*P*32),
 //     thread `lane` the points k = (g*P + p)*32 + lane, p < P (compile-time, unrolled);
 //   * small scenes: one CTA per scene; large scenes: one thread-block CLUSTER (up to 16
 //     CTAs = 16 SMs) per scene;
-//   * per iteration each warp reduces its own points with redux.sync (max on the
-//     non-negative distance bits, then min on the index among the maxima: ties -> lowest
-//     index, H2) and pushes ONE 16-byte record {dist, x, y, z} straight into slot g of
-//     every peer CTA's shared memory with st.async (DSMEM) -- the store itself signals
-//     the peer's mbarrier (complete_tx), so there is no cluster barrier, no CTA barrier
-//     and no global memory on the critical path;
-//   * every warp then reduces the CS*NW records.  Because warps own ascending index
-//     ranges, "lowest slot among equal distances" == "lowest index", so the index never
-//     travels: the winning warp alone writes it to the output.
-// Slots past N get min-dist 0 and an index >= N: they can only ever tie at 0 and then
-// lose to a real point on the index rule.
+//   * the kernel works in ROUNDS.  Per round each warp reduces its points with redux.sync
+//     to {best value, its coordinates, SECOND-best value}; the CTA folds its warps and pushes
+//     one 20-byte record into every peer CTA's shared memory with st.async (DSMEM) -- the
+//     store itself completes the peer's mbarrier, so there is no cluster barrier and no
+//     global memory on the critical path;
+//   * MULTI-PICK: with one record per bin (bin = CTA, or warp in the single-CTA case) every
+//     warp then replays the sequential algorithm on the records and accepts as many picks
+//     as it can PROVE identical to it: the k-th candidate (largest remaining bin-best,
+//     lowest bin = lowest index at ties) is the true next pick iff its value is strictly
+//     above the second-best of every bin already used this round and its distance to every
+//     pick of this round is >= its value (so its min-dist is unchanged).  The first failed
+//     check ends the round; all accepted picks are applied in the next local pass.  The
+//     exchange latency is paid once per round (typically 3-5 picks) instead of per pick,
+//     and the result is still bit-identical to the oracle.
+//   * ties -> lowest index everywhere (H2): redux.max on the (non-negative) distance bits,
+//     then redux.min on the index / lowest bin via ballot+ffs; warps and CTAs own ascending
+//     index ranges so "lowest bin" == "lowest index" and indices never travel.
+// Slots past N get min-dist 0 and an index >= N: they can only tie at 0 and then lose.
 #include "sad_common.cuh"
 
 namespace {
 
 using namespace sad;
+
+constexpr int FPS_KMAX = 8;   // picks accepted per round, at most
 
 __device__ __forceinline__ void st_async_v4(uint32_t raddr, float a, float b, float c, float d, uint32_t rbar) {
   asm volatile(
@@ -32,20 +41,29 @@ __device__ __forceinline__ void st_async_v4(uint32_t raddr, float a, float b, fl
       "f"(a), "f"(b), "f"(c), "f"(d), "r"(rbar)
       : "memory");
 }
+__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr),
+               "r"(v), "r"(rbar)
+               : "memory");
+}
 
 template <int T, int P, int CS>
 __global__ void __launch_bounds__(T, 1)
 fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict__ out) {
   constexpr int NW = T / 32;
-  constexpr int NSLOT = CS * NW;
-  constexpr int RPL = (NSLOT + 31) / 32;                 // records per lane in the final reduce
-  extern __shared__ __align__(16) float4 s_pts[];         // [P*T] (x,y,z,-) copy for winner lookup
-  __shared__ __align__(16) float4 s_rec[2][NSLOT];        // {dist bits, x, y, z} per warp of the cluster
+  constexpr int NB = (CS > 1) ? CS : NW;                   // bins seen by the selection step
+  static_assert(NW <= 32 && CS <= 32, "one record per lane");
+  extern __shared__ __align__(16) float4 s_pts[];          // [P*T] (x,y,z,-) copy for winner lookup
+  __shared__ __align__(16) float4 s_loc[2][NW];            // per warp {best value bits, x, y, z}
+  __shared__ __align__(8) uint2 s_loc2[2][NW];             // per warp {second-best value bits, best index}
+  __shared__ __align__(16) float4 s_rec[2][CS];            // per CTA  {best value bits, x, y, z}   (DSMEM target)
+  __shared__ uint32_t s_rec2[2][CS];                       // per CTA  second-best value bits       (DSMEM target)
+  __shared__ __align__(16) float4 s_q[NW][FPS_KMAX];       // per warp: picks of the current round
   __shared__ __align__(8) uint64_t s_bar[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = (CS > 1) ? cluster_ctarank() : 0u;
-  const int g = (int)rank * NW + warp;                    // slot id == ascending index range id
+  const int g = (int)rank * NW + warp;
   const int b = blockIdx.x / CS;
   const float* pts = xyz + (size_t)b * N * 3;
   int32_t* o = out + (size_t)b * npoint;
@@ -65,10 +83,10 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict
     }
     s_pts[p * T + tid] = make_float4(px[p], py[p], pz[p], 0.f);
   }
-  float qx = __ldg(pts), qy = __ldg(pts + 1), qz = __ldg(pts + 2);
+  if (lane == 0) s_q[warp][0] = make_float4(__ldg(pts), __ldg(pts + 1), __ldg(pts + 2), 0.f);   // pick 0 = point 0
   if (rank == 0 && tid == 0) o[0] = 0;
 
-  uint32_t r_rec[2] = {0, 0}, r_bar[2] = {0, 0};          // DSMEM addresses in peer CTA `lane`
+  uint32_t r_rec[2] = {0, 0}, r_rec2[2] = {0, 0}, r_bar[2] = {0, 0};   // DSMEM addresses in peer CTA `lane`
   if (CS > 1) {
     if (tid == 0) {
       mbar_init(&s_bar[0], 1);
@@ -78,68 +96,110 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict
     const uint32_t dst = (uint32_t)(lane % CS);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      r_rec[u] = mapa(smem_u32(&s_rec[u][g]), dst);
+      r_rec[u] = mapa(smem_u32(&s_rec[u][rank]), dst);
+      r_rec2[u] = mapa(smem_u32(&s_rec2[u][rank]), dst);
       r_bar[u] = mapa(smem_u32(&s_bar[u]), dst);
     }
   }
   __syncthreads();
   if (CS > 1) cluster_sync_all();   // peers resident + mbarrier inits visible before any DSMEM store
 
-  for (int j = 1; j < npoint; ++j) {
-    const int buf = j & 1;
-    if (CS > 1 && tid == 0) mbar_arrive_expect_tx(&s_bar[buf], NSLOT * 16);
+  int K = 1;      // picks to apply in this round's local pass
+  int j = 1;      // next output position
+  for (uint32_t round = 0; j < npoint; ++round) {
+    const int buf = (int)(round & 1u);
+    if (CS > 1 && tid == 0) mbar_arrive_expect_tx(&s_bar[buf], CS * 20);
 
-    // ---- local pass over the P register-resident points (two independent best-chains)
-    float bv0 = -1.f, bv1 = -1.f;
-    int bp0 = 0, bp1 = 1;
+    // ---- 1. apply the K picks of the previous round to the register-resident points
+    for (int k = 0; k < K; ++k) {
+      const float4 q = s_q[warp][k];
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-      const float d = sqdist(px[p], py[p], pz[p], qx, qy, qz);
-      const float m = fminf(md[p], d);
-      md[p] = m;
-      if (p & 1) {
-        if (m > bv1) { bv1 = m; bp1 = p; }   // strict: ascending p == ascending index in a thread
+      for (int p = 0; p < P; ++p) md[p] = fminf(md[p], sqdist(px[p], py[p], pz[p], q.x, q.y, q.z));
+    }
+    // best (first max: ascending p == ascending index inside a thread) and second-best value
+    float b1 = md[0], b2 = 0.f;
+    int bp = 0;
+#pragma unroll
+    for (int p = 1; p < P; ++p) {
+      const float m = md[p];
+      if (m > b1) {
+        b2 = b1;
+        b1 = m;
+        bp = p;
       } else {
-        if (m > bv0) { bv0 = m; bp0 = p; }
+        b2 = fmaxf(b2, m);
       }
     }
-    float bv = bv0;
-    int bp = bp0;
-    if (P > 1 && (bv1 > bv0 || (bv1 == bv0 && bp1 < bp0))) { bv = bv1; bp = bp1; }
-
-    const uint32_t vb = __float_as_uint(bv);
+    // ---- 2. warp: best value, lowest index among the maxima, second-best value
+    const uint32_t vb = __float_as_uint(b1);
     const uint32_t bk = (uint32_t)((g * P + bp) * 32 + lane);
     const uint32_t wmax = __reduce_max_sync(FULL, vb);
     const uint32_t wk = __reduce_min_sync(FULL, vb == wmax ? bk : 0xFFFFFFFFu);
+    const uint32_t w2 = __reduce_max_sync(FULL, (vb == wmax && bk == wk) ? __float_as_uint(b2) : vb);
     const int lp = (int)(wk >> 5) - g * P;
     const float4 c = s_pts[lp * T + warp * 32 + (int)(wk & 31u)];
-
-    if (CS == 1) {
-      if (lane == 0) s_rec[buf][warp] = make_float4(__uint_as_float(wmax), c.x, c.y, c.z);
-      __syncthreads();
-    } else {
-      if (lane < CS) st_async_v4(r_rec[buf], __uint_as_float(wmax), c.x, c.y, c.z, r_bar[buf]);
-      // use u of s_bar[buf] is iteration j = 2u + 1 (buf 1) or 2u + 2 (buf 0): u = (j-1)/2
-      mbar_wait(&s_bar[buf], (uint32_t)(((j - 1) >> 1) & 1));
+    if (lane == 0) {
+      s_loc[buf][warp] = make_float4(__uint_as_float(wmax), c.x, c.y, c.z);
+      s_loc2[buf][warp] = make_uint2(w2, wk);
     }
+    __syncthreads();
 
-    // ---- every warp reduces the NSLOT records: max dist, ties -> lowest slot (== lowest index)
-    uint32_t v = 0u, slot = 0xFFFFFFFFu;
-#pragma unroll
-    for (int r = 0; r < RPL; ++r) {
-      const int s = lane + 32 * r;
-      if (s < NSLOT) {
-        const uint32_t x = __float_as_uint(s_rec[buf][s].x);
-        if (slot == 0xFFFFFFFFu || x > v) { v = x; slot = (uint32_t)s; }
+    // ---- 3. one record per bin in (v1b, v2b) of lane `bin`
+    uint32_t v1b, v2b;
+    int rep_warp = warp;   // CS > 1: the warp whose point represents this CTA
+    if (CS > 1) {
+      const uint32_t lv = (lane < NW) ? __float_as_uint(s_loc[buf][lane].x) : 0u;
+      const uint32_t l2 = (lane < NW) ? s_loc2[buf][lane].x : 0u;
+      const uint32_t cmax = __reduce_max_sync(FULL, lv);
+      rep_warp = __ffs(__ballot_sync(FULL, lane < NW && lv == cmax)) - 1;      // lowest warp == lowest index
+      const uint32_t c2 = __reduce_max_sync(FULL, (lane == rep_warp) ? l2 : lv);
+      const float4 r = s_loc[buf][rep_warp];
+      if (lane < CS && (lane % NW) == warp) {       // each warp serves a quarter of the peers
+        st_async_v4(r_rec[buf], r.x, r.y, r.z, r.w, r_bar[buf]);
+        st_async_b32(r_rec2[buf], c2, r_bar[buf]);
       }
+      mbar_wait(&s_bar[buf], (round >> 1) & 1u);
+      v1b = (lane < CS) ? __float_as_uint(s_rec[buf][lane].x) : 0u;
+      v2b = (lane < CS) ? s_rec2[buf][lane] : 0u;
+    } else {
+      v1b = (lane < NW) ? __float_as_uint(s_loc[buf][lane].x) : 0u;
+      v2b = (lane < NW) ? s_loc2[buf][lane].x : 0u;
     }
-    const uint32_t gmax = __reduce_max_sync(FULL, v);
-    const uint32_t gslot = __reduce_min_sync(FULL, v == gmax ? slot : 0xFFFFFFFFu);
-    const float4 w = s_rec[buf][gslot];
-    qx = w.y;
-    qy = w.z;
-    qz = w.w;
-    if ((int)gslot == g && lane == 0) o[j] = (int32_t)wk;
+
+    // ---- 4. replay the sequential algorithm on the bin records (every warp, identically)
+    uint32_t picked = 0u, bound2 = 0u;
+    int npick = 0;
+    const int room = min(FPS_KMAX, npoint - j);
+    while (npick < room) {
+      const bool avail = (lane < NB) && !((picked >> lane) & 1u);
+      const uint32_t cand = avail ? v1b : 0u;
+      const uint32_t gmax = __reduce_max_sync(FULL, cand);
+      const int w = __ffs(__ballot_sync(FULL, avail && cand == gmax)) - 1;     // lowest bin == lowest index
+      if (w < 0) break;
+      if (npick > 0 && !(gmax > bound2)) break;     // a used bin may still hold something as large
+      const float4 cw = (CS > 1) ? s_rec[buf][w] : s_loc[buf][w];
+      if (npick > 0) {
+        const float v = __uint_as_float(gmax);
+        bool unchanged = true;
+        for (int i = 0; i < npick; ++i) {
+          const float4 q = s_q[warp][i];
+          unchanged = unchanged && (sqdist(cw.y, cw.z, cw.w, q.x, q.y, q.z) >= v);
+        }
+        if (!unchanged) break;                      // an earlier pick of this round lowers its min-dist
+      }
+      __syncwarp();
+      if (lane == 0) {
+        s_q[warp][npick] = make_float4(cw.y, cw.z, cw.w, 0.f);
+        const bool mine = (CS > 1) ? ((int)rank == w && warp == rep_warp) : (warp == w);
+        if (mine) o[j + npick] = (int32_t)wk;
+      }
+      __syncwarp();
+      bound2 = max(bound2, __shfl_sync(FULL, v2b, w));
+      picked |= 1u << w;
+      ++npick;
+    }
+    K = npick;
+    j += npick;
   }
   if (CS > 1) cluster_sync_all();   // no CTA retires while a peer's st.async may still target it
 }
