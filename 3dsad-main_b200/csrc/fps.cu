@@ -27,6 +27,8 @@
 //   * ties -> lowest index everywhere (H2): warps and CTAs own ascending index ranges, so
 //     "lowest bin" == "lowest index" and indices never travel.
 // Slots past N get min-dist 0 and an index >= N: they can only tie at 0 and then lose.
+#include <stdlib.h>
+
 #include "sad_common.cuh"
 
 namespace {
@@ -50,7 +52,7 @@ __device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t v, uint32_
 }
 
 template <int P, int CS>
-__global__ void __launch_bounds__(FPS_T, 1)
+__global__ void __launch_bounds__(FPS_T, (P <= 6) ? 2 : 1)
 fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict__ out, long long* dbg) {
   constexpr int T = FPS_T;
   constexpr int NW = T / 32;
@@ -65,6 +67,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict
   __shared__ int s_npick;
   __shared__ __align__(8) uint64_t s_bar[2];
 
+  const long long t_entry = clock64();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = (CS > 1) ? cluster_ctarank() : 0u;
   const int g = (int)rank * NW + warp;
@@ -197,21 +200,21 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict
       const uint32_t v1i = __float_as_uint(ri.x);
       const float fi = ri.x;
       uint32_t cnt = 0u, earlier = 0u, conflict = 0u;
+      // branch-free on purpose (bitwise, not short-circuit): divergent branches here cost more
+      // than the whole arithmetic of the step
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
-        const int jb = h * 8 + jj;
-        if (jb < NB) {
-          const float4 rj = RA[jb];
-          const uint32_t v1j = __float_as_uint(rj.x);
-          const uint32_t v2j = (CS > 1) ? RB[jb] : s_loc2[buf][jb].x;
-          const bool before = (v1j > v1i) || (v1j == v1i && jb < i);            // bin jb outranks bin i
-          const bool conf = (v2j >= v1i) || (sqdist(ri.y, ri.z, ri.w, rj.y, rj.z, rj.w) < fi);
-          if (jb != i) {
-            cnt += before ? 1u : 0u;
-            earlier |= (before ? 1u : 0u) << jb;
-            conflict |= (conf ? 1u : 0u) << jb;
-          }
-        }
+        const int jb = min(h * 8 + jj, NB - 1);                 // clamp: out-of-range partners are masked below
+        const bool valid = (h * 8 + jj < NB) & (jb != i);
+        const float4 rj = RA[jb];
+        const uint32_t v1j = __float_as_uint(rj.x);
+        const uint32_t v2j = (CS > 1) ? RB[jb] : s_loc2[buf][jb].x;
+        const float dij = sqdist(ri.y, ri.z, ri.w, rj.y, rj.z, rj.w);
+        const uint32_t before = (uint32_t)((v1j > v1i) | ((v1j == v1i) & (jb < i))) & (uint32_t)valid;   // jb outranks i
+        const uint32_t conf = (uint32_t)((v2j >= v1i) | (dij < fi)) & (uint32_t)valid;
+        cnt += before;
+        earlier |= before << jb;
+        conflict |= conf << jb;
       }
       cnt += __shfl_xor_sync(FULL, cnt, 16);
       earlier |= __shfl_xor_sync(FULL, earlier, 16);
@@ -235,8 +238,10 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict
     if (prof) ph[5] += 1;
   }
 #undef SAD_FPS_MARK
-  if (prof)
+  if (prof) {
     for (int i = 0; i < 6; ++i) dbg[i] = ph[i];
+    dbg[6] = clock64() - t_entry;
+  }
   if (CS > 1) cluster_sync_all();   // no CTA retires while a peer's st.async may still target it
 }
 
@@ -252,6 +257,9 @@ int launch_fps(int B, int N, int npoint, const float* xyz, int32_t* idx, cudaStr
   if (configured_dev != dev) {
     SAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (CS > 8) SAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    // several clusters must share an SM for a whole batch to run in one wave
+    SAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
     configured_dev = dev;
   }
   cudaLaunchConfig_t cfg = {};
@@ -266,6 +274,15 @@ int launch_fps(int B, int N, int npoint, const float* xyz, int32_t* idx, cudaStr
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (CS > 1) ? 1 : 0;
+  if (getenv("SAD_DEBUG_OCC")) {
+    int ncl = -1, nb = -1;
+    if (CS > 1) cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, FPS_T, smem);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kern);
+    fprintf(stderr, "[sad] fps_kernel<P=%d,CS=%d>: regs=%d smem=%zu+%zu maxActiveClusters=%d blocks/SM=%d\n", P, CS,
+            fa.numRegs, smem, fa.sharedSizeBytes, ncl, nb);
+  }
   SAD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, xyz, N, npoint, idx, g_fps_dbg));
   sad_count_launch(1);
   return SAD_OK;
@@ -333,14 +350,17 @@ extern "C" int sad_furthest_point_sample_fwd(int B, int N, int npoint, const flo
       while (cs > 2 && (long long)B * cs > 148) cs >>= 1;
     }
   }
-  SAD_REQUIRE(cs == 1 || cs == 2 || cs == 4 || cs == 8 || cs == 16, "fps: bad cluster size %d", cs);
-  while (cs < 16 && (long long)cs * T * kPMax < N) cs <<= 1;   // capacity: P <= 25 points / thread
+  SAD_REQUIRE(cs == 1 || cs == 2 || cs == 4 || cs == 8 || cs == 12 || cs == 14 || cs == 16, "fps: bad cluster size %d",
+              cs);
+  while (cs < 16 && (long long)cs * T * kPMax < N) cs = (cs < 8) ? cs * 2 : (cs == 8 ? 12 : cs + 2);   // P <= 25
   const int P = round_p(sad_ceil_div(N, (long long)cs * T));
   switch (cs) {
     case 1: return dispatch_p<1>(P, B, N, npoint, xyz, idx, stream);
     case 2: return dispatch_p<2>(P, B, N, npoint, xyz, idx, stream);
     case 4: return dispatch_p<4>(P, B, N, npoint, xyz, idx, stream);
     case 8: return dispatch_p<8>(P, B, N, npoint, xyz, idx, stream);
+    case 12: return dispatch_p<12>(P, B, N, npoint, xyz, idx, stream);
+    case 14: return dispatch_p<14>(P, B, N, npoint, xyz, idx, stream);
     default: return dispatch_p<16>(P, B, N, npoint, xyz, idx, stream);
   }
 }
