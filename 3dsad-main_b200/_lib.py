@@ -20,7 +20,6 @@ SIGNATURES = {
     "sad_last_error_string": [],
     "sad_fps_force_cluster_size": [_c_int],
     "sad_launch_count": [],
-    "sad_fps_set_debug_buffer": [_vp],
     "sad_furthest_point_sample_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
     "sad_gather_operation_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_gather_operation_bwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
@@ -38,7 +37,7 @@ SIGNATURES = {
     "sad_three_interpolate_cl_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_cf_to_cl_bf16": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
 }
-_RESTYPES = {"sad_last_error_string": ctypes.c_char_p, "sad_fps_force_cluster_size": None, "sad_fps_set_debug_buffer": None,
+_RESTYPES = {"sad_last_error_string": ctypes.c_char_p, "sad_fps_force_cluster_size": None,
              "sad_launch_count": ctypes.c_ulonglong, "sad_mlp_weight_image_bytes": ctypes.c_longlong}
 
 _lib = None

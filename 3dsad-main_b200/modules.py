@@ -188,30 +188,48 @@ class Pointnet2Backbone(nn.Module):
 
     overlap_geometry = True     # run the coordinate-only chain (FPS, three_nn) on a side stream
 
-    def _geometry_chain(self, xyz):
-        """Everything that depends on coordinates only -- the four dependent FPS passes, the
-        sampled coordinates and the two interpolation plans -- issued on a side stream so the
-        serial FPS latency overlaps the ball queries / MLPs of the earlier stages."""
+    def _side_streams(self, device):
+        st = getattr(self, "_geo_streams", None)
+        if st is None or st[0].device != device:
+            st = self._geo_streams = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+        return st
+
+    def _geometry_chain(self, xyz, ready_event=None):
+        """Everything that depends on coordinates only, issued on two side streams:
+          geoA : FPS over the raw scene (SA1) -- the long serial kernel;
+          geoB : the three smaller dependent FPS passes and the two interpolation plans.
+        The serial FPS latency then overlaps the ball queries / MLPs of the earlier stages, and --
+        when the caller passes `ready_event` (inputs already resident) instead of ordering against
+        the whole main stream -- the feature work of the PREVIOUS batch as well."""
         main = torch.cuda.current_stream(xyz.device)
-        geo = getattr(self, "_geo_stream", None)
-        if geo is None or geo.device != xyz.device:
-            geo = self._geo_stream = torch.cuda.Stream(device=xyz.device)
-        geo.wait_stream(main)
+        geo_a, geo_b = self._side_streams(xyz.device)
+        if ready_event is not None:
+            geo_a.wait_event(ready_event)
+        else:
+            geo_a.wait_stream(main)
         plan = {}
-        with torch.cuda.stream(geo):
-            x = xyz
-            for name in ("sa1", "sa2", "sa3", "sa4"):
+        xyz.record_stream(geo_a)
+        with torch.cuda.stream(geo_a):
+            inds = ops.furthest_point_sample(xyz, self.sa1.npoint)
+            x = _gather_xyz(xyz, inds)
+            ev = torch.cuda.Event()
+            ev.record(geo_a)
+            plan["sa1"] = (inds, x, ev)
+        geo_b.wait_event(ev)
+        with torch.cuda.stream(geo_b):
+            for name in ("sa2", "sa3", "sa4"):
                 inds = ops.furthest_point_sample(x, getattr(self, name).npoint)
                 x = _gather_xyz(x, inds)
                 ev = torch.cuda.Event()
-                ev.record(geo)
+                ev.record(geo_b)
                 plan[name] = (inds, x, ev)
             p1 = PointnetFPModule.interpolation_plan(plan["sa3"][1], plan["sa4"][1])
             p2 = PointnetFPModule.interpolation_plan(plan["sa2"][1], plan["sa3"][1])
             ev = torch.cuda.Event()
-            ev.record(geo)
+            ev.record(geo_b)
             plan["fp"] = (p1, p2, ev)
-        for v in plan.values():           # tensors born on `geo`, consumed on `main`
+        plan["sa1"][1].record_stream(geo_b)
+        for v in plan.values():           # tensors born on a side stream, consumed on `main`
             for t in v:
                 if torch.is_tensor(t):
                     t.record_stream(main)
@@ -220,13 +238,13 @@ class Pointnet2Backbone(nn.Module):
                         u.record_stream(main)
         return plan, main
 
-    def forward(self, xyz, features):
+    def forward(self, xyz, features, ready_event=None):
         end = {}
         x, f = xyz, features
         fast = (self.overlap_geometry and not self.training and not torch.is_grad_enabled() and xyz.is_cuda)
         plan = None
         if fast:
-            plan, main = self._geometry_chain(xyz)
+            plan, main = self._geometry_chain(xyz, ready_event)
         for name in ("sa1", "sa2", "sa3", "sa4"):
             if plan is not None:
                 inds, new_xyz, ev = plan[name]
@@ -308,8 +326,11 @@ class SADHotPath(nn.Module):
         self.agg.sa.mlp_module.load_folded(params["agg"])
         return self
 
-    def forward(self, xyz, features, size):
-        end = self.backbone(xyz, features)
+    def forward(self, xyz, features, size, ready_event=None):
+        """`ready_event` (optional): a CUDA event after which the inputs are valid.  Passing it lets
+        the coordinate-only chain of this batch start while the previous batch is still in its
+        feature stages (two batches in flight); without it the call orders against the stream."""
+        end = self.backbone(xyz, features, ready_event=ready_event)
         vxyz, vfeat = self.vgen(end["fp2_xyz"], end["fp2_features"])
         cxyz, cfeat, cinds, radius_t = self.agg(vxyz, vfeat, size)
         end.update(vote_xyz=vxyz, vote_features=vfeat, cluster_xyz=cxyz, cluster_features=cfeat,
@@ -317,18 +338,43 @@ class SADHotPath(nn.Module):
         return end
 
     @torch.no_grad()
-    def forward_host(self, xyz_host, feat_host, size_host, out_host=None):
-        """End-to-end call with HOST (pinned) buffers: H2D copies, forward, D2H of the cluster
-        features / centres.  Returns (cluster_xyz_host, cluster_features_host)."""
+    def forward_host_async(self, xyz_host, feat_host, size_host, out_host):
+        """End-to-end call with HOST (pinned) buffers, asynchronous: the H2D copies run on a copy
+        stream (so they overlap the previous batch), the forward is ordered after them by an event,
+        and the D2H of (cluster_xyz, cluster_features) into the pinned `out_host` pair is queued
+        behind it.  Returns (out_host, done_event); `out_host` is valid after done_event."""
         dev = next(self.parameters()).device
-        xyz = xyz_host.to(dev, non_blocking=True)
-        feat = feat_host.to(dev, non_blocking=True)
-        size = size_host.to(dev, non_blocking=True)
-        end = self.forward(xyz, feat, size)
-        if out_host is None:
-            out_host = (torch.empty(end["cluster_xyz"].shape, dtype=torch.float32, pin_memory=True),
-                        torch.empty(end["cluster_features"].shape, dtype=torch.float32, pin_memory=True))
+        main = torch.cuda.current_stream(dev)
+        copy = getattr(self, "_copy_stream", None)
+        if copy is None or copy.device != dev:
+            copy = self._copy_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(copy):
+            xyz = xyz_host.to(dev, non_blocking=True)
+            feat = feat_host.to(dev, non_blocking=True)
+            size = size_host.to(dev, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy)
+        main.wait_event(ready)
+        for t in (xyz, feat, size):
+            t.record_stream(main)
+        end = self.forward(xyz, feat, size, ready_event=ready)
         out_host[0].copy_(end["cluster_xyz"], non_blocking=True)
         out_host[1].copy_(end["cluster_features"], non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        done = torch.cuda.Event()
+        done.record(main)
+        return out_host, done
+
+    def make_host_outputs(self, batch: int):
+        npoint = self.agg.sa.npoint
+        c = self.agg.sa.mlp_module.channels[-1]
+        return (torch.empty((batch, npoint, 3), dtype=torch.float32, pin_memory=True),
+                torch.empty((batch, c, npoint), dtype=torch.float32, pin_memory=True))
+
+    @torch.no_grad()
+    def forward_host(self, xyz_host, feat_host, size_host, out_host=None):
+        """Synchronous form of forward_host_async.  Returns (cluster_xyz_host, cluster_features_host)."""
+        if out_host is None:
+            out_host = self.make_host_outputs(xyz_host.shape[0])
+        out_host, done = self.forward_host_async(xyz_host, feat_host, size_host, out_host)
+        done.synchronize()
         return out_host

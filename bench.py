@@ -8,10 +8,14 @@ aggregation) over one batch of synthetic scenes.  Workload at N=1 = BASELINE.jso
 configs[1]: B=8 scenes x 40k points per GPU (weak scaling: every rank gets its own 8
 scenes, no data-path collective).  metric = scenes/s, whole job.
 
-  value : inputs resident in HBM, CUDA-event timed per step, L2 flushed between steps.
-  e2e   : the same metric through SADHotPath.forward_host with HOST (pinned) buffers:
-          H2D of xyz/features/sizes and D2H of the cluster features inside the timed region.
-  roofline     : dominant kernel of the step, measured live with CUDA events.
+  value : inputs resident in HBM; K batches through the pipelined executor (engine.py: one CUDA
+          graph + stream per slot, `--slots` batches in flight), one CUDA-event pair around all K;
+          32 rotating input sets (> L2) instead of an L2 flush.  config.batch_latency_ms is one
+          batch alone on the GPU.
+  e2e   : the same metric through PipelinedHotPath.submit_host / result with HOST (pinned)
+          buffers: H2D of xyz/features/sizes and D2H of the cluster centres + features inside
+          the timed region, host wall clock, every result read on the host.
+  roofline     : dominant kernel of the step, measured live with CUDA events (serial, one stream).
   cpu_baseline : the oracle's C/OpenMP port + NumPy MLP ("port") on the box's host cores,
                  bounded sample, rank 0 at N=1 only.
   --impl reference : the reference arm.  The mounted reference is a README (no code), so
@@ -252,7 +256,7 @@ def build_roofline(model, xyz, feat, size, reps=3):
 
 # ----------------------------------------------------------------------------- GPU arm
 def run_ours(args):
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
     import torch.distributed as dist
 
@@ -266,17 +270,19 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    import sad_b200 as S
+    import sad_b200 as S  # noqa: F401
     from sad_b200 import _lib
     from sad_b200.config import LAYER_CFG, make_params
+    from sad_b200.engine import PipelinedHotPath
     from sad_b200.modules import SADHotPath
     from sad_b200.scenes import make_scenes, make_sizes
 
-    lib = _lib.load()
+    _lib.load()
     model = SADHotPath(input_feature_dim=1).load_params(make_params(0)).to(dev).eval()
 
-    # distinct scenes per rank and per rotating input set
-    NSETS = 4
+    # distinct scenes per rank and per rotating input set; the sets together exceed L2 (126 MB),
+    # so no step finds its inputs cached from an earlier one
+    NSETS = args.sets
     sets = []
     for s in range(NSETS):
         first = (rank * NSETS + s) * B_PER_GPU
@@ -284,49 +290,68 @@ def run_ours(args):
         size = make_sizes(B_PER_GPU, LAYER_CFG["agg"][0], first_scene=first)
         host = tuple(torch.from_numpy(a).pin_memory() for a in (xyz, feat, size))
         sets.append({"host": host, "dev": tuple(h.to(dev) for h in host)})
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    set_bytes = sum(int(h.numel() * h.element_size()) for h in sets[0]["host"])
+
+    eng = PipelinedHotPath(model, B_PER_GPU, N_POINTS, feat_dim=1, slots=args.slots, device=dev)
+    main = torch.cuda.current_stream(dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: inputs resident, per-step CUDA events, L2 flushed between steps
-    with torch.no_grad():
-        for w in range(args.warmup):
-            model(*sets[w % NSETS]["dev"])
-        barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
-        t_wall0 = time.perf_counter()
-        l0 = lib.sad_launch_count()
-        evs = []
-        for k in range(args.steps):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            model(*sets[k % NSETS]["dev"])
-            b.record()
-            evs.append((a, b))
-        barrier()
-        l1 = lib.sad_launch_count()
-        t_wall1 = time.perf_counter()
-        clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    launches_per_step = (l1 - l0) / args.steps
+    # ---- value: inputs resident in HBM, K batches through the pipelined executor, device-timed
+    for w in range(args.warmup):
+        eng.submit_device(*sets[w % NSETS]["dev"])
+    eng.drain()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(main)
+    for k in range(args.steps):
+        eng.submit_device(*sets[(args.warmup + k) % NSETS]["dev"], after=ev0 if k < eng.slots else None)
+    eng.join(main)
+    ev1.record(main)
+    barrier()
+    eng.drain()
+    t_wall1 = time.perf_counter()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    total_ms = ev0.elapsed_time(ev1)
 
-    # ---- e2e: host buffers in, host results out, every step
-    out_host = None
-    with torch.no_grad():
-        for w in range(max(1, args.warmup // 2)):
-            out_host = model.forward_host(*sets[w % NSETS]["host"], out_host=out_host)
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(args.steps):
-            out_host = model.forward_host(*sets[k % NSETS]["host"], out_host=out_host)
+    # ---- latency of ONE batch in isolation (nothing else in flight), device-timed
+    lat = []
+    for k in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(main)
+        eng.submit_device(*sets[k % NSETS]["dev"], after=a)
+        eng.join(main)
+        b.record(main)
         torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        barrier()
-    h2d = sum(int(h.numel() * h.element_size()) for h in sets[0]["host"])
+        eng.drain()
+        lat.append(a.elapsed_time(b))
+    lat.sort()
+
+    # ---- e2e: host (pinned) buffers in, host results out, every step; host wall clock
+    checksum = 0.0
+    for w in range(max(1, args.warmup // 2)):
+        eng.result(eng.submit_host(*sets[w % NSETS]["host"]))
+    barrier()
+    t0 = time.perf_counter()
+    tickets = []
+    for k in range(args.steps):
+        tickets.append(eng.submit_host(*sets[(args.warmup + k) % NSETS]["host"]))
+        if len(tickets) >= eng.slots:                     # results are consumed in order, one pipeline depth behind
+            cx, cf = eng.result(tickets.pop(0))
+            checksum += float(cf[0, 0, 0]) + float(cx[0, 0, 0])
+    for t in tickets:
+        cx, cf = eng.result(t)
+        checksum += float(cf[0, 0, 0]) + float(cx[0, 0, 0])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    out_host = eng.result(0)
+    h2d = set_bytes
     d2h = sum(int(o.numel() * o.element_size()) for o in out_host)
 
     # ---- max over ranks
@@ -339,9 +364,12 @@ def run_ours(args):
     e2e_value = scenes / (e2e_ms / 1e3)
 
     if rank == 0:
+        model.backbone.overlap_geometry = False          # per-kernel view: one stream, nothing overlapped
         roof, kernels = build_roofline(model, *sets[0]["dev"])
+        model.backbone.overlap_geometry = True
+        roof = attach_traffic(roof)
         cpu = None
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             n_s = max(1, min(B_PER_GPU, host_threads()))
             cpu_hot_path_rate(1, 4000)
             rate, secs, threads = cpu_hot_path_rate(n_s, N_POINTS, reps=2)
@@ -353,13 +381,17 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "scenes_per_gpu_per_step": B_PER_GPU, "points_per_scene": N_POINTS,
-                       "l2": "256 MiB flush write between timed steps (outside the per-step events); 4 rotating input sets",
+                       "l2": f"{NSETS} rotating input sets x {set_bytes / 1e6:.1f} MB = {NSETS * set_bytes / 1e6:.0f} MB "
+                             "> 126 MB L2 (inputs larger than L2, no flush)",
+                       "pipeline": f"{eng.slots} batches in flight (one CUDA graph + stream per slot); every batch runs "
+                                   "the full path and results are delivered in order",
+                       "batch_latency_ms": round(lat[len(lat) // 2], 4),
                        "search_dtype": "f32 (bit-exact indices)", "mlp_dtype": "bf16 in / f32 accumulate",
                        "parallelism": f"scene-data-parallel x{world}, no collective"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(e2e_ms / args.steps, 4)},
-            "gpu_launches": int(round(launches_per_step * args.steps)),
-            "gpu_launches_per_step": round(launches_per_step, 1),
+                    "ms_per_step": round(e2e_ms / args.steps, 4), "checksum": round(checksum, 4)},
+            "gpu_launches": int(eng.launches_per_batch * args.steps),
+            "gpu_launches_per_step": eng.launches_per_batch,
             "roofline": roof, "kernels": kernels, "clocks": clocks,
         }
         if cpu is not None:
@@ -371,12 +403,30 @@ def run_ours(args):
     return 0
 
 
+def attach_traffic(roof):
+    """DRAM traffic of the dominant kernel from the committed `ncu --set full` summary
+    (profiles/ncu_full_summary.json, written by tools/ncu_full_summary.py), per launch."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_full_summary.json")))
+        for row in d.get("kernels", []):
+            if row.get("roofline_key") == roof["kernel"]:
+                roof["traffic"] = row.get("dram_bytes_per_launch")
+                roof["traffic_source"] = "profiles/ncu_full_summary.json"
+                break
+    except Exception:  # noqa: BLE001
+        pass
+    return roof
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--slots", type=int, default=3, help="batches in flight in the pipelined executor")
+    ap.add_argument("--sets", type=int, default=32, help="rotating input sets (32 x 5.1 MB > L2)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

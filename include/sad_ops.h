@@ -148,10 +148,6 @@ SAD_API unsigned long long sad_launch_count(void);
 /* Test / benchmark hook: force the FPS thread-block-cluster size for subsequent calls on
  * this thread (1,2,4,8,16; 0 = built-in heuristic).  Results never depend on it. */
 SAD_API void sad_fps_force_cluster_size(int cluster_size);
-/* Tools only: device buffer of 6 int64 that block 0 of subsequent FPS launches on this thread fills
- * with summed clock64 cycles of {local pass, warp reduce, CTA barrier, exchange, selection} and
- * the round count (NULL = off, the default). */
-SAD_API void sad_fps_set_debug_buffer(long long* dev6);
 
 #ifdef __cplusplus
 }
