@@ -2,22 +2,32 @@
 // -- SURVEY.md section 8(a) rows a5/a6, section 8(f) rank 1, hard parts H4/H5.
 // (No reference file exists to cite: /root/reference is README.md:1-2 only.)
 //
-// One launch per SA / FP / voting stage.  For a tile of 128 rows (row = (query point,
-// sample)) the kernel
-//   1. GATHERS the layer-1 operand straight into shared memory in the tcgen05 canonical
-//      K-major SWIZZLE_128B layout: channel-last bf16 feature rows are fetched by `idx` with
-//      16-byte cp.async (the grouped tensor is never materialised in HBM); the relative,
-//      radius-normalised xyz (+ optional fp32 scalar features) form one extra 16-wide K step;
-//   2. runs the 2-3 layer MLP on the 5th-gen tensor cores: tcgen05.mma (bf16 in, fp32
-//      accumulate in TMEM), weights streamed as pre-swizzled images by the TMA engine
-//      (cp.async.bulk) through an mbarrier ring; hidden activations go TMEM -> registers
-//      (bias + ReLU, fp32) -> bf16 -> shared memory and are the next layer's operand;
-//   3. evaluates the LAST layer transposed (D^T = W . H^T), so a TMEM lane is an output
-//      channel and the nsample rows of a query point are consecutive TMEM columns: the
-//      max-pool is an in-register reduction in the epilogue (no shuffles, no extra pass).
-// Warp roles: warps 0-3 gather + epilogue (thread == TMEM lane), warp 4 weight TMA, warp 5
-// MMA issue + TMEM allocation.  Persistent CTAs, static tile round-robin.
+// One launch per SA / FP / voting stage, persistent CTAs (one per SM), 128-row tiles
+// (row = (query point, sample)), warp-specialised and software-pipelined:
+//
+//   warps 4-7  GATHER   build the layer-1 operand of tile t+1, t+2, ... straight in shared memory
+//                       in the tcgen05 K-major SWIZZLE_128B layout while tile t is still being
+//                       computed: channel-last bf16 feature rows fetched by `idx` with 16-byte
+//                       cp.async through an A-ring of 16 KB stages (several groups in flight per
+//                       thread; the grouped tensor never exists in HBM); the relative,
+//                       radius-normalised xyz (+ fp32 scalar features) form one extra 16-wide K
+//                       step whose dependent loads (idx -> xyz) are prefetched one tile ahead.
+//   warp 9     WEIGHTS  pre-swizzled bf16 weight images by TMA bulk copy (cp.async.bulk): as many
+//                       pieces as fit stay PINNED in shared memory for the whole kernel, the rest
+//                       stream through an mbarrier ring.
+//   warp 8     MMA      one thread issues tcgen05.mma (bf16 x bf16 -> fp32 in TMEM).  Two tile
+//                       contexts (A, B) ping-pong: while the epilogue warps drain layer l of tile
+//                       A the tensor core runs layer l of tile B, so neither side waits for the
+//                       other's latency chain.
+//   warps 0-3  EPILOGUE thread == TMEM lane.  Hidden layers: tcgen05.ld -> +bias (shared memory)
+//                       -> ReLU fused into cvt.rn.relu.bf16x2 -> swizzled shared memory = the next
+//                       layer's operand.  Last layer, pooled stages (S > 1): evaluated TRANSPOSED
+//                       (D^T = W . H^T) so a lane is an output channel and the nsample rows of a
+//                       point are consecutive TMEM columns: the max-pool is an in-register
+//                       reduction.  Last layer, S == 1: plain orientation (lane == row), so both
+//                       the channel-first f32 and the channel-last bf16 outputs store coalesced.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "sad_common.cuh"
@@ -26,16 +36,23 @@ namespace {
 
 using namespace sad;
 
-constexpr int kWorkers = 128;
-constexpr int kThreads = 192;
+constexpr int kEpi = 128;                // epilogue threads (warps 0-3)
+constexpr int kGather = 128;             // gather threads   (warps 4-7)
+constexpr int kThreads = 320;            // + MMA warp (8) + weight-TMA warp (9)
 constexpr int kChunkBytes = 128 * 128;   // one 128-row x 64-bf16 K chunk (A operand / activations)
 constexpr int kMaxLayers = 3;
-constexpr int kMaxSlots = 8;
+constexpr int kMaxA = 8;                 // A-ring stages
+constexpr int kMaxPin = 32;              // pinned weight pieces
+constexpr int kMaxRing = 8;              // streamed weight ring slots
+constexpr int kBiasPad = 544;            // floats per layer in the shared bias table
+constexpr int kMiscBytes = 12288;
+constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 
 struct MlpParams {
-  int B, N, P, S;
+  int B, N, P, S, log2S;
   long long total_rows;
   int num_tiles;
+  uint32_t total_points;
   const __nv_bfloat16* feat_cl;   // (B,N,C0) channel-last source gathered by idx (or identity)
   int C0;
   const __nv_bfloat16* feat2_cl;  // (B,P,C1in) rows aligned with the output points (S == 1)
@@ -57,15 +74,42 @@ struct MlpParams {
   int last_relu;
   __nv_bfloat16* out_cl;          // (B,P,c_last) bf16 or null
   float* out_cf;                  // (B,c_last,P) f32 or null
-  int slot_bytes, nst, rw, act_chunks, steps_per_tile;
+  // ---- plan (host)
+  int transposed;                 // last layer evaluated transposed (S > 1)
+  int nslot;                      // tile contexts in flight (2 = ping-pong)
+  int na;                         // A-ring stages
+  int depth;                      // cp.async groups in flight per gather thread
+  int act_chunks;                 // 16 KB chunks per activation buffer (hidden_max / 64)
+  int region_cols;                // TMEM columns per tile context
+  int tmem_cols;                  // TMEM allocation (power of two)
+  int nblk;                       // 128-channel blocks of a transposed last layer
+  int cpad_last;                  // plain last layer: c_last rounded up to 32
+  int piece_bytes[kMaxLayers];    // weight piece size per layer
+  int pieces[kMaxLayers];         // pieces per tile per layer
+  int first_piece[kMaxLayers];    // running piece index of the layer's first piece
+  int pin_off[kMaxLayers];        // byte offset of the layer's first piece inside the pinned area
+  int n_pieces, n_pinned, pinned_bytes, nr, ring_slot_bytes;
 };
+
+struct Misc {
+  uint64_t afull[kMaxA], afree[kMaxA];
+  uint64_t wpin[kMaxPin];
+  uint64_t wfull[kMaxRing], wfree[kMaxRing];
+  uint64_t dfull[2][5], actfull[2];
+  uint32_t tmem_base, pad_;
+  uint32_t src[2][128];
+  alignas(16) float bias[kMaxLayers][kBiasPad];
+};
+static_assert(sizeof(Misc) <= kMiscBytes, "misc area too small");
 
 // ----------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -98,12 +142,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 __device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
@@ -111,350 +154,500 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// bf16x2 of (max(lo,0), max(hi,0)): the ReLU rides on the conversion
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 // byte offset of (row, 16-byte unit) inside a 128-row x 128-byte SWIZZLE_128B chunk
 __device__ __forceinline__ uint32_t swz(int row, int unit) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((unit ^ (row & 7)) << 4));
 }
 
-// emit the pooled / plain outputs held by one thread (= output channel `ch`) for the 32
-// consecutive rows starting at global row R0 (all rows of one tile share S).
+// ---- pooled outputs of one thread (= output channel `ch`) for the 32 consecutive rows held in v
 template <int S>
-__device__ __forceinline__ void emit_group(const MlpParams& p, const uint32_t (&v)[32], float& run, int ch,
-                                           int c_last, float bias, long long R0, bool ch_ok) {
-  if (S >= 32) {
+__device__ __forceinline__ void emit_group(const MlpParams& p, const uint32_t (&v)[32], float& run, int g, int ch,
+                                           int c_last, float bias, uint32_t pt0, uint32_t b0, uint32_t j0,
+                                           bool ch_ok) {
+  auto store = [&](uint32_t q, float m) {       // q = point index inside the tile
+    const uint32_t pt = pt0 + q;
+    if (!ch_ok || pt >= p.total_points) return;
+    uint32_t b = b0, j = j0 + q;
+    while (j >= (uint32_t)p.P) {
+      j -= (uint32_t)p.P;
+      ++b;
+    }
+    float y = m + bias;
+    if (p.last_relu) y = fmaxf(y, 0.f);
+    if (p.out_cf) p.out_cf[((size_t)b * c_last + ch) * p.P + j] = y;
+    if (p.out_cl) p.out_cl[(size_t)pt * c_last + ch] = __float2bfloat16_rn(y);
+  };
+  if constexpr (S >= 32) {
     float m = __uint_as_float(v[0]);
 #pragma unroll
     for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-    const bool first = ((R0 % S) == 0);
-    run = first ? m : fmaxf(run, m);
-    if (((R0 + 32) % S) == 0 && ch_ok && R0 < p.total_rows) {
-      const long long pt = R0 / S;
-      float y = run + bias;
-      if (p.last_relu) y = fmaxf(y, 0.f);
-      if (p.out_cf) {
-        const long long b = pt / p.P, j = pt % p.P;
-        p.out_cf[(b * c_last + ch) * p.P + j] = y;
-      }
-      if (p.out_cl) p.out_cl[pt * c_last + ch] = __float2bfloat16_rn(y);
-    }
+    constexpr int GP = S / 32;                  // 32-column groups per point
+    run = (g % GP == 0) ? m : fmaxf(run, m);
+    if (g % GP == GP - 1) store((uint32_t)(g / GP), run);
   } else {
 #pragma unroll
-    for (int g = 0; g < 32 / S; ++g) {
-      float m = __uint_as_float(v[g * S]);
+    for (int q = 0; q < 32 / S; ++q) {
+      float m = __uint_as_float(v[q * S]);
 #pragma unroll
-      for (int i = 1; i < S; ++i) m = fmaxf(m, __uint_as_float(v[g * S + i]));
-      const long long R = R0 + (long long)g * S;
-      if (ch_ok && R < p.total_rows) {
-        const long long pt = R / S;
-        float y = m + bias;
-        if (p.last_relu) y = fmaxf(y, 0.f);
-        if (p.out_cf) {
-          const long long b = pt / p.P, j = pt % p.P;
-          p.out_cf[(b * c_last + ch) * p.P + j] = y;
-        }
-        if (p.out_cl) p.out_cl[pt * c_last + ch] = __float2bfloat16_rn(y);
-      }
+      for (int i = 1; i < S; ++i) m = fmaxf(m, __uint_as_float(v[q * S + i]));
+      store((uint32_t)(g * (32 / S) + q), m);
     }
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const MlpParams p) {
+__global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_constant__ MlpParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B atoms need 1024-B alignment
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   // carve-up (all offsets multiples of 1024)
-  const uint32_t a_stage = base;                                     // 2 x 16 KB gather stages
-  const uint32_t w_ring = a_stage + 2 * kChunkBytes;                 // nst x slot_bytes weight ring
-  const uint32_t act = w_ring + (uint32_t)p.nst * p.slot_bytes;      // act_chunks x 16 KB activations
-  uint8_t* misc = gbase + (act - base) + (size_t)p.act_chunks * kChunkBytes;
-  uint64_t* wfull = reinterpret_cast<uint64_t*>(misc);               // [kMaxSlots]
-  uint64_t* wfree = wfull + kMaxSlots;                               // [kMaxSlots]
-  uint64_t* afull = wfree + kMaxSlots;                               // [2]
-  uint64_t* afree = afull + 2;                                       // [2]
-  uint64_t* dfull = afree + 2;                                       // [1]
-  uint64_t* actfull = dfull + 1;                                     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(actfull + 1);
-  long long* s_src = reinterpret_cast<long long*>(tmem_slot + 2);    // [128] source row (b*N + id) or -1
+  const uint32_t off_a = 0;
+  const uint32_t off_act = off_a + (uint32_t)p.na * kChunkBytes;
+  const uint32_t off_pin = off_act + (uint32_t)(p.nslot * p.act_chunks) * kChunkBytes;
+  const uint32_t off_ring = off_pin + (uint32_t)p.pinned_bytes;
+  const uint32_t off_misc = off_ring + (uint32_t)(p.nr * p.ring_slot_bytes);
+  Misc* ms = reinterpret_cast<Misc*>(gbase + off_misc);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nl = p.n_layers;
   const int c_last = p.c[nl - 1];
-  const int nblk = (c_last + 127) / 128;
   const int chunks0 = p.kpad[0] / 64;
-  const bool resident = p.steps_per_tile <= p.nst;
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (tid == 0) {
-    for (int i = 0; i < kMaxSlots; ++i) {
-      mbar_init(&wfull[i], 1);
-      mbar_init(&wfree[i], 1);
+    for (int i = 0; i < kMaxA; ++i) {
+      mbar_init(&ms->afull[i], kGather);
+      mbar_init(&ms->afree[i], 1);
+    }
+    for (int i = 0; i < kMaxPin; ++i) mbar_init(&ms->wpin[i], 1);
+    for (int i = 0; i < kMaxRing; ++i) {
+      mbar_init(&ms->wfull[i], 1);
+      mbar_init(&ms->wfree[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&afull[i], kWorkers);
-      mbar_init(&afree[i], 1);
+      for (int k = 0; k < 5; ++k) mbar_init(&ms->dfull[i][k], 1);   // [0] hidden / plain last, [1+blk] transposed blocks
+      mbar_init(&ms->actfull[i], kEpi);
     }
-    mbar_init(dfull, 1);
-    mbar_init(actfull, kWorkers);
     mbar_fence_init();
   }
-  if (warp == 5) {   // TMEM allocation: one warp, power-of-two columns
-    const uint32_t ncols = (uint32_t)(2 * p.rw);
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(ncols)
+  if (warp == 8) {   // TMEM allocation: one warp, power-of-two columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ms->tmem_base)),
+                 "r"((uint32_t)p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int li = 0; li < nl; ++li)     // bias table (zero padded)
+    for (int c = tid; c < kBiasPad; c += kThreads) ms->bias[li][c] = (c < p.c[li]) ? __ldg(p.bias[li] + c) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&ms->tmem_base);
 
-  if (warp == 4) {
+  if (warp == 9) {
     // ================================================================== weight TMA producer
     if (lane == 0) {
-      long long gs = 0;
-      int iter = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
-        if (resident && iter > 0) break;
-        for (int li = 0; li < nl; ++li) {
-          const bool last = (li == nl - 1);
-          const int pieces = last ? nblk * (p.kpad[li] / 64) : (p.kpad[li] / 64);
-          const uint32_t bytes = last ? (uint32_t)kChunkBytes : (uint32_t)p.c[li] * 128u;
-          for (int pc = 0; pc < pieces; ++pc, ++gs) {
-            const int slot = (int)(gs % p.nst);
-            const long long use = gs / p.nst;
-            if (use > 0) mbar_wait(&wfree[slot], (uint32_t)((use - 1) & 1));
-            mbar_arrive_expect_tx(&wfull[slot], bytes);
-            tma_bulk_g2s(gbase + (w_ring - base) + (size_t)slot * p.slot_bytes, p.w_img[li] + (size_t)pc * bytes, bytes,
-                         &wfull[slot]);
-          }
+      for (int li = 0; li < nl; ++li)
+        for (int i = 0; i < p.pieces[li]; ++i) {
+          const int pc = p.first_piece[li] + i;
+          if (pc >= p.n_pinned) break;
+          const uint32_t bytes = (uint32_t)p.piece_bytes[li];
+          mbar_arrive_expect_tx(&ms->wpin[pc], bytes);
+          tma_bulk_g2s(gbase + off_pin + p.pin_off[li] + (size_t)i * bytes, p.w_img[li] + (size_t)i * bytes, bytes,
+                       &ms->wpin[pc]);
+        }
+      if (p.n_pinned < p.n_pieces) {
+        uint32_t cnt = 0;
+        for (int t0 = 0; t0 < my_tiles; t0 += p.nslot) {
+          const int ns = min(p.nslot, my_tiles - t0);
+          for (int li = 0; li < nl; ++li)
+            for (int s = 0; s < ns; ++s)
+              for (int i = 0; i < p.pieces[li]; ++i) {
+                if (p.first_piece[li] + i < p.n_pinned) continue;
+                const uint32_t r = cnt % (uint32_t)p.nr, use = cnt / (uint32_t)p.nr;
+                if (use > 0) mbar_wait(&ms->wfree[r], (use - 1) & 1u);
+                const uint32_t bytes = (uint32_t)p.piece_bytes[li];
+                mbar_arrive_expect_tx(&ms->wfull[r], bytes);
+                tma_bulk_g2s(gbase + off_ring + (size_t)r * p.ring_slot_bytes, p.w_img[li] + (size_t)i * bytes, bytes,
+                             &ms->wfull[r]);
+                ++cnt;
+              }
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 8) {
     // ================================================================== MMA issuer
     if (lane == 0) {
-      long long gs = 0, ga = 0;
-      uint32_t acount = 0;
-      int iter = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
-        const bool wsync = !(resident && iter > 0);
-        if (resident) gs = 0;
+      uint32_t a_cnt = 0, w_cnt = 0;
+      uint32_t act_cnt[2] = {0, 0};
+      // weights of piece (li, i): pinned address or the next ring slot; returns the smem address
+      auto weights = [&](int li, int i, bool& streamed, uint32_t& slot) -> uint32_t {
+        const int pc = p.first_piece[li] + i;
+        if (pc < p.n_pinned) {
+          mbar_wait(&ms->wpin[pc], 0);
+          streamed = false;
+          return base + off_pin + (uint32_t)p.pin_off[li] + (uint32_t)i * (uint32_t)p.piece_bytes[li];
+        }
+        slot = w_cnt % (uint32_t)p.nr;
+        mbar_wait(&ms->wfull[slot], (w_cnt / (uint32_t)p.nr) & 1u);
+        ++w_cnt;
+        streamed = true;
+        return base + off_ring + slot * (uint32_t)p.ring_slot_bytes;
+      };
+      for (int t0 = 0; t0 < my_tiles; t0 += p.nslot) {
+        const int ns = min(p.nslot, my_tiles - t0);
         for (int li = 0; li < nl; ++li) {
           const bool last = (li == nl - 1);
           const int chunks = p.kpad[li] / 64;
-          if (li > 0) {   // previous epilogue has written ACT and drained its TMEM region
-            mbar_wait(actfull, acount & 1);
-            ++acount;
-            tc_fence_after();
-          }
-          if (!last) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)((li & 1) * p.rw);
-            const uint32_t idesc = umma_idesc(128, p.c[li]);
-            for (int kc = 0; kc < chunks; ++kc, ++gs) {
-              const int slot = (int)(gs % p.nst);
-              uint32_t a_addr;
-              int ksteps = 4;
-              if (li == 0) {
-                const int stage = (int)(ga & 1);
-                mbar_wait(&afull[stage], (uint32_t)((ga >> 1) & 1));
-                a_addr = a_stage + stage * kChunkBytes;
-                if (p.has_special && kc == chunks - 1) ksteps = 1;
-              } else {
-                a_addr = act + kc * kChunkBytes;
-              }
-              if (wsync) mbar_wait(&wfull[slot], (uint32_t)((gs / p.nst) & 1));
-              tc_fence_after();
-              const uint32_t b_addr = w_ring + slot * p.slot_bytes;
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc,
-                          (kc > 0 || k > 0) ? 1u : 0u);
-              if (li == 0) {
-                umma_commit(&afree[ga & 1]);
-                ++ga;
-              }
-              if (wsync && !resident) umma_commit(&wfree[slot]);
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            if (s >= ns) break;
+            // the context's TMEM region / activation buffer must have been drained by the epilogue of
+            // the previous layer (li > 0) or of the previous tile in this context (li == 0)
+            if (li > 0 || t0 > 0) {
+              mbar_wait(&ms->actfull[s], act_cnt[s] & 1u);
+              ++act_cnt[s];
             }
-            umma_commit(dfull);
-          } else {
-            const uint32_t idesc = umma_idesc(128, 128);
-            for (int blk = 0; blk < nblk; ++blk) {
-              if (blk > 0) {   // v1: one output block in flight
-                mbar_wait(actfull, acount & 1);
-                ++acount;
+            tc_fence_after();
+            const uint32_t region = tmem_base + (uint32_t)(s * p.region_cols);
+            const uint32_t act_s = base + off_act + (uint32_t)(s * p.act_chunks) * kChunkBytes;
+            if (!(last && p.transposed)) {
+              // D (128 rows x N) = A (rows x K) . W^T ; N = layer width (plain last layer: cpad, split at 256)
+              const int ncols = last ? p.cpad_last : p.c[li];
+              for (int kc = 0; kc < chunks; ++kc) {
+                uint32_t a_addr;
+                int ksteps = 4;
+                uint32_t stage = 0;
+                if (li == 0) {
+                  stage = a_cnt % (uint32_t)p.na;
+                  mbar_wait(&ms->afull[stage], (a_cnt / (uint32_t)p.na) & 1u);
+                  a_addr = base + off_a + stage * kChunkBytes;
+                  if (p.has_special && kc == chunks - 1) ksteps = 1;
+                } else {
+                  a_addr = act_s + (uint32_t)kc * kChunkBytes;
+                }
+                bool streamed;
+                uint32_t slot = 0;
+                const uint32_t b_addr = weights(li, kc, streamed, slot);
                 tc_fence_after();
+                for (int n0 = 0; n0 < ncols; n0 += 256) {
+                  const int nn = min(256, ncols - n0);
+                  const uint32_t idesc = umma_idesc(128, nn);
+                  for (int k = 0; k < ksteps; ++k)
+                    umma_bf16(region + (uint32_t)n0, umma_desc(a_addr + k * 32),
+                              umma_desc(b_addr + (uint32_t)n0 * 128u + k * 32), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                }
+                if (li == 0) {
+                  umma_commit(&ms->afree[stage]);
+                  ++a_cnt;
+                }
+                if (streamed) umma_commit(&ms->wfree[slot]);
               }
-              const uint32_t d_tmem = tmem_base + (uint32_t)((blk & 1) * p.rw);
-              for (int kc = 0; kc < chunks; ++kc, ++gs) {
-                const int slot = (int)(gs % p.nst);
-                if (wsync) mbar_wait(&wfull[slot], (uint32_t)((gs / p.nst) & 1));
-                tc_fence_after();
-                const uint32_t a_addr = w_ring + slot * p.slot_bytes;     // W_last block rows = M
-                const uint32_t b_addr = act + kc * kChunkBytes;           // activations rows = N
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc,
-                            (kc > 0 || k > 0) ? 1u : 0u);
-                if (wsync && !resident) umma_commit(&wfree[slot]);
+              umma_commit(&ms->dfull[s][0]);
+            } else {
+              // transposed last layer: D^T (128 channels x 128 rows) = W_blk . H^T, one commit per block
+              const uint32_t idesc = umma_idesc(128, 128);
+              for (int blk = 0; blk < p.nblk; ++blk) {
+                for (int kc = 0; kc < chunks; ++kc) {
+                  bool streamed;
+                  uint32_t slot = 0;
+                  const uint32_t a_addr = weights(li, blk * chunks + kc, streamed, slot);   // W block rows = M
+                  const uint32_t b_addr = act_s + (uint32_t)kc * kChunkBytes;               // activations rows = N
+                  tc_fence_after();
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(region + (uint32_t)(blk * 128), umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32),
+                              idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                  if (streamed) umma_commit(&ms->wfree[slot]);
+                }
+                umma_commit(&ms->dfull[s][1 + blk]);    // one barrier per block: never two phases outstanding
               }
-              umma_commit(dfull);
             }
           }
         }
-        // last block's epilogue must drain TMEM / ACT before the next tile's layer 1 reuses them
-        mbar_wait(actfull, acount & 1);
-        ++acount;
-        tc_fence_after();
       }
     }
-  } else {
-    // ================================================================== gather + epilogue workers
-    long long ga = 0;
-    uint32_t dcount = 0;
-    const int unit = tid & 7;
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const long long R0 = (long long)tile * 128;
-      // ---- per-row source bookkeeping (thread t <-> row t)
-      {
-        const long long R = R0 + tid;
-        long long src = -1;
-        if (R < p.total_rows) {
-          const long long pt = R / p.S;
-          const long long b = pt / p.P;
-          const long long id = p.idx ? (long long)__ldg(p.idx + R) : (pt % p.P);
-          src = b * p.N + id;
-        }
-        s_src[tid] = src;
-      }
-      named_bar_sync(1, kWorkers);
+  } else if (warp >= 4) {
+    // ================================================================== gather producers
+    const int gt = tid - kEpi;                 // row of the tile this thread owns for bookkeeping / special chunk
+    const int unit = gt & 7, rbase = gt >> 3;
+    const int nf0 = p.C0 / 64, nf1 = p.C1in / 64;
+    uint32_t a_cnt = 0;
+    int pend = 0;
+    uint32_t ps0 = 0, ps1 = 0, ps2 = 0;        // stages of the cp.async groups still in flight (oldest first)
 
-      // ---- layer-1 operand chunks
-      for (int kc = 0; kc < chunks0; ++kc, ++ga) {
-        const int stage = (int)(ga & 1);
-        if (ga >= 2) mbar_wait(&afree[stage], (uint32_t)(((ga >> 1) - 1) & 1));
-        const uint32_t dst = a_stage + stage * kChunkBytes;
-        const int nf0 = p.C0 / 64, nf1 = p.C1in / 64;
-        if (kc < nf0) {
+    struct Special {
+      float x, y, z, qx, qy, qz, r, e[4];
+    };
+    auto load_src = [&](int it) -> uint32_t {
+      if (it >= my_tiles) return kNoRow;
+      const long long R = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + gt;
+      if (R >= p.total_rows) return kNoRow;
+      const uint32_t pt = (uint32_t)(R >> p.log2S);
+      const uint32_t b = pt / (uint32_t)p.P;
+      const uint32_t id = p.idx ? (uint32_t)__ldg(p.idx + R) : (pt - b * (uint32_t)p.P);
+      return b * (uint32_t)p.N + id;
+    };
+    auto load_special = [&](uint32_t src, int it, Special& s) {
+      s.x = s.y = s.z = s.qx = s.qy = s.qz = 0.f;
+      s.r = 1.f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = (tid >> 3) + 16 * i;
-            const long long src = s_src[r];
-            const __nv_bfloat16* g = p.feat_cl + (src < 0 ? 0 : src) * p.C0 + kc * 64 + unit * 8;
-            cp_async16(dst + swz(r, unit), g, src < 0 ? 0u : 16u);
+      for (int e = 0; e < 4; ++e) s.e[e] = 0.f;
+      if (src == kNoRow || !p.has_special) return;
+      const long long R = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + gt;
+      const uint32_t pt = (uint32_t)(R >> p.log2S);
+      if (p.xyz) {
+        const float* a = p.xyz + (size_t)src * 3;
+        const float* q = p.new_xyz + (size_t)pt * 3;
+        s.x = __ldg(a);
+        s.y = __ldg(a + 1);
+        s.z = __ldg(a + 2);
+        s.qx = __ldg(q);
+        s.qy = __ldg(q + 1);
+        s.qz = __ldg(q + 2);
+        if (p.normalize) s.r = p.radius_t ? __ldg(p.radius_t + pt) : p.radius;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (e < p.E) s.e[e] = __ldg(p.extra + (size_t)src * p.E + e);
+    };
+    auto retire_oldest = [&]() {               // oldest cp.async group has landed: publish its stage
+      fence_proxy_async();
+      mbar_arrive(&ms->afull[ps0]);
+      ps0 = ps1;
+      ps1 = ps2;
+      --pend;
+    };
+
+    uint32_t src_cur = load_src(0), src_nxt = load_src(1);
+    Special sp_cur;
+    load_special(src_cur, 0, sp_cur);
+    for (int it = 0; it < my_tiles; ++it) {
+      const long long R0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128;
+      uint32_t* s_src = ms->src[it & 1];
+      s_src[gt] = src_cur;
+      named_bar_sync(1, kGather);
+      const uint32_t src_nn = load_src(it + 2);           // issued two tiles ahead
+      Special sp_nxt;
+      load_special(src_nxt, it + 1, sp_nxt);              // issued one tile ahead
+      for (int kc = 0; kc < chunks0; ++kc, ++a_cnt) {
+        const uint32_t stage = a_cnt % (uint32_t)p.na;
+        if (a_cnt >= (uint32_t)p.na) mbar_wait(&ms->afree[stage], ((a_cnt / (uint32_t)p.na) - 1) & 1u);
+        const uint32_t dst = base + off_a + stage * kChunkBytes;
+        if (kc < nf0 + nf1) {
+          if (kc < nf0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = rbase + 16 * i;
+              const uint32_t src = s_src[r];
+              const __nv_bfloat16* g = p.feat_cl + (size_t)(src == kNoRow ? 0u : src) * p.C0 + kc * 64 + unit * 8;
+              cp_async16(dst + swz(r, unit), g, src == kNoRow ? 0u : 16u);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = rbase + 16 * i;
+              const long long R = R0 + r;
+              const bool ok = R < p.total_rows;
+              const __nv_bfloat16* g = p.feat2_cl + (size_t)(ok ? R : 0) * p.C1in + (kc - nf0) * 64 + unit * 8;
+              cp_async16(dst + swz(r, unit), g, ok ? 16u : 0u);
+            }
           }
-        } else if (kc < nf0 + nf1) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = (tid >> 3) + 16 * i;
-            const long long R = R0 + r;
-            const bool ok = R < p.total_rows;
-            const __nv_bfloat16* g = p.feat2_cl + (ok ? R : 0) * p.C1in + (kc - nf0) * 64 + unit * 8;
-            cp_async16(dst + swz(r, unit), g, ok ? 16u : 0u);
+          cp_async_commit();
+          if (pend == 0) ps0 = stage;
+          else if (pend == 1) ps1 = stage;
+          else ps2 = stage;
+          ++pend;
+          if (pend == p.depth) {
+            if (p.depth == 3) cp_async_wait<2>();
+            else if (p.depth == 2) cp_async_wait<1>();
+            else cp_async_wait<0>();
+            retire_oldest();
           }
         } else {
           // special 16-wide K step: [dx, dy, dz, extras..., 0]
           float vals[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) vals[i] = 0.f;
-          const long long src = s_src[tid];
-          if (src >= 0) {
-            const long long pt = (R0 + tid) / p.S;
+          if (src_cur != kNoRow) {
             if (p.xyz) {
-              const float* a = p.xyz + src * 3;
-              const float* q = p.new_xyz + pt * 3;
-              float dx = __fsub_rn(__ldg(a), __ldg(q)), dy = __fsub_rn(__ldg(a + 1), __ldg(q + 1)),
-                    dz = __fsub_rn(__ldg(a + 2), __ldg(q + 2));
+              float dx = __fsub_rn(sp_cur.x, sp_cur.qx), dy = __fsub_rn(sp_cur.y, sp_cur.qy),
+                    dz = __fsub_rn(sp_cur.z, sp_cur.qz);
               if (p.normalize) {
-                const float r = p.radius_t ? __ldg(p.radius_t + pt) : p.radius;
-                dx = __fdiv_rn(dx, r);
-                dy = __fdiv_rn(dy, r);
-                dz = __fdiv_rn(dz, r);
+                dx = __fdiv_rn(dx, sp_cur.r);
+                dy = __fdiv_rn(dy, sp_cur.r);
+                dz = __fdiv_rn(dz, sp_cur.r);
               }
               vals[0] = dx;
               vals[1] = dy;
               vals[2] = dz;
             }
 #pragma unroll
-            for (int e = 0; e < 13; ++e)
-              if (e < p.E) vals[3 + e] = __ldg(p.extra + src * p.E + e);
+            for (int e = 0; e < 4; ++e) vals[3 + e] = sp_cur.e[e];
+#pragma unroll
+            for (int e = 4; e < 13; ++e)
+              if (e < p.E) vals[3 + e] = __ldg(p.extra + (size_t)src_cur * p.E + e);   // rare
           }
-          st_shared_v4(dst + swz(tid, 0), pack_bf16(vals[0], vals[1]), pack_bf16(vals[2], vals[3]),
+          st_shared_v4(dst + swz(gt, 0), pack_bf16(vals[0], vals[1]), pack_bf16(vals[2], vals[3]),
                        pack_bf16(vals[4], vals[5]), pack_bf16(vals[6], vals[7]));
-          st_shared_v4(dst + swz(tid, 1), pack_bf16(vals[8], vals[9]), pack_bf16(vals[10], vals[11]),
+          st_shared_v4(dst + swz(gt, 1), pack_bf16(vals[8], vals[9]), pack_bf16(vals[10], vals[11]),
                        pack_bf16(vals[12], vals[13]), pack_bf16(vals[14], vals[15]));
+          fence_proxy_async();
+          mbar_arrive(&ms->afull[stage]);
         }
-        cp_async_wait_all();
-        fence_proxy_async();
-        mbar_arrive(&afull[stage]);
       }
-
-      // ---- hidden-layer epilogues: TMEM -> +bias, ReLU -> bf16 -> ACT (thread == row)
-      for (int li = 0; li < nl - 1; ++li) {
-        mbar_wait(dfull, dcount & 1);
-        ++dcount;
-        tc_fence_after();
-        const uint32_t d_tmem = lane_taddr + (uint32_t)((li & 1) * p.rw);
-        const float* bias = p.bias[li];
-        for (int c0 = 0; c0 < p.c[li]; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(d_tmem + c0, v);
-          uint32_t pk[16];
+      src_cur = src_nxt;
+      src_nxt = src_nn;
+      sp_cur = sp_nxt;
+    }
+    cp_async_wait<0>();
+    while (pend > 0) retire_oldest();
+  } else {
+    // ================================================================== epilogue warps (thread == TMEM lane)
+    uint32_t d_cnt[2] = {0, 0};      // uses of dfull[s][0]
+    uint32_t t_cnt[2] = {0, 0};      // tiles finished in context s (= uses of each dfull[s][1+blk])
+    const uint32_t lane_t = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int t0 = 0; t0 < my_tiles; t0 += p.nslot) {
+      const int ns = min(p.nslot, my_tiles - t0);
+      for (int li = 0; li < nl; ++li) {
+        const bool last = (li == nl - 1);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float lo = fmaxf(__uint_as_float(v[2 * i]) + __ldg(bias + c0 + 2 * i), 0.f);
-            const float hi = fmaxf(__uint_as_float(v[2 * i + 1]) + __ldg(bias + c0 + 2 * i + 1), 0.f);
-            pk[i] = pack_bf16(lo, hi);
-          }
-          const uint32_t chunk = act + (c0 >> 6) * kChunkBytes;
-          const int u0 = (c0 & 63) >> 3;
+        for (int s = 0; s < 2; ++s) {
+          if (s >= ns) break;
+          const uint32_t region = lane_t + (uint32_t)(s * p.region_cols);
+          const uint32_t act_s = base + off_act + (uint32_t)(s * p.act_chunks) * kChunkBytes;
+          const long long tile = (long long)blockIdx.x + (long long)(t0 + s) * gridDim.x;
+          if (!last) {
+            // ---- hidden layer: TMEM -> +bias -> ReLU -> bf16 -> swizzled ACT (next layer's operand)
+            mbar_wait(&ms->dfull[s][0], d_cnt[s] & 1u);
+            ++d_cnt[s];
+            tc_fence_after();
+            const float* sb = ms->bias[li];
+            for (int c0 = 0; c0 < p.c[li]; c0 += 64) {
+              uint32_t v0[32], v1[32];
+              tmem_ld32_issue(region + (uint32_t)c0, v0);
+              tmem_ld32_issue(region + (uint32_t)c0 + 32u, v1);
+              tmem_ld_wait();
+              const uint32_t chunk = act_s + (uint32_t)(c0 >> 6) * kChunkBytes;
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            st_shared_v4(chunk + swz(tid, u0 + u), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(actfull);
-      }
-
-      // ---- last layer (transposed): thread == output channel, columns == rows; pool over S
-      for (int blk = 0; blk < nblk; ++blk) {
-        mbar_wait(dfull, dcount & 1);
-        ++dcount;
-        tc_fence_after();
-        const uint32_t d_tmem = lane_taddr + (uint32_t)((blk & 1) * p.rw);
-        const int ch = blk * 128 + tid;
-        const bool ch_ok = ch < c_last;
-        const float bias = ch_ok ? __ldg(p.bias[nl - 1] + ch) : 0.f;
-        float run = 0.f;
-        for (int g = 0; g < 4; ++g) {
-          uint32_t v[32];
-          tmem_ld32(d_tmem + g * 32, v);
-          const long long Rg = R0 + g * 32;
-          switch (p.S) {
-            case 1: emit_group<1>(p, v, run, ch, c_last, bias, Rg, ch_ok); break;
-            case 2: emit_group<2>(p, v, run, ch, c_last, bias, Rg, ch_ok); break;
-            case 4: emit_group<4>(p, v, run, ch, c_last, bias, Rg, ch_ok); break;
-            case 8: emit_group<8>(p, v, run, ch, c_last, bias, Rg, ch_ok); break;
-            case 16: emit_group<16>(p, v, run, ch, c_last, bias, Rg, ch_ok); break;
-            case 32: emit_group<32>(p, v, run, ch, c_last, bias, Rg, ch_ok); break;
-            case 64: emit_group<64>(p, v, run, ch, c_last, bias, Rg, ch_ok); break;
-            default: emit_group<128>(p, v, run, ch, c_last, bias, Rg, ch_ok); break;
+              for (int u = 0; u < 8; ++u) {
+                const uint32_t* v = (u < 4) ? v0 : v1;
+                const int o = (u & 3) * 8;
+                const float4 ba = *reinterpret_cast<const float4*>(sb + c0 + u * 8);
+                const float4 bb = *reinterpret_cast<const float4*>(sb + c0 + u * 8 + 4);
+                st_shared_v4(chunk + swz(tid, u),
+                             pack_bf16_relu(__uint_as_float(v[o + 0]) + ba.x, __uint_as_float(v[o + 1]) + ba.y),
+                             pack_bf16_relu(__uint_as_float(v[o + 2]) + ba.z, __uint_as_float(v[o + 3]) + ba.w),
+                             pack_bf16_relu(__uint_as_float(v[o + 4]) + bb.x, __uint_as_float(v[o + 5]) + bb.y),
+                             pack_bf16_relu(__uint_as_float(v[o + 6]) + bb.z, __uint_as_float(v[o + 7]) + bb.w));
+              }
+            }
+            fence_proxy_async();
+          } else if (p.transposed) {
+            // ---- last layer, transposed: thread == output channel, columns == rows; pool over S
+            const uint32_t npt = 128u >> p.log2S;
+            const uint32_t pt0 = (uint32_t)tile * npt;
+            const uint32_t b0 = pt0 / (uint32_t)p.P, j0 = pt0 - b0 * (uint32_t)p.P;
+            for (int blk = 0; blk < p.nblk; ++blk) {
+              mbar_wait(&ms->dfull[s][1 + blk], t_cnt[s] & 1u);
+              tc_fence_after();
+              const int ch = blk * 128 + tid;
+              const bool ch_ok = ch < c_last;
+              const float bias = ms->bias[li][ch_ok ? ch : 0];
+              float run = 0.f;
+#pragma unroll 1
+              for (int g = 0; g < 4; g += 2) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32_issue(region + (uint32_t)(blk * 128 + g * 32), v0);
+                tmem_ld32_issue(region + (uint32_t)(blk * 128 + g * 32 + 32), v1);
+                tmem_ld_wait();
+                switch (p.S) {
+#define SAD_EMIT(SS)                                                           \
+  case SS:                                                                     \
+    emit_group<SS>(p, v0, run, g, ch, c_last, bias, pt0, b0, j0, ch_ok);       \
+    emit_group<SS>(p, v1, run, g + 1, ch, c_last, bias, pt0, b0, j0, ch_ok);   \
+    break;
+                  SAD_EMIT(2)
+                  SAD_EMIT(4)
+                  SAD_EMIT(8)
+                  SAD_EMIT(16)
+                  SAD_EMIT(32)
+                  SAD_EMIT(64)
+                  default:
+                    emit_group<128>(p, v0, run, g, ch, c_last, bias, pt0, b0, j0, ch_ok);
+                    emit_group<128>(p, v1, run, g + 1, ch, c_last, bias, pt0, b0, j0, ch_ok);
+                    break;
+#undef SAD_EMIT
+                }
+              }
+            }
+            ++t_cnt[s];
+          } else {
+            // ---- last layer, plain orientation (S == 1): thread == row; both outputs store coalesced
+            mbar_wait(&ms->dfull[s][0], d_cnt[s] & 1u);
+            ++d_cnt[s];
+            tc_fence_after();
+            const long long R = tile * 128 + tid;
+            const bool ok = R < p.total_rows;
+            const uint32_t pt = ok ? (uint32_t)R : 0u;
+            const uint32_t b = pt / (uint32_t)p.P, j = pt - b * (uint32_t)p.P;
+            const float* sb = ms->bias[li];
+            float* ocf = p.out_cf ? p.out_cf + (size_t)b * c_last * p.P + j : nullptr;
+            __nv_bfloat16* ocl = p.out_cl ? p.out_cl + (size_t)pt * c_last : nullptr;
+            const bool vec_cl = (c_last % 8) == 0;
+            for (int c0 = 0; c0 < p.cpad_last; c0 += 32) {
+              uint32_t v[32];
+              tmem_ld32_issue(region + (uint32_t)c0, v);
+              tmem_ld_wait();
+              float y[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                y[i] = __uint_as_float(v[i]) + sb[c0 + i];
+                if (p.last_relu) y[i] = fmaxf(y[i], 0.f);
+              }
+              if (ok) {
+                if (ocf) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (c0 + i < c_last) ocf[(size_t)(c0 + i) * p.P] = y[i];
+                }
+                if (ocl) {
+                  if (vec_cl) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                      if (c0 + u * 8 < c_last)
+                        *reinterpret_cast<uint4*>(ocl + c0 + u * 8) =
+                            make_uint4(pack_bf16(y[u * 8], y[u * 8 + 1]), pack_bf16(y[u * 8 + 2], y[u * 8 + 3]),
+                                       pack_bf16(y[u * 8 + 4], y[u * 8 + 5]), pack_bf16(y[u * 8 + 6], y[u * 8 + 7]));
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                      if (c0 + i < c_last) ocl[c0 + i] = __float2bfloat16_rn(y[i]);
+                  }
+                }
+              }
+            }
           }
+          tc_fence_before();
+          mbar_arrive(&ms->actfull[s]);
         }
-        tc_fence_before();
-        mbar_arrive(actfull);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
-    const uint32_t ncols = (uint32_t)(2 * p.rw);
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
   }
 }
 
@@ -511,25 +704,32 @@ cf_to_cl_kernel(int C, int N, const float* __restrict__ in, __nv_bfloat16* __res
 }  // namespace
 
 // ------------------------------------------------------------------------------ host side
+// Weight image formats (all K-major SWIZZLE_128B, one piece per 64-wide K chunk):
+//   mode 0  hidden layer          piece = cout rows                      (cout % 16 == 0, <= 256)
+//   mode 1  last layer, S  > 1    transposed evaluation: pieces of 128 rows, blocked [blk][kc]
+//   mode 2  last layer, S == 1    plain evaluation: piece = cout rounded up to 32 rows (<= 512)
+static int image_rows(int cout, int mode) { return mode == 1 ? 128 : (mode == 2 ? (cout + 31) / 32 * 32 : cout); }
+
 extern "C" long long sad_mlp_weight_image_bytes(int cout, int kpad, int is_last) {
-  if (cout < 1 || kpad < 64 || (kpad % 64)) return -1;
+  if (cout < 1 || kpad < 64 || (kpad % 64) || is_last < 0 || is_last > 2) return -1;
   const long long chunks = kpad / 64;
-  if (is_last) return (long long)((cout + 127) / 128) * chunks * kChunkBytes;
-  return chunks * (long long)cout * 128;
+  const long long nblk = is_last == 1 ? (cout + 127) / 128 : 1;
+  return nblk * chunks * image_rows(cout, is_last) * 128;
 }
 
 // Host-side packer: fp32 W (cout x cin, row-major) -> bf16 image in the exact shared-memory byte
-// layout the kernel consumes (K-major, SWIZZLE_128B, one piece per 64-wide K chunk; the last
-// layer additionally blocked into 128-row pieces, zero padded).  perm[k] = source column of
-// packed K index k, or -1 for a zero column.
+// layout the kernel consumes.  perm[k] = source column of packed K index k, or -1 for a zero column.
 extern "C" int sad_mlp_pack_weights(const float* W, int cout, int cin, const int32_t* perm, int kpad, int is_last,
                                     void* out_image) {
   SAD_REQUIRE(W && perm && out_image, "mlp_pack_weights: null pointer");
   SAD_REQUIRE(cout >= 1 && cin >= 1 && kpad >= 64 && kpad % 64 == 0, "mlp_pack_weights: bad sizes");
-  SAD_REQUIRE(is_last || (cout % 16 == 0 && cout <= 256), "mlp_pack_weights: hidden width must be a multiple of 16, <= 256");
+  SAD_REQUIRE(is_last >= 0 && is_last <= 2, "mlp_pack_weights: is_last must be 0, 1 (pooled) or 2 (S == 1)");
+  SAD_REQUIRE(is_last != 0 || (cout % 16 == 0 && cout <= 256),
+              "mlp_pack_weights: hidden width must be a multiple of 16, <= 256");
+  SAD_REQUIRE(is_last != 2 || cout <= 512, "mlp_pack_weights: S == 1 last layer supports <= 512 channels");
   const int chunks = kpad / 64;
-  const int rows_per_piece = is_last ? 128 : cout;
-  const int nblk = is_last ? (cout + 127) / 128 : 1;
+  const int rows_per_piece = image_rows(cout, is_last);
+  const int nblk = is_last == 1 ? (cout + 127) / 128 : 1;
   uint16_t* img = static_cast<uint16_t*>(out_image);
   const size_t piece_elems = (size_t)rows_per_piece * 64;
   for (int blk = 0; blk < nblk; ++blk)
@@ -557,6 +757,79 @@ extern "C" int sad_mlp_pack_weights(const float* W, int cout, int cin, const int
   return SAD_OK;
 }
 
+// Shared-memory / TMEM plan of one launch.  Returns false when nothing fits.
+static bool plan_launch(MlpParams& p, int hidden_max, size_t& smem_out) {
+  const int nl = p.n_layers;
+  const int c_last = p.c[nl - 1];
+  p.transposed = p.S > 1 ? 1 : 0;
+  p.nblk = p.transposed ? (c_last + 127) / 128 : 0;
+  p.cpad_last = p.transposed ? 0 : (c_last + 31) / 32 * 32;
+  p.act_chunks = hidden_max / 64;
+  p.region_cols = p.transposed ? (hidden_max > 128 * p.nblk ? hidden_max : 128 * p.nblk)
+                               : (hidden_max > p.cpad_last ? hidden_max : p.cpad_last);
+  if (p.region_cols > 512) return false;
+  int np = 0, max_piece = 0;
+  long long total_w = 0;
+  for (int li = 0; li < nl; ++li) {
+    const bool last = (li == nl - 1);
+    const int chunks = p.kpad[li] / 64;
+    p.piece_bytes[li] = (last ? (p.transposed ? 128 : p.cpad_last) : p.c[li]) * 128;
+    p.pieces[li] = (last && p.transposed) ? p.nblk * chunks : chunks;
+    p.first_piece[li] = np;
+    np += p.pieces[li];
+    total_w += (long long)p.pieces[li] * p.piece_bytes[li];
+    if (p.piece_bytes[li] > max_piece) max_piece = p.piece_bytes[li];
+  }
+  p.n_pieces = np;
+  const long long avail = 227 * 1024 - 1024 - kMiscBytes;
+  // tuning hooks (benchmarks only): cap the tile contexts / A-ring stages, force a minimum weight ring
+  const char* e_slot = getenv("SAD_MLP_NSLOT");
+  const char* e_na = getenv("SAD_MLP_NA");
+  const char* e_nr = getenv("SAD_MLP_NR");
+  const int max_slot = e_slot ? atoi(e_slot) : 2, max_na = e_na ? atoi(e_na) : 4, want_nr = e_nr ? atoi(e_nr) : 2;
+  for (int nslot = (2 * p.region_cols <= 512 && p.num_tiles > 1 && max_slot >= 2) ? 2 : 1; nslot >= 1; --nslot) {
+    const long long act = (long long)nslot * p.act_chunks * kChunkBytes;
+    for (int na = (max_na < 2 ? 2 : (max_na > 4 ? 4 : max_na)); na >= 2; --na) {
+      const long long rest = avail - act - (long long)na * kChunkBytes;
+      if (rest < 0) continue;
+      int n_pinned = 0, nr = 0;
+      long long pinned = 0;
+      if (total_w <= rest && np <= kMaxPin) {
+        n_pinned = np;
+        pinned = total_w;
+      } else {
+        nr = want_nr < 2 ? 2 : (want_nr > kMaxRing ? kMaxRing : want_nr);
+        long long budget = rest - (long long)nr * max_piece;
+        if (budget < 0) continue;
+        for (int li = 0; li < nl && n_pinned == p.first_piece[li]; ++li)
+          for (int i = 0; i < p.pieces[li] && n_pinned < kMaxPin; ++i) {
+            if (pinned + p.piece_bytes[li] > budget) break;
+            pinned += p.piece_bytes[li];
+            ++n_pinned;
+          }
+      }
+      p.nslot = nslot;
+      p.na = na;
+      p.depth = na >= 4 ? 3 : (na == 3 ? 2 : 1);
+      p.n_pinned = n_pinned;
+      p.pinned_bytes = (int)pinned;
+      p.nr = nr;
+      p.ring_slot_bytes = nr ? max_piece : 0;
+      long long off = 0;
+      for (int li = 0; li < nl; ++li) {
+        p.pin_off[li] = (int)off;
+        off += (long long)p.pieces[li] * p.piece_bytes[li];
+      }
+      int cols = nslot * p.region_cols, pow2 = 32;
+      while (pow2 < cols) pow2 <<= 1;
+      p.tmem_cols = pow2;
+      smem_out = (size_t)(1024 + act + (long long)na * kChunkBytes + pinned + (long long)nr * max_piece + kMiscBytes);
+      return true;
+    }
+  }
+  return false;
+}
+
 extern "C" int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_cl, int C0, const void* feat2_cl,
                                   int C1in, const float* xyz, const float* new_xyz, const int32_t* idx, float radius,
                                   const float* radius_t, int normalize_xyz, const float* extra, int E, int n_layers,
@@ -577,19 +850,24 @@ extern "C" int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_c
   const int has_special = (xyz != nullptr || E > 0) ? 1 : 0;
   SAD_REQUIRE(!xyz || new_xyz, "shared_mlp: xyz needs new_xyz");
   SAD_REQUIRE(C0 + C1in + has_special > 0, "shared_mlp: no input");
+  SAD_REQUIRE((long long)B * N < 0x7FFFFFFFLL && (long long)B * P < 0x7FFFFFFFLL, "shared_mlp: B*N and B*P must fit 31 bits");
   if (B == 0 || P == 0) return SAD_OK;
 
   MlpParams p = {};
   p.B = B; p.N = N; p.P = P; p.S = S;
+  for (p.log2S = 0; (1 << p.log2S) < S; ++p.log2S) {}
   p.total_rows = (long long)B * P * S;
-  p.num_tiles = (int)((p.total_rows + 127) / 128);
+  p.total_points = (uint32_t)((long long)B * P);
+  const long long tiles = (p.total_rows + 127) / 128;
+  SAD_REQUIRE(tiles < 0x7FFFFFFFLL, "shared_mlp: too many rows");
+  p.num_tiles = (int)tiles;
   p.feat_cl = static_cast<const __nv_bfloat16*>(feat_cl); p.C0 = C0;
   p.feat2_cl = static_cast<const __nv_bfloat16*>(feat2_cl); p.C1in = C1in;
   p.xyz = xyz; p.new_xyz = new_xyz; p.idx = idx; p.radius_t = radius_t; p.radius = radius;
   p.normalize = normalize_xyz; p.extra = extra; p.E = E; p.has_special = has_special;
   p.n_layers = n_layers; p.last_relu = last_relu;
   p.out_cl = static_cast<__nv_bfloat16*>(out_cl_bf16); p.out_cf = out_cf_f32;
-  int hidden_max = 0, steps = 0;
+  int hidden_max = 0;
   for (int li = 0; li < n_layers; ++li) {
     SAD_REQUIRE(w_img[li] && bias[li] && c_out[li] >= 1, "shared_mlp: layer %d incomplete", li);
     p.c[li] = c_out[li];
@@ -600,23 +878,11 @@ extern "C" int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_c
       SAD_REQUIRE(c_out[li] % 64 == 0 && c_out[li] <= 256, "shared_mlp: hidden width %d must be a multiple of 64, <= 256",
                   c_out[li]);
       hidden_max = c_out[li] > hidden_max ? c_out[li] : hidden_max;
-      steps += p.kpad[li] / 64;
-    } else {
-      steps += ((c_out[li] + 127) / 128) * (p.kpad[li] / 64);
     }
   }
-  p.steps_per_tile = steps;
-  p.rw = hidden_max > 128 ? 256 : 128;
-  p.act_chunks = hidden_max / 64;
-  p.slot_bytes = hidden_max > 128 ? 2 * kChunkBytes : kChunkBytes;
-  const int misc = 1024;
-  const int fixed = 2 * kChunkBytes + p.act_chunks * kChunkBytes + misc + 1024 /*alignment slack*/ + 128 * 8;
-  int nst = steps <= kMaxSlots ? steps : 4;                     // everything resident when it fits in the ring
-  while (nst > 2 && fixed + nst * p.slot_bytes > 227 * 1024) --nst;
-  if (steps <= kMaxSlots && nst < steps) nst = nst < 4 ? nst : 4;
-  SAD_REQUIRE(fixed + nst * p.slot_bytes <= 227 * 1024, "shared_mlp: shared-memory budget exceeded");
-  p.nst = nst;
-  const size_t smem = (size_t)fixed + (size_t)nst * p.slot_bytes;
+  SAD_REQUIRE(c_out[n_layers - 1] <= 512, "shared_mlp: at most 512 output channels");
+  size_t smem = 0;
+  SAD_REQUIRE(plan_launch(p, hidden_max, smem), "shared_mlp: shared-memory / TMEM budget exceeded");
 
   int dev = 0, sms = 0;
   SAD_CUDA_OK(cudaGetDevice(&dev));
@@ -626,8 +892,11 @@ extern "C" int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_c
     SAD_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured_dev = dev;
   }
-  const int per_sm = (2 * p.rw <= 256 && smem <= 113 * 1024) ? 2 : 1;
-  const int grid = p.num_tiles < sms * per_sm ? p.num_tiles : sms * per_sm;
+  if (getenv("SAD_DEBUG_MLP"))
+    fprintf(stderr, "[sad] fused_mlp: rows=%lld tiles=%d S=%d K0=%d c=[%d,%d,%d] nslot=%d na=%d depth=%d pinned=%d/%d "
+            "(%d B) ring=%dx%d tmem=%d smem=%zu\n", p.total_rows, p.num_tiles, S, p.kpad[0], p.c[0], p.c[1], p.c[2], p.nslot,
+            p.na, p.depth, p.n_pinned, p.n_pieces, p.pinned_bytes, p.nr, p.ring_slot_bytes, p.tmem_cols, smem);
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   fused_mlp_kernel<<<grid, kThreads, smem, stream>>>(p);
   SAD_LAUNCH_CHECK("fused_mlp_kernel");
   return SAD_OK;

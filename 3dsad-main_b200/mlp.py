@@ -102,10 +102,13 @@ class PreparedMLP:
     def fusable(self, S: int) -> bool:
         n = len(self.layers)
         hidden_ok = all(c % 64 == 0 and c <= 256 for c in self.c_out[:-1])
-        return 2 <= n <= 3 and hidden_ok and S in (1, 2, 4, 8, 16, 32, 64, 128)
+        return 2 <= n <= 3 and hidden_ok and self.c_out[-1] <= 512 and S in (1, 2, 4, 8, 16, 32, 64, 128)
 
-    def packed(self, layout: Layout):
-        key = layout.key()
+    def packed(self, layout: Layout, S: int = 1):
+        """Weight images for this K layout.  The last layer's image depends on how the kernel evaluates
+        it: transposed (mode 1) for pooled stages (S > 1), plain (mode 2) for S == 1."""
+        last_mode = 1 if S > 1 else 2
+        key = (layout.key(), last_mode)
         if key not in self._packed:
             lib = _lib.load()
             dev = self.layers[0][0].device
@@ -118,7 +121,7 @@ class PreparedMLP:
                 if li > 0:
                     perm[cin:] = -1
                 kpad = int(perm.shape[0])
-                is_last = int(li == n - 1)
+                is_last = last_mode if li == n - 1 else 0
                 nbytes = lib.sad_mlp_weight_image_bytes(cout, kpad, is_last)
                 if nbytes <= 0:
                     raise RuntimeError("sad_mlp_weight_image_bytes rejected the layer shape")
@@ -169,7 +172,7 @@ def fused_mlp(mlp: PreparedMLP, layout: Layout, B, N, P, S, feat_cl=None, feat2_
               idx=None, radius=0.0, radius_t=None, normalize_xyz=False, extra=None, last_relu=True,
               want_cf=True, want_cl=True):
     """Raw launcher of sad_shared_mlp_fwd -> (out_cf (B,Clast,P) f32 | None, out_cl (B,P,Clast) bf16 | None)."""
-    imgs, biases, w_ptrs, b_ptrs, c_arr = mlp.packed(layout)
+    imgs, biases, w_ptrs, b_ptrs, c_arr = mlp.packed(layout, S)
     dev = imgs[0].device
     c_last = mlp.c_out[-1]
     out_cf = torch.empty((B, c_last, P), dtype=torch.float32, device=dev) if want_cf else None
@@ -227,13 +230,14 @@ def fp_interp_mlp(known_feats, unknow_feats, idx, weight, mlp: PreparedMLP):
     return _attach(out_cf, out_cl)
 
 
-def pointwise_mlp(x: torch.Tensor, mlp: PreparedMLP, last_relu: bool = True) -> torch.Tensor:
+def pointwise_mlp(x: torch.Tensor, mlp: PreparedMLP, last_relu: bool = True, want_cl: bool = True) -> torch.Tensor:
     """x (B,C,n) -> (B,Cout,n) f32 (voting and other per-point stacks)."""
     B, C, n = x.shape
     if not mlp.fusable(1):
         return composed_pointwise(x, mlp, last_relu)
     layout = Layout(c0=_round64(C), c0_cols=range(C))
-    out_cf, out_cl = fused_mlp(mlp, layout, B, n, n, 1, feat_cl=to_cl_bf16(x, pad_to=layout.c0), last_relu=last_relu)
+    out_cf, out_cl = fused_mlp(mlp, layout, B, n, n, 1, feat_cl=to_cl_bf16(x, pad_to=layout.c0), last_relu=last_relu,
+                               want_cl=want_cl)
     return _attach(out_cf, out_cl)
 
 

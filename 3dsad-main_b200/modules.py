@@ -277,7 +277,7 @@ class VotingModule(nn.Module):
 
     def forward(self, seed_xyz, seed_features):
         if not self.training and not torch.is_grad_enabled():
-            y = _mlp.pointwise_mlp(seed_features, self.mlp.folded(), last_relu=False)
+            y = _mlp.pointwise_mlp(seed_features, self.mlp.folded(), last_relu=False, want_cl=False)
         else:
             y = self.mlp(seed_features.unsqueeze(-1)).squeeze(-1)
         vote_xyz = (seed_xyz + y[:, :3, :].transpose(1, 2)).contiguous()

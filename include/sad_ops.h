@@ -108,7 +108,9 @@ SAD_API int sad_three_interpolate_bwd(int B, int C, int n, int m, const float* g
  *   perm   kpad int32: perm[k] = column of W feeding packed K index k, -1 = zero column
  *          (layer 1 K order: [feat_cl C0 | feat2_cl C1in | special chunk of 64: dx,dy,dz,
  *          extras..., zeros]; later layers: identity over the previous layer's outputs),
- *   kpad   K rounded up to a multiple of 64,  is_last = 1 for the final layer of the stack.
+ *   kpad   K rounded up to a multiple of 64,
+ *   is_last  0 = hidden layer; final layer of the stack: 1 when the stage pools (S > 1, evaluated
+ *          transposed in 128-channel blocks), 2 when S == 1 (plain, rows padded to 32, <= 512).
  * Returns bytes (or -1) / SAD_OK. */
 SAD_API long long sad_mlp_weight_image_bytes(int cout, int kpad, int is_last);
 SAD_API int sad_mlp_pack_weights(const float* W, int cout, int cin, const int32_t* perm, int kpad,

@@ -132,7 +132,7 @@ def test_weight_image_matches_numpy_swizzle():
     mlp = M.prepare_layers([(torch.from_numpy(W).to(DEV), torch.zeros(80, device=DEV)),
                             (torch.zeros(8, 80, device=DEV), torch.zeros(8, device=DEV))])
     lay = M.Layout(c0=192, c0_cols=range(150))
-    imgs, *_ = mlp.packed(lay)
+    imgs, *_ = mlp.packed(lay, 1)
     img = imgs[0].cpu().numpy().view(np.uint16)
     ref = (O.bf16_round(W).view(np.uint32) >> 16).astype(np.uint16)
     for (r, k) in [(0, 0), (5, 9), (79, 149), (33, 64), (8, 127), (17, 63)]:

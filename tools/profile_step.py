@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--B", type=int, default=8)
     ap.add_argument("--N", type=int, default=40000)
+    ap.add_argument("--calls", action="store_true", help="print CUDA-event time of every C-ABI call (serial, one stream)")
     a = ap.parse_args()
     dev = "cuda:0"
     model = SADHotPath(1).load_params(make_params(0)).to(dev).eval()
@@ -34,6 +35,21 @@ def main():
         for _ in range(a.warmup + a.steps):
             end = model(x, f, s)
     torch.cuda.synchronize()
+    if a.calls:
+        from sad_b200 import _lib
+        model.backbone.overlap_geometry = False
+        acc = {}
+        for rep in range(5):
+            with _lib.CallProfiler() as prof, torch.no_grad():
+                model(x, f, s)
+            for i, (name, args, ms) in enumerate(prof.rows()):
+                acc.setdefault((i, name, tuple(v for v in args[:4] if isinstance(v, int))), []).append(ms)
+        tot = 0.0
+        for (i, name, dims), v in acc.items():
+            v.sort()
+            tot += v[len(v) // 2]
+            print(f"{i:3d} {name:34s} {str(dims):28s} {1e3 * v[len(v) // 2]:9.1f} us")
+        print(f"sum of C-ABI calls: {1e3 * tot:.1f} us")
     print("checksum", float(end["cluster_features"].sum()))
 
 
