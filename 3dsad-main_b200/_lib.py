@@ -30,6 +30,11 @@ SIGNATURES = {
     "sad_three_nn_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_three_interpolate_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_three_interpolate_bwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
+    "sad_scene_grid_workspace_bytes": [_c_int, _c_int],
+    "sad_scene_grid_build": [_c_int, _c_int, _vp, _vp, _vp],
+    "sad_ball_query_grid_fwd": [_c_int, _c_int, _c_int, _c_float, _vp, _c_int, _vp, _vp, _vp, _vp, _vp],
+    "sad_fps_grid_max_points": [],
+    "sad_furthest_point_sample_grid_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_mlp_weight_image_bytes": [_c_int, _c_int, _c_int],
     "sad_mlp_pack_weights": [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp],
     "sad_shared_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _c_float, _vp,
@@ -38,7 +43,7 @@ SIGNATURES = {
     "sad_cf_to_cl_bf16": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
 }
 _RESTYPES = {"sad_last_error_string": ctypes.c_char_p, "sad_fps_force_cluster_size": None,
-             "sad_launch_count": ctypes.c_ulonglong, "sad_mlp_weight_image_bytes": ctypes.c_longlong}
+             "sad_launch_count": ctypes.c_ulonglong, "sad_scene_grid_workspace_bytes": ctypes.c_longlong, "sad_mlp_weight_image_bytes": ctypes.c_longlong}
 
 _lib = None
 _lock = threading.Lock()
@@ -93,7 +98,7 @@ class CallProfiler:
         import torch
         lib = load()
         for name in SIGNATURES:
-            if not (name.endswith("_fwd") or name.endswith("_bwd") or name == "sad_cf_to_cl_bf16"):
+            if not (name.endswith("_fwd") or name.endswith("_bwd") or name in ("sad_cf_to_cl_bf16", "sad_scene_grid_build")):
                 continue
             fn = getattr(lib, name)
             self._saved[name] = fn

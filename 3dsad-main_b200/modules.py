@@ -122,16 +122,20 @@ class PointnetSAModuleVotes(nn.Module):
             ch[0] += 3
         self.mlp_module = SharedMLP(ch, bn=bn)
 
-    def forward(self, xyz, features=None, inds=None, radius_t=None, new_xyz=None):
+    def forward(self, xyz, features=None, inds=None, radius_t=None, new_xyz=None, grid=None):
+        """`grid`: optional ops.SceneGrid of `xyz` shared by the sampling and the neighbour search (large
+        scenes build one on the fly when none is passed)."""
+        if grid is None and inds is None and xyz.shape[1] >= ops.GRID_MIN_POINTS:
+            grid = ops.build_scene_grid(xyz)
         if inds is None:
-            inds = ops.furthest_point_sample(xyz, self.npoint)
+            inds = ops.furthest_point_sample(xyz, self.npoint, grid)
         if new_xyz is None:
             new_xyz = _gather_xyz(xyz, inds)
         if radius_t is not None:
-            idx = ops.ball_query_adaptive(radius_t, self.nsample, xyz, new_xyz)
+            idx = ops.ball_query_adaptive(radius_t, self.nsample, xyz, new_xyz, grid)
             rad = radius_t
         else:
-            idx = ops.ball_query(self.radius, self.nsample, xyz, new_xyz)
+            idx = ops.ball_query(self.radius, self.nsample, xyz, new_xyz, grid)
             rad = self.radius
         if not self.training and not torch.is_grad_enabled():
             new_features = _mlp.sa_group_mlp(xyz, new_xyz, features, idx, rad, self.mlp_module.folded(),
@@ -210,11 +214,15 @@ class Pointnet2Backbone(nn.Module):
         plan = {}
         xyz.record_stream(geo_a)
         with torch.cuda.stream(geo_a):
-            inds = ops.furthest_point_sample(xyz, self.sa1.npoint)
+            grid = ops.build_scene_grid(xyz) if xyz.shape[1] >= ops.GRID_MIN_POINTS else None
+            inds = ops.furthest_point_sample(xyz, self.sa1.npoint, grid)
             x = _gather_xyz(xyz, inds)
             ev = torch.cuda.Event()
             ev.record(geo_a)
             plan["sa1"] = (inds, x, ev)
+            plan["grid"] = grid
+            if grid is not None:
+                grid.workspace.record_stream(main)
         geo_b.wait_event(ev)
         with torch.cuda.stream(geo_b):
             for name in ("sa2", "sa3", "sa4"):
@@ -229,7 +237,9 @@ class Pointnet2Backbone(nn.Module):
             ev.record(geo_b)
             plan["fp"] = (p1, p2, ev)
         plan["sa1"][1].record_stream(geo_b)
-        for v in plan.values():           # tensors born on a side stream, consumed on `main`
+        for k, v in plan.items():         # tensors born on a side stream, consumed on `main`
+            if k == "grid":
+                continue
             for t in v:
                 if torch.is_tensor(t):
                     t.record_stream(main)
@@ -249,7 +259,8 @@ class Pointnet2Backbone(nn.Module):
             if plan is not None:
                 inds, new_xyz, ev = plan[name]
                 main.wait_event(ev)
-                x, f, inds = getattr(self, name)(x, f, inds=inds, new_xyz=new_xyz)
+                x, f, inds = getattr(self, name)(x, f, inds=inds, new_xyz=new_xyz,
+                                                 grid=plan["grid"] if name == "sa1" else None)
             else:
                 x, f, inds = getattr(self, name)(x, f)
             end[name + "_xyz"], end[name + "_features"], end[name + "_inds"] = x, f, inds

@@ -33,6 +33,9 @@ def _p(t: torch.Tensor):
     return ctypes.c_void_p(t.data_ptr())
 
 
+_VP0 = ctypes.c_void_p(0)
+
+
 def _req(t, name, dtype, ndim, last=None):
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
@@ -57,26 +60,69 @@ def _same_dev(*ts):
     return d
 
 
+class SceneGrid:
+    """Spatial sort of a batch of scenes (csrc/grid.cu): points ordered by cell of a 32^3 grid plus the
+    cell offsets.  Built once per coordinate tensor and shared by the culled FPS and the grid ball
+    query over the same `xyz`; results of both are bit-identical to the plain kernels."""
+
+    __slots__ = ("xyz", "B", "N", "workspace")
+
+    def __init__(self, xyz: torch.Tensor):
+        _req(xyz, "xyz", torch.float32, 3, 3)
+        self.xyz, (self.B, self.N) = xyz, xyz.shape[:2]
+        lib = _lib.load()
+        nbytes = int(lib.sad_scene_grid_workspace_bytes(self.B, self.N))
+        if nbytes < 0:
+            raise ValueError("scene grid: bad sizes")
+        self.workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=xyz.device)
+        with torch.cuda.device(xyz.device):
+            _lib.check(lib.sad_scene_grid_build(self.B, self.N, _p(xyz), _p(self.workspace), _stream(xyz)),
+                       "scene_grid_build")
+
+    def check(self, xyz: torch.Tensor):
+        if xyz.data_ptr() != self.xyz.data_ptr() or tuple(xyz.shape) != tuple(self.xyz.shape):
+            raise ValueError("SceneGrid was built for a different xyz tensor")
+        return self
+
+
+def build_scene_grid(xyz: torch.Tensor) -> SceneGrid:
+    return SceneGrid(xyz)
+
+
+# Scenes at least this large get a scene grid built on the fly by furthest_point_sample / ball_query
+# when the caller passes none (the build costs one short kernel; below it the plain kernels win).
+GRID_MIN_POINTS = 8192
+
+
 class FurthestPointSampling(Function):
-    """a1.  xyz (B,N,3) f32 -> (B,npoint) i32; sel[0]=0, ties to the lowest index."""
+    """a1.  xyz (B,N,3) f32 -> (B,npoint) i32; sel[0]=0, ties to the lowest index.
+    Optional `grid` (SceneGrid of the same xyz) selects the exact culled kernel."""
 
     @staticmethod
-    def forward(ctx, xyz, npoint):
+    def forward(ctx, xyz, npoint, grid=None):
         _req(xyz, "xyz", torch.float32, 3, 3)
         B, N, _ = xyz.shape
         npoint = int(npoint)
         if npoint < 1 or N < 1:
             raise ValueError("furthest_point_sample: need N >= 1 and npoint >= 1")
+        lib = _lib.load()
         out = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+        if grid is None and GRID_MIN_POINTS <= N <= lib.sad_fps_grid_max_points():
+            grid = SceneGrid(xyz)
         with torch.cuda.device(xyz.device):
-            _lib.check(_lib.load().sad_furthest_point_sample_fwd(B, N, npoint, _p(xyz), _p(out), _stream(xyz)),
-                       "furthest_point_sample")
+            if grid is not None and N <= lib.sad_fps_grid_max_points():
+                grid.check(xyz)
+                _lib.check(lib.sad_furthest_point_sample_grid_fwd(B, N, npoint, _p(xyz), _p(grid.workspace), _p(out),
+                                                                  _stream(xyz)), "furthest_point_sample_grid")
+            else:
+                _lib.check(lib.sad_furthest_point_sample_fwd(B, N, npoint, _p(xyz), _p(out), _stream(xyz)),
+                           "furthest_point_sample")
         ctx.mark_non_differentiable(out)
         return out
 
     @staticmethod
     def backward(ctx, grad=None):
-        return None, None
+        return None, None, None
 
 
 class GatherOperation(Function):
@@ -112,10 +158,11 @@ class GatherOperation(Function):
 
 
 class BallQuery(Function):
-    """a3.  (radius, nsample, xyz (B,N,3), new_xyz (B,npoint,3)) -> idx (B,npoint,nsample) i32."""
+    """a3.  (radius, nsample, xyz (B,N,3), new_xyz (B,npoint,3)) -> idx (B,npoint,nsample) i32.
+    Optional `grid` (SceneGrid of the same xyz) selects the grid-accelerated kernel."""
 
     @staticmethod
-    def forward(ctx, radius, nsample, xyz, new_xyz):
+    def forward(ctx, radius, nsample, xyz, new_xyz, grid=None):
         _req(xyz, "xyz", torch.float32, 3, 3)
         _req(new_xyz, "new_xyz", torch.float32, 3, 3)
         _same_dev(xyz, new_xyz)
@@ -126,22 +173,31 @@ class BallQuery(Function):
         if nsample < 1:
             raise ValueError("ball_query: nsample must be >= 1")
         out = torch.empty((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
+        if grid is None and N >= GRID_MIN_POINTS:
+            grid = SceneGrid(xyz)
         with torch.cuda.device(xyz.device):
-            _lib.check(_lib.load().sad_ball_query_fwd(B, N, npoint, float(radius), nsample, _p(xyz), _p(new_xyz),
-                                                      _p(out), _stream(xyz)), "ball_query")
+            if grid is not None:
+                grid.check(xyz)
+                _lib.check(_lib.load().sad_ball_query_grid_fwd(B, N, npoint, float(radius), _VP0, nsample, _p(xyz),
+                                                               _p(grid.workspace), _p(new_xyz), _p(out), _stream(xyz)),
+                           "ball_query_grid")
+            else:
+                _lib.check(_lib.load().sad_ball_query_fwd(B, N, npoint, float(radius), nsample, _p(xyz), _p(new_xyz),
+                                                          _p(out), _stream(xyz)), "ball_query")
         ctx.mark_non_differentiable(out)
         return out
 
     @staticmethod
     def backward(ctx, grad=None):
-        return None, None, None, None
+        return None, None, None, None, None
 
 
 class BallQueryAdaptive(Function):
-    """a4 (3DSAD).  radius_t (B,npoint) f32: per-cluster radius from predicted object size."""
+    """a4 (3DSAD).  radius_t (B,npoint) f32: per-cluster radius from predicted object size.
+    Optional `grid` as for ball_query."""
 
     @staticmethod
-    def forward(ctx, radius_t, nsample, xyz, new_xyz):
+    def forward(ctx, radius_t, nsample, xyz, new_xyz, grid=None):
         _req(xyz, "xyz", torch.float32, 3, 3)
         _req(new_xyz, "new_xyz", torch.float32, 3, 3)
         _req(radius_t, "radius_t", torch.float32, 2)
@@ -153,16 +209,24 @@ class BallQueryAdaptive(Function):
         if nsample < 1:
             raise ValueError("ball_query_adaptive: nsample must be >= 1")
         out = torch.empty((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
+        if grid is None and N >= GRID_MIN_POINTS:
+            grid = SceneGrid(xyz)
         with torch.cuda.device(xyz.device):
-            _lib.check(_lib.load().sad_ball_query_adaptive_fwd(B, N, npoint, _p(radius_t), nsample, _p(xyz),
-                                                               _p(new_xyz), _p(out), _stream(xyz)),
-                       "ball_query_adaptive")
+            if grid is not None:
+                grid.check(xyz)
+                _lib.check(_lib.load().sad_ball_query_grid_fwd(B, N, npoint, 0.0, _p(radius_t), nsample, _p(xyz),
+                                                               _p(grid.workspace), _p(new_xyz), _p(out), _stream(xyz)),
+                           "ball_query_grid")
+            else:
+                _lib.check(_lib.load().sad_ball_query_adaptive_fwd(B, N, npoint, _p(radius_t), nsample, _p(xyz),
+                                                                   _p(new_xyz), _p(out), _stream(xyz)),
+                           "ball_query_adaptive")
         ctx.mark_non_differentiable(out)
         return out
 
     @staticmethod
     def backward(ctx, grad=None):
-        return None, None, None, None
+        return None, None, None, None, None
 
 
 class GroupingOperation(Function):

@@ -56,6 +56,23 @@ SAD_API const char* sad_last_error_string(void);
 SAD_API int sad_furthest_point_sample_fwd(int B, int N, int npoint, const float* xyz, int32_t* idx,
                                   sad_stream_t stream);
 
+/* ---- scene grid: spatial sort shared by the exact culled FPS and the grid ball query ----------
+ * workspace (caller-owned, 16-byte aligned, sad_scene_grid_workspace_bytes(B,N) bytes) receives, per
+ * scene, the points sorted by cell of a 32^3 grid (x,y,z,original index) and the cell offsets.  It
+ * is valid for exactly the xyz it was built from.  Results of the *_grid_fwd entry points are
+ * bit-identical to sad_furthest_point_sample_fwd / sad_ball_query(_adaptive)_fwd. */
+SAD_API long long sad_scene_grid_workspace_bytes(int B, int N);
+SAD_API int sad_scene_grid_build(int B, int N, const float* xyz, void* workspace, sad_stream_t stream);
+/* a1 over the grid: points resident in the shared memory of a 1..16-CTA cluster, bounding-box
+ * culling of the per-pick update.  N <= sad_fps_grid_max_points(), else SAD_EUNSUPPORTED. */
+SAD_API int sad_fps_grid_max_points(void);
+SAD_API int sad_furthest_point_sample_grid_fwd(int B, int N, int npoint, const float* xyz,
+                                               const void* grid_workspace, int32_t* idx, sad_stream_t stream);
+/* a3 / a4 over the grid: radius_t (B,npoint) per-query radius or NULL (then `radius`). */
+SAD_API int sad_ball_query_grid_fwd(int B, int N, int npoint, float radius, const float* radius_t,
+                                    int nsample, const float* xyz, const void* grid_workspace,
+                                    const float* new_xyz, int32_t* idx, sad_stream_t stream);
+
 /* a2  gather_operation: out[b,c,j] = features[b,c,idx[b,j]].
  * features (B,C,N) f32, idx (B,npoint) i32 -> out (B,C,npoint) f32. */
 SAD_API int sad_gather_operation_fwd(int B, int C, int N, int npoint, const float* features,
