@@ -131,6 +131,12 @@ fps_cull_kernel(int N, int npoint, const float* __restrict__ xyz, const uint8_t*
   const float4* wp = s_pts + warp * 32 + lane;      // + s * NW * 32
   float* wm = s_md + warp * 32 + lane;
 
+#ifdef SAD_FPS_PROFILE
+  long long ph[5] = {0, 0, 0, 0, 0}, nupd = 0, tprev = clock64();
+#define SAD_MARK(i) { const long long tn = clock64(); ph[i] += tn - tprev; tprev = tn; }
+#else
+#define SAD_MARK(i)
+#endif
   for (int j = 1; j < npoint; ++j) {
     const int buf = j & 1;
     if (CS > 1 && tid == 0) mbar_arrive_expect_tx(&s_bar[buf], NSLOT * 20);
@@ -143,6 +149,10 @@ fps_cull_kernel(int N, int npoint, const float* __restrict__ xyz, const uint8_t*
     }
     uint32_t mask = __ballot_sync(FULL, aff);
     const bool changed = (mask != 0u) || (j == 1);
+    SAD_MARK(0)
+#ifdef SAD_FPS_PROFILE
+    nupd += __popc(mask);
+#endif
     while (mask) {
       const int s = __ffs(mask) - 1;
       mask &= mask - 1;
@@ -158,6 +168,7 @@ fps_cull_kernel(int N, int npoint, const float* __restrict__ xyz, const uint8_t*
         bidx = ix;
       }
     }
+    SAD_MARK(1)
     if (changed) {
       const uint32_t wb = (lane < nb) ? __float_as_uint(bmax) : 0u;
       wmax = __reduce_max_sync(FULL, wb);
@@ -172,6 +183,7 @@ fps_cull_kernel(int N, int npoint, const float* __restrict__ xyz, const uint8_t*
       cz = __shfl_sync(FULL, p.z, src);
     }
 
+    SAD_MARK(2)
     // ---- publish
     if (CS == 1) {
       if (lane == 0) {
@@ -189,6 +201,7 @@ fps_cull_kernel(int N, int npoint, const float* __restrict__ xyz, const uint8_t*
       mbar_wait(&s_bar[buf], (uint32_t)(((j - 1) >> 1) & 1));
     }
 
+    SAD_MARK(3)
     // ---- every warp reduces the NSLOT records: max value, ties -> lowest original index
     uint32_t v = 0u, vi = kInf, vs = 0u;
 #pragma unroll
@@ -213,8 +226,203 @@ fps_cull_kernel(int N, int npoint, const float* __restrict__ xyz, const uint8_t*
     qy = w.z;
     qz = w.w;
     if (rank == 0 && tid == 0) o[j] = (int32_t)gidx;
+    SAD_MARK(4)
   }
+#ifdef SAD_FPS_PROFILE
+  if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7))
+    printf("[fps_cull CS=%d N=%d warp %d] per pick: cull %lld  update %lld (%.2f buckets)  record %lld  exchange %lld  reduce %lld cycles\n",
+           CS, N, warp, ph[0] / (npoint - 1), ph[1] / (npoint - 1), (double)nupd / (npoint - 1), ph[2] / (npoint - 1),
+           ph[3] / (npoint - 1), ph[4] / (npoint - 1));
+#endif
+#undef SAD_MARK
   if (CS > 1) cluster_sync_all();   // no CTA retires while a peer's st.async may still target it
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-CTA variant: one SM per scene, any N.  The points stay in the (L2-resident) sorted array and
+// the min-distances in the workspace scratch; the CTA keeps only per-bucket state on chip: box / bmax /
+// bidx in registers (slot s of a warp lives in lane s % 32, register set s / 32) and each bucket's
+// best point in shared memory.  A pick costs: one block barrier, a 16-record reduce, the lane-parallel
+// box test, and an L2 round trip for the handful of buckets that survive it (two at a time per warp for
+// latency overlap) -- no cluster, no DSMEM exchange, and 1/4 .. 1/16 of the SMs of the other kernels.
+constexpr int FC1_T = 512;
+constexpr int FC1_NW = FC1_T / 32;
+
+template <int R>
+__global__ void __launch_bounds__(FC1_T, 1)
+fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __restrict__ ws, size_t stride,
+                 int32_t* __restrict__ out) {
+  constexpr int NW = FC1_NW;
+  extern __shared__ __align__(16) float4 s_best[];      // [slot * NW + warp] best point of the bucket {x,y,z,bits(idx)}
+  __shared__ __align__(16) float4 s_wrec[2][NW];        // per warp: best point {x,y,z,bits(idx)}
+  __shared__ uint32_t s_wval[2][NW];                    // per warp: its min-dist bits
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  uint8_t* base = ws + (size_t)b * stride;
+  const float4* sorted = reinterpret_cast<const float4*>(base + kGridHeaderBytes + kGridCellBytes);
+  float* mind = reinterpret_cast<float*>(base + grid_scratch_offset(N));
+  int32_t* o = out + (size_t)b * npoint;
+  const int NB = (N + 31) >> 5;
+  const int nslots = NB > warp ? (NB - warp + NW - 1) / NW : 0;      // buckets warp, warp+NW, ...
+
+  const float* p0 = xyz + (size_t)b * N * 3;
+  float qx = __ldg(p0), qy = __ldg(p0 + 1), qz = __ldg(p0 + 2);       // pick 0 = point 0
+  if (tid == 0) o[0] = 0;
+
+  float blx[R], bly[R], blz[R], bhx[R], bhy[R], bhz[R], bmax[R];
+  uint32_t bidx[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    blx[r] = bly[r] = blz[r] = bhx[r] = bhy[r] = bhz[r] = bmax[r] = 0.f;
+    bidx[r] = kInf;
+  }
+  // ---- load pass: boxes, and pick 0 applied on the fly (min-dist = min(1e10, d2(p, p0)))
+  for (int s = 0; s < nslots; ++s) {
+    const int k = (s * NW + warp) * 32 + lane;
+    const bool ok = k < N;
+    float4 p = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInf));
+    float m = 0.f;
+    if (ok) {
+      p = __ldg(sorted + k);
+      m = fminf(1e10f, sqdist(p.x, p.y, p.z, qx, qy, qz));
+      mind[k] = m;
+    }
+    const uint32_t lx = __reduce_min_sync(FULL, ok ? f2o(p.x) : kInf), hx = __reduce_max_sync(FULL, ok ? f2o(p.x) : 0u);
+    const uint32_t ly = __reduce_min_sync(FULL, ok ? f2o(p.y) : kInf), hy = __reduce_max_sync(FULL, ok ? f2o(p.y) : 0u);
+    const uint32_t lz = __reduce_min_sync(FULL, ok ? f2o(p.z) : kInf), hz = __reduce_max_sync(FULL, ok ? f2o(p.z) : 0u);
+    const uint32_t mb = __float_as_uint(m);
+    const uint32_t mx = __reduce_max_sync(FULL, mb);
+    const uint32_t ix = __reduce_min_sync(FULL, (ok && mb == mx) ? __float_as_uint(p.w) : kInf);
+    if (ok && __float_as_uint(p.w) == ix) s_best[s * NW + warp] = p;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if ((s >> 5) == r && lane == (s & 31)) {
+        blx[r] = o2f(lx); bly[r] = o2f(ly); blz[r] = o2f(lz);
+        bhx[r] = o2f(hx); bhy[r] = o2f(hy); bhz[r] = o2f(hz);
+        bmax[r] = __uint_as_float(mx);
+        bidx[r] = ix;
+      }
+  }
+  bool changed = true;
+
+  for (int j = 1; j < npoint; ++j) {
+    const int buf = j & 1;
+    // ---- this warp's record: its best bucket (recomputed only when one of its buckets changed)
+    __syncwarp();
+    if (changed) {
+      uint32_t v = 0u, vi = kInf;
+      int vr = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const bool valid = (r * 32 + lane) < nslots;
+        const uint32_t x = valid ? __float_as_uint(bmax[r]) : 0u;
+        const uint32_t id = valid ? bidx[r] : kInf;
+        if (x > v || (x == v && id < vi)) {
+          v = x;
+          vi = id;
+          vr = r;
+        }
+      }
+      const uint32_t wmax = __reduce_max_sync(FULL, v);
+      const uint32_t widx = __reduce_min_sync(FULL, v == wmax ? vi : kInf);
+      if (widx == kInf) {
+        if (lane == 0) {
+          s_wval[buf][warp] = 0u;
+          s_wrec[buf][warp] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInf));
+        }
+      } else if (v == wmax && vi == widx) {
+        s_wval[buf][warp] = wmax;
+        s_wrec[buf][warp] = s_best[(vr * 32 + lane) * NW + warp];
+      }
+    } else if (lane == 0) {
+      s_wval[buf][warp] = s_wval[buf ^ 1][warp];
+      s_wrec[buf][warp] = s_wrec[buf ^ 1][warp];
+    }
+    __syncthreads();
+
+    // ---- every warp reduces the NW records: max value, ties -> lowest original index
+    const uint32_t x = lane < NW ? s_wval[buf][lane] : 0u;
+    const uint32_t id = lane < NW ? __float_as_uint(s_wrec[buf][lane].w) : kInf;
+    const uint32_t gmax = __reduce_max_sync(FULL, x);
+    const uint32_t gidx = __reduce_min_sync(FULL, x == gmax ? id : kInf);
+    const uint32_t gl = __ballot_sync(FULL, x == gmax && id == gidx);
+    const float4 w = s_wrec[buf][gl ? __ffs(gl) - 1 : 0];
+    qx = w.x;
+    qy = w.y;
+    qz = w.z;
+    if (tid == 0) o[j] = (int32_t)gidx;
+    if (j == npoint - 1) break;
+
+    // ---- cull + update: only buckets whose box the pick can reach
+    changed = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      bool aff = false;
+      if (r * 32 + lane < nslots) {
+        const float ccx = fminf(fmaxf(qx, blx[r]), bhx[r]), ccy = fminf(fmaxf(qy, bly[r]), bhy[r]),
+                    ccz = fminf(fmaxf(qz, blz[r]), bhz[r]);
+        aff = sqdist(ccx, ccy, ccz, qx, qy, qz) < bmax[r];
+      }
+      uint32_t mask = __ballot_sync(FULL, aff);
+      if (mask) changed = true;
+      while (mask) {                                   // two buckets in flight per step (independent L2 round trips)
+        const int b0 = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const bool two = mask != 0u;
+        const int b1 = two ? __ffs(mask) - 1 : b0;
+        if (two) mask &= mask - 1;
+        const int s0 = r * 32 + b0, s1 = r * 32 + b1;
+        const int k0 = (s0 * NW + warp) * 32 + lane, k1 = (s1 * NW + warp) * 32 + lane;
+        const bool ok0 = k0 < N, ok1 = two && (k1 < N);
+        float4 pa = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInf)), pb = pa;
+        float ma = 0.f, mb_ = 0.f;
+        if (ok0) {
+          pa = __ldg(sorted + k0);
+          ma = mind[k0];
+        }
+        if (ok1) {
+          pb = __ldg(sorted + k1);
+          mb_ = mind[k1];
+        }
+        const float na = fminf(ma, sqdist(pa.x, pa.y, pa.z, qx, qy, qz));
+        const float nb_ = fminf(mb_, sqdist(pb.x, pb.y, pb.z, qx, qy, qz));
+        if (ok0 && na < ma) mind[k0] = na;
+        if (ok1 && nb_ < mb_) mind[k1] = nb_;
+        const uint32_t ua = __float_as_uint(na), ub = __float_as_uint(nb_);      // >= 0: bit order == value order
+        const uint32_t mxa = __reduce_max_sync(FULL, ua), mxb = __reduce_max_sync(FULL, ub);
+        const uint32_t ixa = __reduce_min_sync(FULL, (ok0 && ua == mxa) ? __float_as_uint(pa.w) : kInf);
+        const uint32_t ixb = __reduce_min_sync(FULL, (ok1 && ub == mxb) ? __float_as_uint(pb.w) : kInf);
+        if (ok0 && __float_as_uint(pa.w) == ixa) s_best[s0 * NW + warp] = pa;
+        if (ok1 && __float_as_uint(pb.w) == ixb) s_best[s1 * NW + warp] = pb;
+        if (lane == b0) {
+          bmax[r] = __uint_as_float(mxa);
+          bidx[r] = ixa;
+        }
+        if (two && lane == b1) {
+          bmax[r] = __uint_as_float(mxb);
+          bidx[r] = ixb;
+        }
+      }
+    }
+  }
+}
+
+template <int R>
+int launch_cull1(int B, int N, int npoint, const float* xyz, void* ws, int32_t* idx, cudaStream_t stream) {
+  auto kern = fps_cull1_kernel<R>;
+  const int nb = (N + 31) / 32;
+  const size_t smem = (size_t)sad_ceil_div(nb, FC1_NW) * FC1_NW * sizeof(float4);
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  SAD_CUDA_OK(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    SAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, R * 32 * FC1_NW * 16));
+    configured_dev = dev;
+  }
+  kern<<<B, FC1_T, smem, stream>>>(N, npoint, xyz, static_cast<uint8_t*>(ws), sad::grid_stride(N), idx);
+  SAD_LAUNCH_CHECK("fps_cull1_kernel");
+  return SAD_OK;
 }
 
 template <int CS>
@@ -250,29 +458,44 @@ int launch_cull(int B, int N, int npoint, const float* xyz, const void* ws, int3
 
 }  // namespace
 
-// Largest scene the culled kernel holds in the shared memory of a 16-CTA cluster.
-extern "C" int sad_fps_grid_max_points(void) { return 16 * FC_MAX_SLOTS * FC_NW * 32; }
+// Tests / benchmarks: 0 = default (shared-memory-resident cluster kernel with the fewest CTAs that hold the
+// scene; single-CTA L2-resident kernel beyond its capacity); 1,2,4,8,16 = cluster kernel with at least that
+// many CTAs per scene; -1 = single-CTA kernel.
+static thread_local int g_cull_cluster = 0;
+extern "C" void sad_fps_grid_force_cluster(int cs) { g_cull_cluster = cs; }
 
-extern "C" int sad_furthest_point_sample_grid_fwd(int B, int N, int npoint, const float* xyz, const void* grid_ws,
+// Largest scene the culled kernels accept.
+extern "C" int sad_fps_grid_max_points(void) { return 16 * 32 * FC1_NW * 32; }
+
+extern "C" int sad_furthest_point_sample_grid_fwd(int B, int N, int npoint, const float* xyz, void* grid_ws,
                                                   int32_t* idx, sad_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SAD_REQUIRE(B >= 0 && N >= 1 && npoint >= 1, "furthest_point_sample_grid: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
   if (B == 0) return SAD_OK;
   SAD_REQUIRE(xyz && grid_ws && idx, "furthest_point_sample_grid: null pointer");
-  const int cap = FC_MAX_SLOTS * FC_NW * 32;           // points per CTA
-  if (N > 16 * cap) {
-    sad_set_error("furthest_point_sample_grid: N=%d exceeds the shared-memory-resident capacity (%d)", N, 16 * cap);
+  if (N > sad_fps_grid_max_points()) {
+    sad_set_error("furthest_point_sample_grid: N=%d exceeds the capacity (%d)", N, sad_fps_grid_max_points());
     return SAD_EUNSUPPORTED;
   }
-  int cs = 1;
-  while (cs * cap < N) cs <<= 1;
   const int nbk = (N + 31) / 32;
-  const int slots = sad_ceil_div(sad_ceil_div(nbk, cs), FC_NW);
-  switch (cs) {
-    case 1: return launch_cull<1>(B, N, npoint, xyz, grid_ws, idx, slots, stream);
-    case 2: return launch_cull<2>(B, N, npoint, xyz, grid_ws, idx, slots, stream);
-    case 4: return launch_cull<4>(B, N, npoint, xyz, grid_ws, idx, slots, stream);
-    case 8: return launch_cull<8>(B, N, npoint, xyz, grid_ws, idx, slots, stream);
-    default: return launch_cull<16>(B, N, npoint, xyz, grid_ws, idx, slots, stream);
+  const int cap = FC_MAX_SLOTS * FC_NW * 32;           // points per CTA of the cluster kernel
+  if (g_cull_cluster >= 0 && N <= 16 * cap) {
+    int cs = 1;
+    while (cs < g_cull_cluster && cs < 16) cs <<= 1;
+    while (cs * cap < N) cs <<= 1;
+    const int slots = sad_ceil_div(sad_ceil_div(nbk, cs), FC_NW);
+    switch (cs) {
+      case 1: return launch_cull<1>(B, N, npoint, xyz, grid_ws, idx, slots, stream);
+      case 2: return launch_cull<2>(B, N, npoint, xyz, grid_ws, idx, slots, stream);
+      case 4: return launch_cull<4>(B, N, npoint, xyz, grid_ws, idx, slots, stream);
+      case 8: return launch_cull<8>(B, N, npoint, xyz, grid_ws, idx, slots, stream);
+      default: return launch_cull<16>(B, N, npoint, xyz, grid_ws, idx, slots, stream);
+    }
   }
+  const int per_lane = sad_ceil_div(sad_ceil_div(nbk, FC1_NW), 32);   // bucket slots per lane
+  if (per_lane <= 1) return launch_cull1<1>(B, N, npoint, xyz, grid_ws, idx, stream);
+  if (per_lane <= 2) return launch_cull1<2>(B, N, npoint, xyz, grid_ws, idx, stream);
+  if (per_lane <= 4) return launch_cull1<4>(B, N, npoint, xyz, grid_ws, idx, stream);
+  if (per_lane <= 8) return launch_cull1<8>(B, N, npoint, xyz, grid_ws, idx, stream);
+  return launch_cull1<16>(B, N, npoint, xyz, grid_ws, idx, stream);
 }

@@ -74,6 +74,7 @@ struct MlpParams {
   int last_relu;
   __nv_bfloat16* out_cl;          // (B,P,c_last) bf16 or null
   float* out_cf;                  // (B,c_last,P) f32 or null
+  int* tile_counter;              // zeroed by the caller: dynamic tile scheduling; null: static round-robin
   // ---- plan (host)
   int transposed;                 // last layer evaluated transposed (S > 1)
   int nslot;                      // tile contexts in flight (2 = ping-pong)
@@ -96,6 +97,9 @@ struct Misc {
   uint64_t wpin[kMaxPin];
   uint64_t wfull[kMaxRing], wfree[kMaxRing];
   uint64_t dfull[2][5], actfull[2];
+  uint64_t tfull[16];             // tile ordinal k of this CTA published in tiles[k & 15]
+  int tiles[16];
+  int boot[2], fetch[2];
   uint32_t tmem_base, pad_;
   uint32_t src[2][128];
   alignas(16) float bias[kMaxLayers][kBiasPad];
@@ -222,7 +226,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
   const int nl = p.n_layers;
   const int c_last = p.c[nl - 1];
   const int chunks0 = p.kpad[0] / 64;
-  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // tile ordinal k of this CTA -> tile id (or -1 = no more work); published by the gather warps, which
+  // run ahead of every other role
+  auto get_tile = [&](int ord) -> int {
+    mbar_wait(&ms->tfull[ord & 15], (uint32_t)((ord >> 4) & 1));
+    return *reinterpret_cast<volatile int*>(&ms->tiles[ord & 15]);
+  };
 
   if (tid == 0) {
     for (int i = 0; i < kMaxA; ++i) {
@@ -234,6 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
       mbar_init(&ms->wfull[i], 1);
       mbar_init(&ms->wfree[i], 1);
     }
+    for (int i = 0; i < 16; ++i) mbar_init(&ms->tfull[i], 1);
     for (int i = 0; i < 2; ++i) {
       for (int k = 0; k < 5; ++k) mbar_init(&ms->dfull[i][k], 1);   // [0] hidden / plain last, [1+blk] transposed blocks
       mbar_init(&ms->actfull[i], kEpi);
@@ -267,10 +277,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         }
       if (p.n_pinned < p.n_pieces) {
         uint32_t cnt = 0;
-        for (int t0 = 0; t0 < my_tiles; t0 += p.nslot) {
-          const int ns = min(p.nslot, my_tiles - t0);
+        for (int t0 = 0;; t0 += p.nslot) {
+          int ns = p.nslot;
           for (int li = 0; li < nl; ++li)
-            for (int s = 0; s < ns; ++s)
+            for (int s = 0; s < ns; ++s) {
+              if (li == 0 && get_tile(t0 + s) < 0) {
+                ns = s;
+                break;
+              }
               for (int i = 0; i < p.pieces[li]; ++i) {
                 if (p.first_piece[li] + i < p.n_pinned) continue;
                 const uint32_t r = cnt % (uint32_t)p.nr, use = cnt / (uint32_t)p.nr;
@@ -281,6 +295,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                              &ms->wfull[r]);
                 ++cnt;
               }
+            }
+          if (ns < p.nslot) break;
         }
       }
     }
@@ -303,14 +319,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         streamed = true;
         return base + off_ring + slot * (uint32_t)p.ring_slot_bytes;
       };
-      for (int t0 = 0; t0 < my_tiles; t0 += p.nslot) {
-        const int ns = min(p.nslot, my_tiles - t0);
+      for (int t0 = 0;; t0 += p.nslot) {
+        int ns = p.nslot;
         for (int li = 0; li < nl; ++li) {
           const bool last = (li == nl - 1);
           const int chunks = p.kpad[li] / 64;
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
             if (s >= ns) break;
+            if (li == 0 && get_tile(t0 + s) < 0) {
+              ns = s;
+              break;
+            }
             // the context's TMEM region / activation buffer must have been drained by the epilogue of
             // the previous layer (li > 0) or of the previous tile in this context (li == 0)
             if (li > 0 || t0 > 0) {
@@ -373,6 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             }
           }
         }
+        if (ns < p.nslot) break;
       }
     }
   } else if (warp >= 4) {
@@ -387,22 +408,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     struct Special {
       float x, y, z, qx, qy, qz, r, e[4];
     };
-    auto load_src = [&](int it) -> uint32_t {
-      if (it >= my_tiles) return kNoRow;
-      const long long R = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + gt;
+    auto load_src = [&](int tile) -> uint32_t {
+      if (tile < 0) return kNoRow;
+      const long long R = (long long)tile * 128 + gt;
       if (R >= p.total_rows) return kNoRow;
       const uint32_t pt = (uint32_t)(R >> p.log2S);
       const uint32_t b = pt / (uint32_t)p.P;
       const uint32_t id = p.idx ? (uint32_t)__ldg(p.idx + R) : (pt - b * (uint32_t)p.P);
       return b * (uint32_t)p.N + id;
     };
-    auto load_special = [&](uint32_t src, int it, Special& s) {
+    auto load_special = [&](uint32_t src, int tile, Special& s) {
       s.x = s.y = s.z = s.qx = s.qy = s.qz = 0.f;
       s.r = 1.f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) s.e[e] = 0.f;
       if (src == kNoRow || !p.has_special) return;
-      const long long R = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + gt;
+      const long long R = (long long)tile * 128 + gt;
       const uint32_t pt = (uint32_t)(R >> p.log2S);
       if (p.xyz) {
         const float* a = p.xyz + (size_t)src * 3;
@@ -427,17 +448,42 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
       --pend;
     };
 
-    uint32_t src_cur = load_src(0), src_nxt = load_src(1);
+    // next tile of this CTA: static round-robin, or one atomic on the caller-zeroed counter (dynamic: CTAs
+    // that start late -- SMs held by another stream's kernel -- simply find less work left)
+    auto fetch_tile = [&](int ord) -> int {
+      long long t;
+      if (p.tile_counter) t = (long long)gridDim.x + atomicAdd(p.tile_counter, 1);
+      else t = (long long)blockIdx.x + (long long)ord * gridDim.x;
+      return t < p.num_tiles ? (int)t : -1;
+    };
+    int tq0 = (int)blockIdx.x, tq1, tq2, fetched = -1;
+    if (gt == 0) {
+      ms->boot[0] = fetch_tile(1);
+      ms->boot[1] = fetch_tile(2);
+    }
+    named_bar_sync(1, kGather);
+    tq1 = ms->boot[0];
+    tq2 = ms->boot[1];
+    if (gt == 0) fetched = tq2;
+    uint32_t src_cur = load_src(tq0), src_nxt = load_src(tq1);
     Special sp_cur;
-    load_special(src_cur, 0, sp_cur);
-    for (int it = 0; it < my_tiles; ++it) {
-      const long long R0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128;
+    load_special(src_cur, tq0, sp_cur);
+    int it = 0;
+    for (; tq0 >= 0; ++it) {
+      const long long R0 = (long long)tq0 * 128;
       uint32_t* s_src = ms->src[it & 1];
       s_src[gt] = src_cur;
+      if (gt == 0) {
+        ms->tiles[it & 15] = tq0;
+        mbar_arrive(&ms->tfull[it & 15]);
+        ms->fetch[it & 1] = fetched;                      // tile id of ordinal it + 2 (fetched one iteration ago)
+      }
       named_bar_sync(1, kGather);
-      const uint32_t src_nn = load_src(it + 2);           // issued two tiles ahead
+      tq2 = ms->fetch[it & 1];
+      if (gt == 0) fetched = fetch_tile(it + 3);          // latency hidden behind this tile's gather
+      const uint32_t src_nn = load_src(tq2);              // issued two tiles ahead
       Special sp_nxt;
-      load_special(src_nxt, it + 1, sp_nxt);              // issued one tile ahead
+      load_special(src_nxt, tq1, sp_nxt);                 // issued one tile ahead
       for (int kc = 0; kc < chunks0; ++kc, ++a_cnt) {
         const uint32_t stage = a_cnt % (uint32_t)p.na;
         if (a_cnt >= (uint32_t)p.na) mbar_wait(&ms->afree[stage], ((a_cnt / (uint32_t)p.na) - 1) & 1u);
@@ -507,6 +553,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
       src_cur = src_nxt;
       src_nxt = src_nn;
       sp_cur = sp_nxt;
+      tq0 = tq1;
+      tq1 = tq2;
+    }
+    if (gt == 0) {                                        // end marker for the other roles
+      ms->tiles[it & 15] = -1;
+      mbar_arrive(&ms->tfull[it & 15]);
     }
     cp_async_wait<0>();
     while (pend > 0) retire_oldest();
@@ -515,16 +567,24 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     uint32_t d_cnt[2] = {0, 0};      // uses of dfull[s][0]
     uint32_t t_cnt[2] = {0, 0};      // tiles finished in context s (= uses of each dfull[s][1+blk])
     const uint32_t lane_t = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int t0 = 0; t0 < my_tiles; t0 += p.nslot) {
-      const int ns = min(p.nslot, my_tiles - t0);
+    for (int t0 = 0;; t0 += p.nslot) {
+      int ns = p.nslot;
+      int tile_of[2] = {-1, -1};
       for (int li = 0; li < nl; ++li) {
         const bool last = (li == nl - 1);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           if (s >= ns) break;
+          if (li == 0) {
+            tile_of[s] = get_tile(t0 + s);
+            if (tile_of[s] < 0) {
+              ns = s;
+              break;
+            }
+          }
           const uint32_t region = lane_t + (uint32_t)(s * p.region_cols);
           const uint32_t act_s = base + off_act + (uint32_t)(s * p.act_chunks) * kChunkBytes;
-          const long long tile = (long long)blockIdx.x + (long long)(t0 + s) * gridDim.x;
+          const long long tile = tile_of[s];
           if (!last) {
             // ---- hidden layer: TMEM -> +bias -> ReLU -> bf16 -> swizzled ACT (next layer's operand)
             mbar_wait(&ms->dfull[s][0], d_cnt[s] & 1u);
@@ -640,6 +700,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
           mbar_arrive(&ms->actfull[s]);
         }
       }
+      if (ns < p.nslot) break;
     }
   }
 
@@ -834,7 +895,7 @@ extern "C" int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_c
                                   int C1in, const float* xyz, const float* new_xyz, const int32_t* idx, float radius,
                                   const float* radius_t, int normalize_xyz, const float* extra, int E, int n_layers,
                                   const void* const* w_img, const float* const* bias, const int* c_out, int last_relu,
-                                  void* out_cl_bf16, float* out_cf_f32, sad_stream_t stream_) {
+                                  void* out_cl_bf16, float* out_cf_f32, int* tile_counter, sad_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SAD_REQUIRE(B >= 0 && N >= 1 && P >= 0 && S >= 1, "shared_mlp: bad sizes B=%d N=%d P=%d S=%d", B, N, P, S);
   SAD_REQUIRE(S == 1 || S == 2 || S == 4 || S == 8 || S == 16 || S == 32 || S == 64 || S == 128,
@@ -867,6 +928,7 @@ extern "C" int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_c
   p.normalize = normalize_xyz; p.extra = extra; p.E = E; p.has_special = has_special;
   p.n_layers = n_layers; p.last_relu = last_relu;
   p.out_cl = static_cast<__nv_bfloat16*>(out_cl_bf16); p.out_cf = out_cf_f32;
+  p.tile_counter = tile_counter;
   int hidden_max = 0;
   for (int li = 0; li < n_layers; ++li) {
     SAD_REQUIRE(w_img[li] && bias[li] && c_out[li] >= 1, "shared_mlp: layer %d incomplete", li);

@@ -10,7 +10,9 @@ constexpr int kGridCells = kGridDim * kGridDim * kGridDim;     // 32768
 constexpr size_t kGridHeaderBytes = 64;
 constexpr size_t kGridCellBytes = ((size_t)(kGridCells + 1) * 4 + 15) / 16 * 16;
 
-inline __host__ __device__ size_t grid_stride(int N) { return kGridHeaderBytes + kGridCellBytes + (size_t)N * 16; }
+// per scene: header | cell_start | N float4 sorted points | N float min-dist scratch (FPS only, padded to 16 B)
+inline __host__ __device__ size_t grid_scratch_offset(int N) { return kGridHeaderBytes + kGridCellBytes + (size_t)N * 16; }
+inline __host__ __device__ size_t grid_stride(int N) { return grid_scratch_offset(N) + ((size_t)N * 4 + 15) / 16 * 16; }
 
 #ifdef __CUDACC__
 // clamp(int(floor((v - mn) * inv_h)), 0, G-1): monotone non-decreasing in v (every step is).

@@ -25,6 +25,9 @@ from . import _lib, ops
 
 _VP = ctypes.c_void_p
 
+# Hand 128-row tiles to the persistent CTAs through an atomic counter (robust when other streams hold SMs).
+DYNAMIC_TILES = True
+
 
 def _ptr(t: Optional[torch.Tensor]):
     return _VP(t.data_ptr()) if t is not None else _VP(0)
@@ -178,11 +181,13 @@ def fused_mlp(mlp: PreparedMLP, layout: Layout, B, N, P, S, feat_cl=None, feat2_
     out_cf = torch.empty((B, c_last, P), dtype=torch.float32, device=dev) if want_cf else None
     out_cl = torch.empty((B, P, c_last), dtype=torch.bfloat16, device=dev) if want_cl else None
     E = len(layout.extra_cols)
+    counter = torch.zeros(1, dtype=torch.int32, device=dev) if DYNAMIC_TILES else None
     with torch.cuda.device(dev):
         rc = _lib.load().sad_shared_mlp_fwd(
             B, N, P, S, _ptr(feat_cl), layout.c0, _ptr(feat2_cl), layout.c1, _ptr(xyz), _ptr(new_xyz), _ptr(idx),
             float(radius), _ptr(radius_t), int(bool(normalize_xyz)), _ptr(extra), E, len(mlp), w_ptrs, b_ptrs, c_arr,
-            int(bool(last_relu)), _ptr(out_cl), _ptr(out_cf), _VP(torch.cuda.current_stream(dev).cuda_stream))
+            int(bool(last_relu)), _ptr(out_cl), _ptr(out_cf), _ptr(counter),
+            _VP(torch.cuda.current_stream(dev).cuda_stream))
     _lib.check(rc, "shared_mlp")
     return out_cf, out_cl
 

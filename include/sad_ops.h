@@ -63,11 +63,16 @@ SAD_API int sad_furthest_point_sample_fwd(int B, int N, int npoint, const float*
  * bit-identical to sad_furthest_point_sample_fwd / sad_ball_query(_adaptive)_fwd. */
 SAD_API long long sad_scene_grid_workspace_bytes(int B, int N);
 SAD_API int sad_scene_grid_build(int B, int N, const float* xyz, void* workspace, sad_stream_t stream);
-/* a1 over the grid: points resident in the shared memory of a 1..16-CTA cluster, bounding-box
- * culling of the per-pick update.  N <= sad_fps_grid_max_points(), else SAD_EUNSUPPORTED. */
+/* a1 over the grid: bounding-box culling of the per-pick update; points resident in the shared memory
+ * of a 1..16-CTA cluster (or, beyond that capacity, one CTA over the L2-resident sorted array: the
+ * workspace's min-distance scratch is then written, so two FPS calls must not share a workspace).
+ * N <= sad_fps_grid_max_points(), else SAD_EUNSUPPORTED. */
 SAD_API int sad_fps_grid_max_points(void);
 SAD_API int sad_furthest_point_sample_grid_fwd(int B, int N, int npoint, const float* xyz,
-                                               const void* grid_workspace, int32_t* idx, sad_stream_t stream);
+                                               void* grid_workspace, int32_t* idx, sad_stream_t stream);
+/* Test / benchmark hook: 0 = default; 1,2,4,8,16 = cluster kernel with at least that many CTAs per
+ * scene; -1 = single-CTA kernel.  Results never depend on it. */
+SAD_API void sad_fps_grid_force_cluster(int cluster_size);
 /* a3 / a4 over the grid: radius_t (B,npoint) per-query radius or NULL (then `radius`). */
 SAD_API int sad_ball_query_grid_fwd(int B, int N, int npoint, float radius, const float* radius_t,
                                     int nsample, const float* xyz, const void* grid_workspace,
@@ -144,13 +149,16 @@ SAD_API int sad_mlp_pack_weights(const float* W, int cout, int cin, const int32_
  *   w_img, bias    n_layers device pointers (packed images / f32 biases), c_out widths;
  *                  hidden widths % 64 == 0 and <= 256
  *   out_cl_bf16    (B,P,c_last) bf16 channel-last and/or out_cf_f32 (B,c_last,P) f32 (either may be NULL)
+ *   tile_counter   one device int32 the CALLER ZEROES before every call (stream-ordered): tiles are then
+ *                  handed to the persistent CTAs dynamically; NULL = static round-robin
  * bf16 operands, fp32 accumulate/bias/ReLU/max (tolerance 2e-2 vs the fp32 oracle). */
 SAD_API int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_cl, int C0,
                                const void* feat2_cl, int C1in, const float* xyz, const float* new_xyz,
                                const int32_t* idx, float radius, const float* radius_t,
                                int normalize_xyz, const float* extra, int E, int n_layers,
                                const void* const* w_img, const float* const* bias, const int* c_out,
-                               int last_relu, void* out_cl_bf16, float* out_cf_f32, sad_stream_t stream);
+                               int last_relu, void* out_cl_bf16, float* out_cf_f32, int* tile_counter,
+                               sad_stream_t stream);
 
 /* a9 on the internal layout: features (B,m,C) bf16 channel-last -> out (B,n,C) bf16 (C % 8 == 0). */
 SAD_API int sad_three_interpolate_cl_fwd(int B, int C, int m, int n, const void* feat_cl_bf16,

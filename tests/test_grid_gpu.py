@@ -46,13 +46,13 @@ def test_grid_build_is_a_cell_sorted_permutation(ops, B, N):
     xyz = scene(rng, B, N)
     grid = ops.build_scene_grid(cu(xyz))
     raw = grid.workspace.cpu().numpy()
-    stride = HDR + CELL_BYTES + N * 16
+    stride = HDR + CELL_BYTES + N * 16 + (N * 4 + 15) // 16 * 16
     assert raw.size == B * stride
     for b in range(B):
         blk = raw[b * stride:(b + 1) * stride]
         hdr = blk[:16].view(np.float32)
         start = blk[HDR:HDR + CELLS].view(np.uint32)
-        pts = blk[HDR + CELL_BYTES:].view(np.float32).reshape(N, 4)
+        pts = blk[HDR + CELL_BYTES:HDR + CELL_BYTES + N * 16].view(np.float32).reshape(N, 4)
         oidx = pts[:, 3].copy().view(np.uint32)
         assert np.array_equal(np.sort(oidx), np.arange(N, dtype=np.uint32))          # a permutation ...
         assert np.array_equal(pts[:, :3], xyz[b][oidx])                              # ... carrying its coordinates
@@ -76,7 +76,8 @@ def test_grid_build_is_a_cell_sorted_permutation(ops, B, N):
     (2, 20000, 512, 0.25, "uniform"),                    # cluster of 2, ties
     (8, 40000, 2048, None, "surface"),                   # BASELINE config 2 shape (cluster of 4)
     (1, 50000, 300, None, "uniform"),                    # cluster of 8
-    (1, 100003, 200, None, "blobs"),                     # cluster of 16, N % 32 != 0
+    (1, 100003, 200, None, "blobs"),                     # N % 32 != 0, 7 bucket slots per lane
+    (1, 250000, 64, None, "uniform"),                    # beyond the cluster capacity: single-CTA kernel
 ])
 def test_culled_fps_matches_oracle(ops, B, N, npoint, quant, kind):
     rng = np.random.default_rng(N * 7 + npoint)
@@ -85,6 +86,21 @@ def test_culled_fps_matches_oracle(ops, B, N, npoint, quant, kind):
     x = cu(xyz)
     got = ops.furthest_point_sample(x, npoint, ops.build_scene_grid(x))
     assert got.dtype == torch.int32 and tuple(got.shape) == (B, npoint)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("cs", [-1, 1, 2, 4, 16])
+def test_culled_fps_every_kernel_variant_is_bitexact(ops, cs):
+    from sad_b200 import _lib
+    rng = np.random.default_rng(cs + 7)
+    xyz = scene(rng, 2, 9000, 0.125)          # lattice => many exact ties
+    want = C.furthest_point_sample(xyz, 300)
+    x = cu(xyz)
+    _lib.load().sad_fps_grid_force_cluster(cs)
+    try:
+        got = ops.furthest_point_sample(x, 300, ops.build_scene_grid(x))
+    finally:
+        _lib.load().sad_fps_grid_force_cluster(0)
     assert np.array_equal(got.cpu().numpy(), want)
 
 
