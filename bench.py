@@ -169,9 +169,15 @@ class ClockSampler:
 def call_cost(name, a):
     """(algorithmic bytes, flops) of one C-ABI call from its integer arguments (SURVEY 8(d) formulae)."""
     v = [x if isinstance(x, int) else None for x in a]
-    if name == "sad_furthest_point_sample_fwd":
+    if name in ("sad_furthest_point_sample_fwd", "sad_furthest_point_sample_grid_fwd"):
         B, N, P = v[0], v[1], v[2]
         return B * (N * 12 + P * 4), 0
+    if name == "sad_scene_grid_build":
+        B, N = v[0], v[1]
+        return B * (N * 12 + N * 16 + 32769 * 4), 0
+    if name == "sad_ball_query_grid_fwd":
+        B, N, P, S = v[0], v[1], v[2], v[5]
+        return B * (N * 12 + P * 12 + P * S * 4), 0
     if name in ("sad_ball_query_fwd", "sad_ball_query_adaptive_fwd"):
         B, N, P, S = v[0], v[1], v[2], v[4]
         return B * (N * 12 + P * 12 + P * S * 4), 0
@@ -218,7 +224,7 @@ def build_roofline(model, xyz, feat, size, reps=3):
         for name, a, ms in prof.rows():
             nbytes, flops = call_cost(name, a)
             key = name.replace("sad_", "").replace("_fwd", "")
-            if name == "sad_furthest_point_sample_fwd":
+            if name in ("sad_furthest_point_sample_fwd", "sad_furthest_point_sample_grid_fwd"):
                 key += f"[N={a[1]}]"
             d = agg.setdefault(key, {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
             d["ms"] += ms / reps
@@ -248,9 +254,17 @@ def build_roofline(model, xyz, feat, size, reps=3):
                 "frac": top["hbm_frac"], "traffic": None, "peak_source": peaks["src"],
                 "alg_bytes_per_launch": round(top["alg_MB_per_step"] * 1e6 / launches),
                 "launch_ms": round(top["ms_per_step"] / launches, 4),
-                "note": "FPS is a serial-latency kernel (SURVEY H3): its HBM fraction is reported as the contract asks "
-                        "but the meaningful unit is iterations/s; see `kernels` for the HBM- and tensor-bound ops"
+                "note": "FPS is a serial-latency kernel (SURVEY H3: npoint dependent picks, each a block/cluster-wide "
+                        "argmax): its HBM fraction is reported as the contract asks, the meaningful unit is picks/s; "
+                        "see `kernels` for the HBM- and tensor-bound ops and `roofline_tensor` for the fused MLP"
                 if top["kernel"].startswith("furthest") else ""}
+    mlp = next((k for k in kernels if k["kernel"] == "shared_mlp"), None)
+    if mlp is not None and roof["kernel"] != "shared_mlp":
+        n = max(1.0, mlp["launches_per_step"])
+        roof["also"] = {"bound": "tensor", "kernel": "shared_mlp (8 fused gather+MLP+max-pool launches per step)",
+                        "achieved": mlp["TFLOPs"], "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": mlp["tensor_frac"],
+                        "alg_flops_per_launch": round(mlp["GFLOP_per_step"] * 1e9 / n),
+                        "launch_ms": round(mlp["ms_per_step"] / n, 4), "peak_source": peaks["src"]}
     return roof, kernels
 
 
@@ -408,11 +422,13 @@ def attach_traffic(roof):
     (profiles/ncu_full_summary.json, written by tools/ncu_full_summary.py), per launch."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "ncu_full_summary.json")))
-        for row in d.get("kernels", []):
-            if row.get("roofline_key") == roof["kernel"]:
-                roof["traffic"] = row.get("dram_bytes_per_launch")
-                roof["traffic_source"] = "profiles/ncu_full_summary.json"
-                break
+        key = roof["kernel"].split("[")[0]
+        rows = [r for r in d.get("kernels", []) if r.get("roofline_key") == key and "dram_bytes_per_launch" in r]
+        if key.startswith("furthest_point_sample"):      # several FPS launches per step: the one over the raw scene
+            rows = sorted(rows, key=lambda r: -r.get("duration_us", 0))[:1]
+        if rows:
+            roof["traffic"] = int(sum(r["dram_bytes_per_launch"] for r in rows) / len(rows))
+            roof["traffic_source"] = "profiles/ncu_full_summary.json (ncu --set full, mean over the step's launches of this kernel)"
     except Exception:  # noqa: BLE001
         pass
     return roof
