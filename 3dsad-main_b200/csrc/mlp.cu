@@ -92,6 +92,22 @@ struct MlpParams {
   int n_pieces, n_pinned, pinned_bytes, nr, ring_slot_bytes;
 };
 
+#ifdef SAD_MLP_PROFILE
+__device__ long long g_mlp_log[4][2048];        // role (0 epilogue, 1 gather, 2 mma, 3 producer) x (event, clock)...
+__device__ int g_mlp_logn[4];
+#define SAD_LOG(role, ev)                                                                  \
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) == (role == 0 ? 0 : role == 1 ? 4 : role == 2 ? 8 : 9)) { \
+    const int n_ = g_mlp_logn[role];                                                       \
+    if (n_ < 1023) {                                                                       \
+      g_mlp_log[role][2 * n_] = (ev);                                                      \
+      g_mlp_log[role][2 * n_ + 1] = clock64();                                             \
+      g_mlp_logn[role] = n_ + 1;                                                           \
+    }                                                                                      \
+  }
+#else
+#define SAD_LOG(role, ev)
+#endif
+
 struct Misc {
   uint64_t afull[kMaxA], afree[kMaxA];
   uint64_t wpin[kMaxPin];
@@ -114,6 +130,29 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// Prefetch loads: `volatile` pins them where they are written (one / two tiles ahead of their use);
+// a plain __ldg gets sunk by the compiler to just before the first use, exposing the L2 round trip.
+__device__ __forceinline__ float ldg_f32_pinned(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ldg_s32_pinned(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+// one lane of a converged warp (the warp runs the role's loop uniformly; only the tcgen05 / TMA
+// instructions are predicated, so loop state stays in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -302,20 +341,25 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     }
   } else if (warp == 8) {
     // ================================================================== MMA issuer
-    if (lane == 0) {
-      uint32_t a_cnt = 0, w_cnt = 0;
+    {
+      uint32_t a_stage = 0, a_phase = 0, w_slot = 0, w_phase = 0;      // ring positions (wrap counters, no division)
       uint32_t act_cnt[2] = {0, 0};
+      bool pinned_ready = false;                                        // pinned pieces are waited for once
+      const bool leader = elect_one();
       // weights of piece (li, i): pinned address or the next ring slot; returns the smem address
       auto weights = [&](int li, int i, bool& streamed, uint32_t& slot) -> uint32_t {
         const int pc = p.first_piece[li] + i;
         if (pc < p.n_pinned) {
-          mbar_wait(&ms->wpin[pc], 0);
+          if (!pinned_ready) mbar_wait(&ms->wpin[pc], 0);
           streamed = false;
           return base + off_pin + (uint32_t)p.pin_off[li] + (uint32_t)i * (uint32_t)p.piece_bytes[li];
         }
-        slot = w_cnt % (uint32_t)p.nr;
-        mbar_wait(&ms->wfull[slot], (w_cnt / (uint32_t)p.nr) & 1u);
-        ++w_cnt;
+        slot = w_slot;
+        mbar_wait(&ms->wfull[slot], w_phase);
+        if (++w_slot == (uint32_t)p.nr) {
+          w_slot = 0;
+          w_phase ^= 1u;
+        }
         streamed = true;
         return base + off_ring + slot * (uint32_t)p.ring_slot_bytes;
       };
@@ -333,11 +377,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             }
             // the context's TMEM region / activation buffer must have been drained by the epilogue of
             // the previous layer (li > 0) or of the previous tile in this context (li == 0)
+            SAD_LOG(2, 100 + li * 10 + s)
             if (li > 0 || t0 > 0) {
               mbar_wait(&ms->actfull[s], act_cnt[s] & 1u);
               ++act_cnt[s];
             }
             tc_fence_after();
+            SAD_LOG(2, 200 + li * 10 + s)
             const uint32_t region = tmem_base + (uint32_t)(s * p.region_cols);
             const uint32_t act_s = base + off_act + (uint32_t)(s * p.act_chunks) * kChunkBytes;
             if (!(last && p.transposed)) {
@@ -348,8 +394,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 int ksteps = 4;
                 uint32_t stage = 0;
                 if (li == 0) {
-                  stage = a_cnt % (uint32_t)p.na;
-                  mbar_wait(&ms->afull[stage], (a_cnt / (uint32_t)p.na) & 1u);
+                  stage = a_stage;
+                  mbar_wait(&ms->afull[stage], a_phase);
+                  if (++a_stage == (uint32_t)p.na) {
+                    a_stage = 0;
+                    a_phase ^= 1u;
+                  }
                   a_addr = base + off_a + stage * kChunkBytes;
                   if (p.has_special && kc == chunks - 1) ksteps = 1;
                 } else {
@@ -359,20 +409,21 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 uint32_t slot = 0;
                 const uint32_t b_addr = weights(li, kc, streamed, slot);
                 tc_fence_after();
-                for (int n0 = 0; n0 < ncols; n0 += 256) {
-                  const int nn = min(256, ncols - n0);
-                  const uint32_t idesc = umma_idesc(128, nn);
-                  for (int k = 0; k < ksteps; ++k)
-                    umma_bf16(region + (uint32_t)n0, umma_desc(a_addr + k * 32),
-                              umma_desc(b_addr + (uint32_t)n0 * 128u + k * 32), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                if (leader) {
+                  for (int n0 = 0; n0 < ncols; n0 += 256) {
+                    const int nn = min(256, ncols - n0);
+                    const uint32_t idesc = umma_idesc(128, nn);
+                    const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr + (uint32_t)n0 * 128u);
+                    for (int k = 0; k < ksteps; ++k)     // +2 per 32-byte K step in the (addr >> 4) field
+                      umma_bf16(region + (uint32_t)n0, ad + 2u * k, bd + 2u * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                  }
+                  if (li == 0) umma_commit(&ms->afree[stage]);
+                  if (streamed) umma_commit(&ms->wfree[slot]);
+                  if (kc == chunks - 1) umma_commit(&ms->dfull[s][0]);
                 }
-                if (li == 0) {
-                  umma_commit(&ms->afree[stage]);
-                  ++a_cnt;
-                }
-                if (streamed) umma_commit(&ms->wfree[slot]);
               }
-              umma_commit(&ms->dfull[s][0]);
+              __syncwarp();
+              SAD_LOG(2, 300 + li * 10 + s)
             } else {
               // transposed last layer: D^T (128 channels x 128 rows) = W_blk . H^T, one commit per block
               const uint32_t idesc = umma_idesc(128, 128);
@@ -383,16 +434,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                   const uint32_t a_addr = weights(li, blk * chunks + kc, streamed, slot);   // W block rows = M
                   const uint32_t b_addr = act_s + (uint32_t)kc * kChunkBytes;               // activations rows = N
                   tc_fence_after();
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16(region + (uint32_t)(blk * 128), umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32),
-                              idesc, (kc > 0 || k > 0) ? 1u : 0u);
-                  if (streamed) umma_commit(&ms->wfree[slot]);
+                  if (leader) {
+                    const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_bf16(region + (uint32_t)(blk * 128), ad + 2u * k, bd + 2u * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                    if (streamed) umma_commit(&ms->wfree[slot]);
+                    // one barrier per block: never two phases outstanding
+                    if (kc == chunks - 1) umma_commit(&ms->dfull[s][1 + blk]);
+                  }
                 }
-                umma_commit(&ms->dfull[s][1 + blk]);    // one barrier per block: never two phases outstanding
+                __syncwarp();
+                SAD_LOG(2, 300 + li * 10 + s)
               }
             }
           }
         }
+        pinned_ready = true;
         if (ns < p.nslot) break;
       }
     }
@@ -401,7 +459,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     const int gt = tid - kEpi;                 // row of the tile this thread owns for bookkeeping / special chunk
     const int unit = gt & 7, rbase = gt >> 3;
     const int nf0 = p.C0 / 64, nf1 = p.C1in / 64;
-    uint32_t a_cnt = 0;
+    uint32_t g_stage = 0, g_phase = 0;                 // afree parity of the NEXT wait (the first pass over the ring never waits)
+    bool g_first = true;
     int pend = 0;
     uint32_t ps0 = 0, ps1 = 0, ps2 = 0;        // stages of the cp.async groups still in flight (oldest first)
 
@@ -414,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
       if (R >= p.total_rows) return kNoRow;
       const uint32_t pt = (uint32_t)(R >> p.log2S);
       const uint32_t b = pt / (uint32_t)p.P;
-      const uint32_t id = p.idx ? (uint32_t)__ldg(p.idx + R) : (pt - b * (uint32_t)p.P);
+      const uint32_t id = p.idx ? (uint32_t)ldg_s32_pinned(p.idx + R) : (pt - b * (uint32_t)p.P);
       return b * (uint32_t)p.N + id;
     };
     auto load_special = [&](uint32_t src, int tile, Special& s) {
@@ -428,17 +487,17 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
       if (p.xyz) {
         const float* a = p.xyz + (size_t)src * 3;
         const float* q = p.new_xyz + (size_t)pt * 3;
-        s.x = __ldg(a);
-        s.y = __ldg(a + 1);
-        s.z = __ldg(a + 2);
-        s.qx = __ldg(q);
-        s.qy = __ldg(q + 1);
-        s.qz = __ldg(q + 2);
-        if (p.normalize) s.r = p.radius_t ? __ldg(p.radius_t + pt) : p.radius;
+        s.x = ldg_f32_pinned(a);
+        s.y = ldg_f32_pinned(a + 1);
+        s.z = ldg_f32_pinned(a + 2);
+        s.qx = ldg_f32_pinned(q);
+        s.qy = ldg_f32_pinned(q + 1);
+        s.qz = ldg_f32_pinned(q + 2);
+        if (p.normalize) s.r = p.radius_t ? ldg_f32_pinned(p.radius_t + pt) : p.radius;
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (e < p.E) s.e[e] = __ldg(p.extra + (size_t)src * p.E + e);
+        if (e < p.E) s.e[e] = ldg_f32_pinned(p.extra + (size_t)src * p.E + e);
     };
     auto retire_oldest = [&]() {               // oldest cp.async group has landed: publish its stage
       fence_proxy_async();
@@ -478,15 +537,30 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         mbar_arrive(&ms->tfull[it & 15]);
         ms->fetch[it & 1] = fetched;                      // tile id of ordinal it + 2 (fetched one iteration ago)
       }
+      SAD_LOG(1, 100)
       named_bar_sync(1, kGather);
+      SAD_LOG(1, 200)
       tq2 = ms->fetch[it & 1];
       if (gt == 0) fetched = fetch_tile(it + 3);          // latency hidden behind this tile's gather
       const uint32_t src_nn = load_src(tq2);              // issued two tiles ahead
       Special sp_nxt;
       load_special(src_nxt, tq1, sp_nxt);                 // issued one tile ahead
-      for (int kc = 0; kc < chunks0; ++kc, ++a_cnt) {
-        const uint32_t stage = a_cnt % (uint32_t)p.na;
-        if (a_cnt >= (uint32_t)p.na) mbar_wait(&ms->afree[stage], ((a_cnt / (uint32_t)p.na) - 1) & 1u);
+      for (int kc = 0; kc < chunks0; ++kc) {
+        const uint32_t stage = g_stage;
+        if (!g_first && !mbar_try_wait(&ms->afree[stage], g_phase)) {
+          // ring full: publish everything already issued before blocking, or the MMA warp (which frees
+          // the stage) would be waiting for a chunk that only the next issue would have published
+          if (pend > 0) {
+            cp_async_wait<0>();
+            while (pend > 0) retire_oldest();
+          }
+          mbar_wait(&ms->afree[stage], g_phase);
+        }
+        if (++g_stage == (uint32_t)p.na) {
+          g_stage = 0;
+          if (g_first) g_first = false;
+          else g_phase ^= 1u;
+        }
         const uint32_t dst = base + off_a + stage * kChunkBytes;
         if (kc < nf0 + nf1) {
           if (kc < nf0) {
@@ -550,6 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
           mbar_arrive(&ms->afull[stage]);
         }
       }
+      SAD_LOG(1, 300)
       src_cur = src_nxt;
       src_nxt = src_nn;
       sp_cur = sp_nxt;
@@ -585,11 +660,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
           const uint32_t region = lane_t + (uint32_t)(s * p.region_cols);
           const uint32_t act_s = base + off_act + (uint32_t)(s * p.act_chunks) * kChunkBytes;
           const long long tile = tile_of[s];
+          SAD_LOG(0, 100 + li * 10 + s)
           if (!last) {
             // ---- hidden layer: TMEM -> +bias -> ReLU -> bf16 -> swizzled ACT (next layer's operand)
             mbar_wait(&ms->dfull[s][0], d_cnt[s] & 1u);
             ++d_cnt[s];
             tc_fence_after();
+            SAD_LOG(0, 200 + li * 10 + s)
             const float* sb = ms->bias[li];
             for (int c0 = 0; c0 < p.c[li]; c0 += 64) {
               uint32_t v0[32], v1[32];
@@ -619,6 +696,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             for (int blk = 0; blk < p.nblk; ++blk) {
               mbar_wait(&ms->dfull[s][1 + blk], t_cnt[s] & 1u);
               tc_fence_after();
+              SAD_LOG(0, 200 + li * 10 + s)
               const int ch = blk * 128 + tid;
               const bool ch_ok = ch < c_last;
               const float bias = ms->bias[li][ch_ok ? ch : 0];
@@ -698,6 +776,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
           }
           tc_fence_before();
           mbar_arrive(&ms->actfull[s]);
+          SAD_LOG(0, 300 + li * 10 + s)
         }
       }
       if (ns < p.nslot) break;
@@ -770,6 +849,18 @@ cf_to_cl_kernel(int C, int N, const float* __restrict__ in, __nv_bfloat16* __res
 //   mode 1  last layer, S  > 1    transposed evaluation: pieces of 128 rows, blocked [blk][kc]
 //   mode 2  last layer, S == 1    plain evaluation: piece = cout rounded up to 32 rows (<= 512)
 static int image_rows(int cout, int mode) { return mode == 1 ? 128 : (mode == 2 ? (cout + 31) / 32 * 32 : cout); }
+
+#ifdef SAD_MLP_PROFILE
+// tools only: copy the CTA-0 timeline of the last launch to the host and reset it
+extern "C" int sad_mlp_profile_dump(long long* host_log /*4*2048*/, int* host_n /*4*/) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host_log, g_mlp_log, sizeof(long long) * 4 * 2048);
+  cudaMemcpyFromSymbol(host_n, g_mlp_logn, sizeof(int) * 4);
+  int z[4] = {0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_mlp_logn, z, sizeof(z));
+  return 0;
+}
+#endif
 
 extern "C" long long sad_mlp_weight_image_bytes(int cout, int kpad, int is_last) {
   if (cout < 1 || kpad < 64 || (kpad % 64) || is_last < 0 || is_last > 2) return -1;
@@ -872,6 +963,7 @@ static bool plan_launch(MlpParams& p, int hidden_max, size_t& smem_out) {
       p.nslot = nslot;
       p.na = na;
       p.depth = na >= 4 ? 3 : (na == 3 ? 2 : 1);
+      if (const char* e_d = getenv("SAD_MLP_DEPTH")) p.depth = atoi(e_d) < 1 ? 1 : (atoi(e_d) > p.depth ? p.depth : atoi(e_d));
       p.n_pinned = n_pinned;
       p.pinned_bytes = (int)pinned;
       p.nr = nr;
