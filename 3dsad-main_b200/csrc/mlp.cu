@@ -97,11 +97,10 @@ __device__ long long g_mlp_log[4][2048];        // role (0 epilogue, 1 gather, 2
 __device__ int g_mlp_logn[4];
 #define SAD_LOG(role, ev)                                                                  \
   if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) == (role == 0 ? 0 : role == 1 ? 4 : role == 2 ? 8 : 9)) { \
-    const int n_ = g_mlp_logn[role];                                                       \
-    if (n_ < 1023) {                                                                       \
-      g_mlp_log[role][2 * n_] = (ev);                                                      \
-      g_mlp_log[role][2 * n_ + 1] = clock64();                                             \
-      g_mlp_logn[role] = n_ + 1;                                                           \
+    if (sad_logn < 1023) {                                                                 \
+      g_mlp_log[role][2 * sad_logn] = (ev);                                                \
+      g_mlp_log[role][2 * sad_logn + 1] = clock64();                                       \
+      g_mlp_logn[role] = ++sad_logn;                                                       \
     }                                                                                      \
   }
 #else
@@ -262,6 +261,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
   Misc* ms = reinterpret_cast<Misc*>(gbase + off_misc);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef SAD_MLP_PROFILE
+  int sad_logn = 0;      // events logged by this thread (register counter: the log must not stall the role)
+#endif
   const int nl = p.n_layers;
   const int c_last = p.c[nl - 1];
   const int chunks0 = p.kpad[0] / 64;

@@ -68,6 +68,7 @@ def cpu_hot_path_rate(n_scenes, n_points, reps=1, seed0=0):
     from sad_b200.scenes import make_scenes, make_sizes
 
     C.build()
+    C.set_threads(host_threads())
     params = make_params(0)
     xyz, feat = make_scenes(n_scenes, n_points, "surface", first_scene=seed0)
     size = make_sizes(n_scenes, LAYER_CFG["agg"][0], first_scene=seed0)
@@ -446,6 +447,9 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
+        # torchrun pins its workers to one OpenMP thread; the CPU arm uses every host thread it can get
+        for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+            os.environ[k] = str(host_threads())
         return run_reference(args)
     return run_ours(args)
 

@@ -39,6 +39,11 @@ def lib():
     return _lib
 
 
+def set_threads(n: int) -> None:
+    """Use `n` OpenMP threads from now on (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib().orc_set_threads(int(n))
+
+
 def _p(a, ct):
     return a.ctypes.data_as(ctypes.POINTER(ct))
 

@@ -12,6 +12,9 @@
  *    rounding per operation; vectorisation keeps per-element IEEE semantics).
  */
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -139,4 +142,13 @@ int orc_three_interpolate(int B, int C, int m, int n, const float *features, con
     }
   }
   return 0;
+}
+
+/* Thread count of the OpenMP regions above (bench.py: torchrun exports OMP_NUM_THREADS=1). */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n >= 1) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
 }

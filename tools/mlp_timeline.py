@@ -20,7 +20,7 @@ def layers(ch):
 def timeline(tag, fn, first=0, count=60):
     fn(); torch.cuda.synchronize()
     log = np.zeros((4, 2048), dtype=np.int64); n = np.zeros(4, dtype=np.int32)
-    dump(log.ctypes.data, n.ctypes.data)          # reset
+    dump(log.ctypes.data, n.ctypes.data)          # reset (counters live in registers: nothing to clear on the device)
     fn(); torch.cuda.synchronize()
     dump(log.ctypes.data, n.ctypes.data)
     ev = []
