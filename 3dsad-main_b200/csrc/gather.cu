@@ -7,6 +7,13 @@
 // gathers (the source row f[b,c,:] is L1/L2 resident) and ONE 128-bit streaming store
 // per channel, so every store instruction of a warp writes 512 contiguous bytes.
 // gather_operation is grouping_operation with nsample == 1.
+//
+// Row-staged variant (group_fwd_staged_kernel), used when a chunk of source rows fits shared memory
+// and every row is read many times (P*S >= 2N: the SA2..SA4 / vote-aggregation shapes): the chunk
+// f[b, c0:c0+cn, :] is ONE contiguous block of the channel-first tensor, so a single TMA bulk copy
+// brings it on chip; the 4-byte gathers then hit shared-memory banks instead of L1 sectors (a
+// random warp-wide gather costs ~3 bank wavefronts instead of up to 32 sector lookups), and HBM sees
+// each source row once plus the streaming 128-bit stores.
 #include "sad_common.cuh"
 
 namespace {
@@ -52,6 +59,43 @@ group_fwd_kernel(int C, int N, long long PS, const float* __restrict__ features,
   }
 }
 
+__global__ void __launch_bounds__(GR_T)
+group_fwd_staged_kernel(int C, int N, long long quads, int cch, const float* __restrict__ features,
+                        const int32_t* __restrict__ idx, float* __restrict__ out) {
+  extern __shared__ __align__(128) float s_rows[];          // [cn][N]
+  __shared__ __align__(8) uint64_t s_bar;
+  using namespace sad;
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * cch;
+  const int cn = min(cch, C - c0);
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    const uint32_t bytes = (uint32_t)cn * (uint32_t)N * 4u;
+    mbar_arrive_expect_tx(&s_bar, bytes);
+    tma_bulk_g2s(s_rows, features + ((size_t)b * C + c0) * N, bytes, &s_bar);
+  }
+  __syncthreads();
+  // this CTA's share of the position quads
+  const long long per = (quads + gridDim.x - 1) / gridDim.x;
+  const long long q0 = (long long)blockIdx.x * per, q1 = min(quads, q0 + per);
+  const int4* ip = reinterpret_cast<const int4*>(idx) + (size_t)b * quads;
+  float4* op = reinterpret_cast<float4*>(out) + ((size_t)b * C + c0) * quads;
+  long long q = q0 + threadIdx.x;
+  int4 id = (q < q1) ? __ldg(ip + q) : make_int4(0, 0, 0, 0);
+  mbar_wait(&s_bar, 0);
+  for (; q < q1; q += GR_T) {
+    const long long qn = q + GR_T;
+    const int4 nxt = (qn < q1) ? __ldg(ip + qn) : make_int4(0, 0, 0, 0);      // next indices while this quad gathers
+#pragma unroll 4
+    for (int c = 0; c < cn; ++c) {
+      const float* r = s_rows + (size_t)c * N;
+      __stcs(op + (size_t)c * quads + q, make_float4(r[id.x], r[id.y], r[id.z], r[id.w]));
+    }
+    id = nxt;
+  }
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(GR_T)
 group_bwd_kernel(int C, int N, long long PS, const float* __restrict__ grad_out,
@@ -92,6 +136,30 @@ int group_fwd(const char* name, int B, int C, int N, long long PS, const float* 
   SAD_REQUIRE(features && idx && out, "%s: null pointer", name);
   SAD_REQUIRE(B <= 65535 && sad_ceil_div(C, GR_CCH) <= 65535, "%s: B/C exceed grid limits", name);
   const bool vec = (PS % 4 == 0) && aligned16(idx) && aligned16(out);
+  // row-staged path: rows fit (<= 72 KB per CTA, so three CTAs share an SM), are 16-byte granular, and are re-read
+  // often enough (P*S >= 2N) to pay for staging
+  const int cch = (N % 4 == 0 && N <= 4608) ? (int)(18432 / N < 16 ? 18432 / N : 16) : 0;
+  if (vec && cch >= 4 && PS >= 2LL * N && aligned16(features)) {
+    const long long quads = PS / 4;
+    const int ychunks = sad_ceil_div(C, cch);
+    long long x = sad_ceil_div(444, (long long)ychunks * B);            // ~3 CTAs per SM in flight ...
+    const long long xmax = quads / N > 1 ? quads / N : 1;               // ... but >= N quads each (4x the staged bytes)
+    if (x > xmax) x = xmax;
+    if (x < 1) x = 1;
+    SAD_REQUIRE(ychunks <= 65535, "%s: C exceeds grid limits", name);
+    const size_t smem = (size_t)cch * N * sizeof(float);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    SAD_CUDA_OK(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+      SAD_CUDA_OK(cudaFuncSetAttribute(group_fwd_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 73728));
+      configured_dev = dev;
+    }
+    dim3 g2((unsigned)x, (unsigned)ychunks, (unsigned)B);
+    group_fwd_staged_kernel<<<g2, GR_T, smem, stream>>>(C, N, quads, cch, features, idx, out);
+    SAD_LAUNCH_CHECK(name);
+    return SAD_OK;
+  }
   dim3 grid((unsigned)sad_ceil_div(vec ? PS / 4 : PS, GR_T), (unsigned)sad_ceil_div(C, GR_CCH), (unsigned)B);
   if (vec)
     group_fwd_kernel<true><<<grid, GR_T, 0, stream>>>(C, N, PS, features, idx, out);
