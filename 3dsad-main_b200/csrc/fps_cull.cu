@@ -153,19 +153,29 @@ fps_cull_kernel(int N, int npoint, const float* __restrict__ xyz, const uint8_t*
 #ifdef SAD_FPS_PROFILE
     nupd += __popc(mask);
 #endif
-    while (mask) {
-      const int s = __ffs(mask) - 1;
+    while (mask) {                                     // two buckets per step: their redux chains overlap
+      const int s0 = __ffs(mask) - 1;
       mask &= mask - 1;
-      const float4 p = wp[s * NW * 32];
-      const float m0 = wm[s * NW * 32];
-      const float m = fminf(m0, sqdist(p.x, p.y, p.z, qx, qy, qz));
-      if (m < m0) wm[s * NW * 32] = m;
-      const uint32_t mb = __float_as_uint(m);       // m >= 0: bit order == value order
-      const uint32_t mx = __reduce_max_sync(FULL, mb);
-      const uint32_t ix = __reduce_min_sync(FULL, mb == mx ? __float_as_uint(p.w) : kInf);
-      if (lane == s) {
-        bmax = __uint_as_float(mx);
-        bidx = ix;
+      const bool two = mask != 0u;
+      const int s1 = two ? __ffs(mask) - 1 : s0;
+      if (two) mask &= mask - 1;
+      const float4 pa = wp[s0 * NW * 32], pb = wp[s1 * NW * 32];
+      const float ma0 = wm[s0 * NW * 32], mb0 = wm[s1 * NW * 32];
+      const float ma = fminf(ma0, sqdist(pa.x, pa.y, pa.z, qx, qy, qz));
+      const float mb = fminf(mb0, sqdist(pb.x, pb.y, pb.z, qx, qy, qz));
+      if (ma < ma0) wm[s0 * NW * 32] = ma;
+      if (two && mb < mb0) wm[s1 * NW * 32] = mb;
+      const uint32_t ua = __float_as_uint(ma), ub = __float_as_uint(mb);       // >= 0: bit order == value order
+      const uint32_t mxa = __reduce_max_sync(FULL, ua), mxb = __reduce_max_sync(FULL, ub);
+      const uint32_t ixa = __reduce_min_sync(FULL, ua == mxa ? __float_as_uint(pa.w) : kInf);
+      const uint32_t ixb = __reduce_min_sync(FULL, ub == mxb ? __float_as_uint(pb.w) : kInf);
+      if (lane == s0) {
+        bmax = __uint_as_float(mxa);
+        bidx = ixa;
+      }
+      if (two && lane == s1) {
+        bmax = __uint_as_float(mxb);
+        bidx = ixb;
       }
     }
     SAD_MARK(1)

@@ -36,7 +36,11 @@ def timeline(tag, fn, first=0, count=60):
 
 
 dev = "cuda"
-for (N, P, S, C, hid) in [(40000, 2048 * 8, 64, 0, [64, 64, 128]), (2048, 1024 * 8, 32, 128, [128, 128, 256])]:
+shapes = [(40000, 2048 * 8, 64, 0, [64, 64, 128]), (2048, 1024 * 8, 32, 128, [128, 128, 256]),
+          (512, 256 * 8, 16, 256, [128, 128, 256])]
+if len(sys.argv) > 2:
+    shapes = [shapes[int(sys.argv[2])]]
+for (N, P, S, C, hid) in shapes:
     xyz = torch.rand(1, N, 3, device=dev)
     new_xyz = torch.rand(1, P, 3, device=dev)
     idx = torch.randint(0, N, (1, P, S), device=dev, dtype=torch.int32)
