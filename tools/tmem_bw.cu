@@ -1,0 +1,69 @@
+// TMEM read bandwidth of tcgen05.ld on this GPU (what bounds the fused MLP's epilogues).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/tmem_bw tools/tmem_bw.cu && ./tools/tmem_bw
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// `nwarps` warps (warp w reads lane quadrant w % 4) each issue `iters` x 4 x32 loads (16 KB per warp per iteration)
+__global__ void tmem_read(int iters, unsigned long long* cycles, uint32_t* sink) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((uint32_t)__cvta_generic_to_shared(&slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t base = *(volatile uint32_t*)&slot + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  __syncthreads();
+  const unsigned long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    uint32_t a[32], b[32];
+    ld32(base + ((i * 64) & 448), a);
+    ld32(base + ((i * 64 + 32) & 448), b);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc ^= a[k] ^ b[k];
+  }
+  __syncthreads();
+  const unsigned long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (acc == 0x12345678u) sink[0] = acc;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*(volatile uint32_t*)&slot) : "memory");
+}
+
+int main() {
+  unsigned long long* cyc;
+  uint32_t* sink;
+  cudaMalloc(&cyc, 148 * 8);
+  cudaMalloc(&sink, 4);
+  const int iters = 4096;
+  for (int nw : {1, 2, 4, 8, 16}) {
+    tmem_read<<<148, nw * 32, 0>>>(iters, cyc, sink);
+    cudaDeviceSynchronize();
+    tmem_read<<<148, nw * 32, 0>>>(iters, cyc, sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    unsigned long long h[148];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    const double bytes = (double)nw * iters * 2 * 32 * 32 * 4;      // per CTA (= per SM)
+    printf("%2d warps/SM: %8llu cycles  -> %6.1f B/clk/SM (%s)\n", nw, h[0], bytes / (double)h[0], cudaGetErrorString(e));
+  }
+  return 0;
+}
