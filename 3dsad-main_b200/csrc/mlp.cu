@@ -964,7 +964,10 @@ static bool plan_launch(MlpParams& p, int hidden_max, size_t& smem_out) {
       }
       p.nslot = nslot;
       p.na = na;
-      p.depth = na >= 4 ? 3 : (na == 3 ? 2 : 1);
+      // cp.async groups a gather thread keeps in flight before it publishes the oldest chunk.  Measured (SA2: 80 us
+      // at 1, 84 at 2, 92 at 3): publishing every chunk as soon as it lands beats deeper prefetch, because the MMA warp
+      // consumes chunks in order and the four gather warps already overlap each other's round trips.
+      p.depth = 1;
       if (const char* e_d = getenv("SAD_MLP_DEPTH")) p.depth = atoi(e_d) < 1 ? 1 : (atoi(e_d) > p.depth ? p.depth : atoi(e_d));
       p.n_pinned = n_pinned;
       p.pinned_bytes = (int)pinned;
