@@ -483,6 +483,8 @@ extern "C" int sad_furthest_point_sample_grid_fwd(int B, int N, int npoint, cons
   SAD_REQUIRE(B >= 0 && N >= 1 && npoint >= 1, "furthest_point_sample_grid: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
   if (B == 0) return SAD_OK;
   SAD_REQUIRE(xyz && grid_ws && idx, "furthest_point_sample_grid: null pointer");
+  if (N > 16 * (FC_MAX_SLOTS * FC_NW * 32) && N <= 204800 && g_cull_cluster == 0)
+    return sad_furthest_point_sample_fwd(B, N, npoint, xyz, idx, stream_);   // beyond the cluster capacity the register-resident kernel wins
   if (N > sad_fps_grid_max_points()) {
     sad_set_error("furthest_point_sample_grid: N=%d exceeds the capacity (%d)", N, sad_fps_grid_max_points());
     return SAD_EUNSUPPORTED;
