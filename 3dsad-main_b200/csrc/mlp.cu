@@ -935,7 +935,11 @@ static bool plan_launch(MlpParams& p, int hidden_max, size_t& smem_out) {
     if (p.piece_bytes[li] > max_piece) max_piece = p.piece_bytes[li];
   }
   p.n_pieces = np;
-  const long long avail = 227 * 1024 - 1024 - kMiscBytes;
+  // shared-memory budget per CTA: everything the SM has by default; SAD_MLP_SMEM_KB (tuning hook) leaves room for
+  // another stream's CTAs (e.g. a latency-bound FPS cluster) to share the SM
+  long long budget_kb = 227;
+  if (const char* e_kb = getenv("SAD_MLP_SMEM_KB")) budget_kb = atoi(e_kb) < 64 ? 64 : (atoi(e_kb) > 227 ? 227 : atoi(e_kb));
+  const long long avail = budget_kb * 1024 - 1024 - kMiscBytes;
   // tuning hooks (benchmarks only): cap the tile contexts / A-ring stages, force a minimum weight ring
   const char* e_slot = getenv("SAD_MLP_NSLOT");
   const char* e_na = getenv("SAD_MLP_NA");
