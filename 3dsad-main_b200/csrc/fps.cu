@@ -225,6 +225,11 @@ int dispatch_big(int T, int P, int B, int N, int npoint, const float* xyz, int32
 
 }  // namespace
 
+#ifdef SAD_TOOLS_ABLATE
+__global__ void ablate_strided_idx_plain(int N, int npoint, int32_t* idx) {
+  for (int j = threadIdx.x; j < npoint; j += blockDim.x) idx[(size_t)blockIdx.x * npoint + j] = (int32_t)((long long)j * N / npoint);
+}
+#endif
 // Exposed for tests/benchmarks: force a cluster size (0 = heuristic).
 static thread_local int g_force_cs = 0;
 extern "C" void sad_fps_force_cluster_size(int cs) { g_force_cs = cs; }
@@ -236,6 +241,12 @@ extern "C" int sad_furthest_point_sample_fwd(int B, int N, int npoint, const flo
               npoint);
   if (B == 0) return SAD_OK;
   SAD_REQUIRE(xyz && idx, "furthest_point_sample: null pointer");
+#ifdef SAD_TOOLS_ABLATE
+  if (sad_ablate_mask() & 4) {
+    ablate_strided_idx_plain<<<B, 256, 0, stream>>>(N, npoint, idx);
+    return SAD_OK;
+  }
+#endif
   constexpr int T = 128, PMAX = 48;
   if ((long long)N > 16LL * 512 * 25) {
     sad_set_error("furthest_point_sample: N=%d exceeds the register-resident capacity (%d)", N, 16 * 512 * 25);

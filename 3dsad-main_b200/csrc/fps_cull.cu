@@ -471,7 +471,16 @@ int launch_cull(int B, int N, int npoint, const float* xyz, const void* ws, int3
 // Tests / benchmarks: 0 = default (shared-memory-resident cluster kernel with the fewest CTAs that hold the
 // scene; single-CTA L2-resident kernel beyond its capacity); 1,2,4,8,16 = cluster kernel with at least that
 // many CTAs per scene; -1 = single-CTA kernel.
-static thread_local int g_cull_cluster = 0;
+#ifdef SAD_TOOLS_ABLATE
+__global__ void ablate_strided_idx(int N, int npoint, int32_t* idx) {
+  for (int j = threadIdx.x; j < npoint; j += blockDim.x) idx[(size_t)blockIdx.x * npoint + j] = (int32_t)((long long)j * N / npoint);
+}
+#endif
+static int env_cull_cluster() {                       // SAD_FPS_CLUSTER: tools only (A/B runs of the kernel choice)
+  const char* e = getenv("SAD_FPS_CLUSTER");
+  return e ? atoi(e) : 0;
+}
+static thread_local int g_cull_cluster = env_cull_cluster();
 extern "C" void sad_fps_grid_force_cluster(int cs) { g_cull_cluster = cs; }
 
 // Largest scene the culled kernels accept.
@@ -483,6 +492,12 @@ extern "C" int sad_furthest_point_sample_grid_fwd(int B, int N, int npoint, cons
   SAD_REQUIRE(B >= 0 && N >= 1 && npoint >= 1, "furthest_point_sample_grid: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
   if (B == 0) return SAD_OK;
   SAD_REQUIRE(xyz && grid_ws && idx, "furthest_point_sample_grid: null pointer");
+#ifdef SAD_TOOLS_ABLATE
+  if (sad_ablate_mask() & 1) {                           // tools only: what does the pipeline cost without this kernel?
+    ablate_strided_idx<<<B, 256, 0, stream>>>(N, npoint, idx);
+    return SAD_OK;
+  }
+#endif
   if (N > 16 * (FC_MAX_SLOTS * FC_NW * 32) && N <= 204800 && g_cull_cluster == 0)
     return sad_furthest_point_sample_fwd(B, N, npoint, xyz, idx, stream_);   // beyond the cluster capacity the register-resident kernel wins
   if (N > sad_fps_grid_max_points()) {

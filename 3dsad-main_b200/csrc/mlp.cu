@@ -5,21 +5,21 @@
 // One launch per SA / FP / voting stage, persistent CTAs (one per SM), 128-row tiles
 // (row = (query point, sample)), warp-specialised and software-pipelined:
 //
-//   warps 4-7  GATHER   build the layer-1 operand of tile t+1, t+2, ... straight in shared memory
+//   warps 8-11 GATHER   build the layer-1 operand of tile t+1, t+2, ... straight in shared memory
 //                       in the tcgen05 K-major SWIZZLE_128B layout while tile t is still being
 //                       computed: channel-last bf16 feature rows fetched by `idx` with 16-byte
 //                       cp.async through an A-ring of 16 KB stages (several groups in flight per
 //                       thread; the grouped tensor never exists in HBM); the relative,
 //                       radius-normalised xyz (+ fp32 scalar features) form one extra 16-wide K
 //                       step whose dependent loads (idx -> xyz) are prefetched one tile ahead.
-//   warp 9     WEIGHTS  pre-swizzled bf16 weight images by TMA bulk copy (cp.async.bulk): as many
+//   warp 14    WEIGHTS  pre-swizzled bf16 weight images by TMA bulk copy (cp.async.bulk): as many
 //                       pieces as fit stay PINNED in shared memory for the whole kernel, the rest
 //                       stream through an mbarrier ring.
-//   warp 8     MMA      one thread issues tcgen05.mma (bf16 x bf16 -> fp32 in TMEM).  Two tile
+//   warps 12,13 MMA     one warp per tile context; one elected thread issues tcgen05.mma (bf16 x bf16 -> fp32 in TMEM).  Two tile
 //                       contexts (A, B) ping-pong: while the epilogue warps drain layer l of tile
 //                       A the tensor core runs layer l of tile B, so neither side waits for the
 //                       other's latency chain.
-//   warps 0-3  EPILOGUE thread == TMEM lane.  Hidden layers: tcgen05.ld -> +bias (shared memory)
+//   warps 0-7  EPILOGUE two warpgroups, one per tile context (they drain concurrently); thread == TMEM lane.  Hidden layers: tcgen05.ld -> +bias (shared memory)
 //                       -> ReLU fused into cvt.rn.relu.bf16x2 -> swizzled shared memory = the next
 //                       layer's operand.  Last layer, pooled stages (S > 1): evaluated TRANSPOSED
 //                       (D^T = W . H^T) so a lane is an output channel and the nsample rows of a
@@ -36,20 +36,28 @@ namespace {
 
 using namespace sad;
 
-constexpr int kEpi = 128;                // epilogue threads (warps 0-3)
-constexpr int kGather = 128;             // gather threads   (warps 4-7)
-constexpr int kThreads = 320;            // + MMA warp (8) + weight-TMA warp (9)
+constexpr int kEpiWG = 128;              // threads of one epilogue warpgroup (thread == TMEM lane)
+constexpr int kEpi = 2 * kEpiWG;         // two epilogue warpgroups: warps 0-3 drain tile context 0, warps 4-7 context 1
+constexpr int kGather = 128;             // gather threads   (warps 8-11)
+constexpr int kWarpMma = 12, kWarpTma = 14;
+constexpr int kThreads = 480;            // + MMA warps (12: context 0, 13: context 1) + weight-TMA warp (14)
 constexpr int kChunkBytes = 128 * 128;   // one 128-row x 64-bf16 K chunk (A operand / activations)
 constexpr int kMaxLayers = 3;
 constexpr int kMaxA = 8;                 // A-ring stages
 constexpr int kMaxPin = 32;              // pinned weight pieces
 constexpr int kMaxRing = 8;              // streamed weight ring slots
+// "full" barriers of the two rings are indexed by ring POSITION modulo kFullBars, not by stage: with one consumer
+// warp per tile context a consumer skips the other context's share of the ring, and a parity wait is only sound
+// while the waiter is less than one barrier period away from the last fill it knows to be complete
+// (plan_launch checks share + 1 + stages <= kFullBars before it allows two contexts).
+constexpr int kFullBars = 32;
 constexpr int kBiasPad = 544;            // floats per layer in the shared bias table
 constexpr int kMiscBytes = 12288;
 constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 
 struct MlpParams {
   int B, N, P, S, log2S;
+  int log2P;                      // >= 0 when P is a power of two (batch index by shift), else -1
   long long total_rows;
   int num_tiles;
   uint32_t total_points;
@@ -96,7 +104,7 @@ struct MlpParams {
 __device__ long long g_mlp_log[4][2048];        // role (0 epilogue, 1 gather, 2 mma, 3 producer) x (event, clock)...
 __device__ int g_mlp_logn[4];
 #define SAD_LOG(role, ev)                                                                  \
-  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) == (role == 0 ? 0 : role == 1 ? 4 : role == 2 ? 8 : 9)) { \
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) == (role == 0 ? 0 : role == 1 ? 8 : role == 2 ? kWarpMma : kWarpTma)) { \
     if (sad_logn < 1023) {                                                                 \
       g_mlp_log[role][2 * sad_logn] = (ev);                                                \
       g_mlp_log[role][2 * sad_logn + 1] = clock64();                                       \
@@ -108,9 +116,9 @@ __device__ int g_mlp_logn[4];
 #endif
 
 struct Misc {
-  uint64_t afull[kMaxA], afree[kMaxA];
+  uint64_t afull[kFullBars], afree[kMaxA];
   uint64_t wpin[kMaxPin];
-  uint64_t wfull[kMaxRing], wfree[kMaxRing];
+  uint64_t wfull[kFullBars], wfree[kMaxRing];
   uint64_t dfull[2][5], actfull[2];
   uint64_t tfull[16];             // tile ordinal k of this CTA published in tiles[k & 15]
   int tiles[16];
@@ -212,6 +220,25 @@ __device__ __forceinline__ uint32_t swz(int row, int unit) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((unit ^ (row & 7)) << 4));
 }
 
+// max of N accumulator words as a ternary tree (depth 4 for 32 values instead of a 31-long dependent chain;
+// max.f32 takes three operands on sm_100)
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+template <int N>
+__device__ __forceinline__ float vmax(const uint32_t* v) {
+  if constexpr (N == 1) {
+    return __uint_as_float(v[0]);
+  } else if constexpr (N == 2) {
+    return fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+  } else {
+    constexpr int A = N / 3 + (N % 3 > 0), B = N / 3 + (N % 3 > 1);
+    return max3(vmax<A>(v), vmax<B>(v + A), vmax<N - A - B>(v + A + B));
+  }
+}
+
 // ---- pooled outputs of one thread (= output channel `ch`) for the 32 consecutive rows held in v
 template <int S>
 __device__ __forceinline__ void emit_group(const MlpParams& p, const uint32_t (&v)[32], float& run, int g, int ch,
@@ -231,18 +258,14 @@ __device__ __forceinline__ void emit_group(const MlpParams& p, const uint32_t (&
     if (p.out_cl) p.out_cl[(size_t)pt * c_last + ch] = __float2bfloat16_rn(y);
   };
   if constexpr (S >= 32) {
-    float m = __uint_as_float(v[0]);
-#pragma unroll
-    for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+    const float m = vmax<32>(&v[0]);
     constexpr int GP = S / 32;                  // 32-column groups per point
     run = (g % GP == 0) ? m : fmaxf(run, m);
     if (g % GP == GP - 1) store((uint32_t)(g / GP), run);
   } else {
 #pragma unroll
     for (int q = 0; q < 32 / S; ++q) {
-      float m = __uint_as_float(v[q * S]);
-#pragma unroll
-      for (int i = 1; i < S; ++i) m = fmaxf(m, __uint_as_float(v[q * S + i]));
+      const float m = vmax<S>(&v[q * S]);
       store((uint32_t)(g * (32 / S) + q), m);
     }
   }
@@ -275,23 +298,21 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
   };
 
   if (tid == 0) {
-    for (int i = 0; i < kMaxA; ++i) {
+    for (int i = 0; i < kFullBars; ++i) {
       mbar_init(&ms->afull[i], kGather);
-      mbar_init(&ms->afree[i], 1);
-    }
-    for (int i = 0; i < kMaxPin; ++i) mbar_init(&ms->wpin[i], 1);
-    for (int i = 0; i < kMaxRing; ++i) {
       mbar_init(&ms->wfull[i], 1);
-      mbar_init(&ms->wfree[i], 1);
     }
+    for (int i = 0; i < kMaxA; ++i) mbar_init(&ms->afree[i], 1);
+    for (int i = 0; i < kMaxPin; ++i) mbar_init(&ms->wpin[i], 1);
+    for (int i = 0; i < kMaxRing; ++i) mbar_init(&ms->wfree[i], 1);
     for (int i = 0; i < 16; ++i) mbar_init(&ms->tfull[i], 1);
     for (int i = 0; i < 2; ++i) {
       for (int k = 0; k < 5; ++k) mbar_init(&ms->dfull[i][k], 1);   // [0] hidden / plain last, [1+blk] transposed blocks
-      mbar_init(&ms->actfull[i], kEpi);
+      mbar_init(&ms->actfull[i], kEpiWG);
     }
     mbar_fence_init();
   }
-  if (warp == 8) {   // TMEM allocation: one warp, power-of-two columns
+  if (warp == kWarpMma) {   // TMEM allocation: one warp, power-of-two columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ms->tmem_base)),
                  "r"((uint32_t)p.tmem_cols)
                  : "memory");
@@ -304,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&ms->tmem_base);
 
-  if (warp == 9) {
+  if (warp == kWarpTma) {
     // ================================================================== weight TMA producer
     if (lane == 0) {
       for (int li = 0; li < nl; ++li)
@@ -331,9 +352,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 const uint32_t r = cnt % (uint32_t)p.nr, use = cnt / (uint32_t)p.nr;
                 if (use > 0) mbar_wait(&ms->wfree[r], (use - 1) & 1u);
                 const uint32_t bytes = (uint32_t)p.piece_bytes[li];
-                mbar_arrive_expect_tx(&ms->wfull[r], bytes);
-                tma_bulk_g2s(gbase + off_ring + (size_t)r * p.ring_slot_bytes, p.w_img[li] + (size_t)i * bytes, bytes,
-                             &ms->wfull[r]);
+                uint64_t* full = &ms->wfull[cnt & (kFullBars - 1)];
+                mbar_arrive_expect_tx(full, bytes);
+                tma_bulk_g2s(gbase + off_ring + (size_t)r * p.ring_slot_bytes, p.w_img[li] + (size_t)i * bytes, bytes, full);
                 ++cnt;
               }
             }
@@ -341,13 +362,31 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 8) {
-    // ================================================================== MMA issuer
-    {
-      uint32_t a_stage = 0, a_phase = 0, w_slot = 0, w_phase = 0;      // ring positions (wrap counters, no division)
-      uint32_t act_cnt[2] = {0, 0};
+  } else if (warp == kWarpMma || warp == kWarpMma + 1) {
+    // ================================================================== MMA issuers (one warp per tile context)
+    // Each context has its own issuing warp, so the two contexts' wait -> issue -> commit sequences (a few hundred
+    // single-warp instructions per layer) run concurrently.  The A ring and the streamed-weight ring are filled in one
+    // global order (round, layer, context, piece); each warp keeps the global position and skips the other context's
+    // share, so no hand-off between the two warps is needed.
+    const int s = warp - kWarpMma;
+    if (s < p.nslot) {
+      uint32_t a_pos = 0, a_stage = 0, w_pos = 0, w_slot = 0;      // global ring positions + stage wrap counters
+      auto skip_a = [&](int n) {
+        a_pos += (uint32_t)n;
+        for (int i = 0; i < n; ++i)
+          if (++a_stage == (uint32_t)p.na) a_stage = 0;
+      };
+      auto skip_w = [&](int n) {
+        w_pos += (uint32_t)n;
+        for (int i = 0; i < n; ++i)
+          if (++w_slot == (uint32_t)p.nr) w_slot = 0;
+      };
+      uint32_t act_cnt = 0;
       bool pinned_ready = false;                                        // pinned pieces are waited for once
       const bool leader = elect_one();
+      const uint32_t region = tmem_base + (uint32_t)(s * p.region_cols);
+      const uint32_t act_s = base + off_act + (uint32_t)(s * p.act_chunks) * kChunkBytes;
+      const int chunks0 = p.kpad[0] / 64;
       // weights of piece (li, i): pinned address or the next ring slot; returns the smem address
       auto weights = [&](int li, int i, bool& streamed, uint32_t& slot) -> uint32_t {
         const int pc = p.first_piece[li] + i;
@@ -357,136 +396,161 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
           return base + off_pin + (uint32_t)p.pin_off[li] + (uint32_t)i * (uint32_t)p.piece_bytes[li];
         }
         slot = w_slot;
-        mbar_wait(&ms->wfull[slot], w_phase);
-        if (++w_slot == (uint32_t)p.nr) {
-          w_slot = 0;
-          w_phase ^= 1u;
-        }
+        mbar_wait(&ms->wfull[w_pos & (kFullBars - 1)], (w_pos / kFullBars) & 1u);
+        skip_w(1);
         streamed = true;
         return base + off_ring + slot * (uint32_t)p.ring_slot_bytes;
       };
       for (int t0 = 0;; t0 += p.nslot) {
-        int ns = p.nslot;
-        for (int li = 0; li < nl; ++li) {
+        // contexts active in this round (the last round of a CTA may have only context 0).  Context 0 must not ask
+        // for ordinal t0 + 1 before its own layer-0 chunks are consumed: with more K chunks than A-ring stages the
+        // gather warps publish that ordinal only after this warp has freed stages (ns < 0: not known yet).
+        if (get_tile(t0) < 0) break;
+        int ns = -1;
+        if (s == 1) {
+          if (get_tile(t0 + 1) < 0) break;
+          ns = 2;
+        }
+#pragma unroll
+        for (int li = 0; li < kMaxLayers; ++li) {
+          if (li >= nl) break;
           const bool last = (li == nl - 1);
           const int chunks = p.kpad[li] / 64;
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            if (s >= ns) break;
-            if (li == 0 && get_tile(t0 + s) < 0) {
-              ns = s;
-              break;
-            }
-            // the context's TMEM region / activation buffer must have been drained by the epilogue of
-            // the previous layer (li > 0) or of the previous tile in this context (li == 0)
-            SAD_LOG(2, 100 + li * 10 + s)
-            if (li > 0 || t0 > 0) {
-              mbar_wait(&ms->actfull[s], act_cnt[s] & 1u);
-              ++act_cnt[s];
-            }
-            tc_fence_after();
-            SAD_LOG(2, 200 + li * 10 + s)
-            const uint32_t region = tmem_base + (uint32_t)(s * p.region_cols);
-            const uint32_t act_s = base + off_act + (uint32_t)(s * p.act_chunks) * kChunkBytes;
-            if (!(last && p.transposed)) {
-              // D (128 rows x N) = A (rows x K) . W^T ; N = layer width (plain last layer: cpad, split at 256)
-              const int ncols = last ? p.cpad_last : p.c[li];
-              for (int kc = 0; kc < chunks; ++kc) {
-                uint32_t a_addr;
-                int ksteps = 4;
-                uint32_t stage = 0;
-                if (li == 0) {
-                  stage = a_stage;
-                  mbar_wait(&ms->afull[stage], a_phase);
-                  if (++a_stage == (uint32_t)p.na) {
-                    a_stage = 0;
-                    a_phase ^= 1u;
-                  }
-                  a_addr = base + off_a + stage * kChunkBytes;
-                  if (p.has_special && kc == chunks - 1) ksteps = 1;
-                } else {
-                  a_addr = act_s + (uint32_t)kc * kChunkBytes;
+          // streamed pieces of this layer per context (the other context's share is skipped, before or after mine)
+          const int lo = p.first_piece[li] > p.n_pinned ? p.first_piece[li] : p.n_pinned;
+          const int nstream = p.first_piece[li] + p.pieces[li] > lo ? p.first_piece[li] + p.pieces[li] - lo : 0;
+          if (s == 1) {
+            skip_w(nstream);
+            if (li == 0) skip_a(chunks0);
+          }
+          // the context's TMEM region / activation buffer must have been drained by the epilogue of
+          // the previous layer (li > 0) or of the previous tile in this context (li == 0)
+          SAD_LOG(2, 100 + li * 10 + s)
+          if (li > 0 || t0 > 0) {
+            mbar_wait(&ms->actfull[s], act_cnt & 1u);
+            ++act_cnt;
+          }
+          tc_fence_after();
+          SAD_LOG(2, 200 + li * 10 + s)
+          if (!(last && p.transposed)) {
+            // D (128 rows x N) = A (rows x K) . W^T ; N = layer width (plain last layer: cpad, split at 256)
+            const int ncols = last ? p.cpad_last : p.c[li];
+            for (int kc = 0; kc < chunks; ++kc) {
+              uint32_t a_addr;
+              int ksteps = 4;
+              uint32_t stage = 0;
+              if (li == 0) {
+                stage = a_stage;
+                mbar_wait(&ms->afull[a_pos & (kFullBars - 1)], (a_pos / kFullBars) & 1u);
+                skip_a(1);
+                a_addr = base + off_a + stage * kChunkBytes;
+                if (p.has_special && kc == chunks - 1) ksteps = 1;
+              } else {
+                a_addr = act_s + (uint32_t)kc * kChunkBytes;
+              }
+              bool streamed;
+              uint32_t slot = 0;
+              const uint32_t b_addr = weights(li, kc, streamed, slot);
+              tc_fence_after();
+              SAD_LOG(2, 400 + li * 10 + s)
+              if (leader) {
+                for (int n0 = 0; n0 < ncols; n0 += 256) {
+                  const int nn = min(256, ncols - n0);
+                  const uint32_t idesc = umma_idesc(128, nn);
+                  const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr + (uint32_t)n0 * 128u);
+                  for (int k = 0; k < ksteps; ++k)     // +2 per 32-byte K step in the (addr >> 4) field
+                    umma_bf16(region + (uint32_t)n0, ad + 2u * k, bd + 2u * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
                 }
+                if (li == 0) umma_commit(&ms->afree[stage]);
+                if (streamed) umma_commit(&ms->wfree[slot]);
+                if (kc == chunks - 1) umma_commit(&ms->dfull[s][0]);
+              }
+            }
+            __syncwarp();
+            SAD_LOG(2, 300 + li * 10 + s)
+          } else {
+            // transposed last layer: D^T (128 channels x 128 rows) = W_blk . H^T, one commit per block
+            const uint32_t idesc = umma_idesc(128, 128);
+            for (int blk = 0; blk < p.nblk; ++blk) {
+              for (int kc = 0; kc < chunks; ++kc) {
                 bool streamed;
                 uint32_t slot = 0;
-                const uint32_t b_addr = weights(li, kc, streamed, slot);
+                const uint32_t a_addr = weights(li, blk * chunks + kc, streamed, slot);   // W block rows = M
+                const uint32_t b_addr = act_s + (uint32_t)kc * kChunkBytes;               // activations rows = N
                 tc_fence_after();
+                SAD_LOG(2, 400 + li * 10 + s)
                 if (leader) {
-                  for (int n0 = 0; n0 < ncols; n0 += 256) {
-                    const int nn = min(256, ncols - n0);
-                    const uint32_t idesc = umma_idesc(128, nn);
-                    const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr + (uint32_t)n0 * 128u);
-                    for (int k = 0; k < ksteps; ++k)     // +2 per 32-byte K step in the (addr >> 4) field
-                      umma_bf16(region + (uint32_t)n0, ad + 2u * k, bd + 2u * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
-                  }
-                  if (li == 0) umma_commit(&ms->afree[stage]);
+                  const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(region + (uint32_t)(blk * 128), ad + 2u * k, bd + 2u * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
                   if (streamed) umma_commit(&ms->wfree[slot]);
-                  if (kc == chunks - 1) umma_commit(&ms->dfull[s][0]);
+                  // one barrier per block: never two phases outstanding
+                  if (kc == chunks - 1) umma_commit(&ms->dfull[s][1 + blk]);
                 }
               }
               __syncwarp();
               SAD_LOG(2, 300 + li * 10 + s)
-            } else {
-              // transposed last layer: D^T (128 channels x 128 rows) = W_blk . H^T, one commit per block
-              const uint32_t idesc = umma_idesc(128, 128);
-              for (int blk = 0; blk < p.nblk; ++blk) {
-                for (int kc = 0; kc < chunks; ++kc) {
-                  bool streamed;
-                  uint32_t slot = 0;
-                  const uint32_t a_addr = weights(li, blk * chunks + kc, streamed, slot);   // W block rows = M
-                  const uint32_t b_addr = act_s + (uint32_t)kc * kChunkBytes;               // activations rows = N
-                  tc_fence_after();
-                  if (leader) {
-                    const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                      umma_bf16(region + (uint32_t)(blk * 128), ad + 2u * k, bd + 2u * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
-                    if (streamed) umma_commit(&ms->wfree[slot]);
-                    // one barrier per block: never two phases outstanding
-                    if (kc == chunks - 1) umma_commit(&ms->dfull[s][1 + blk]);
-                  }
-                }
-                __syncwarp();
-                SAD_LOG(2, 300 + li * 10 + s)
-              }
+            }
+          }
+          if (s == 0) {
+            if (ns < 0) ns = (p.nslot > 1 && get_tile(t0 + 1) >= 0) ? 2 : 1;
+            if (ns == 2) {
+              skip_w(nstream);
+              if (li == 0) skip_a(chunks0);
             }
           }
         }
         pinned_ready = true;
-        if (ns < p.nslot) break;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= kEpi / 32) {
     // ================================================================== gather producers
     const int gt = tid - kEpi;                 // row of the tile this thread owns for bookkeeping / special chunk
     const int unit = gt & 7, rbase = gt >> 3;
     const int nf0 = p.C0 / 64, nf1 = p.C1in / 64;
+    uint32_t g_pos = 0;                                // ring position of the next chunk (its full barrier: g_pos % kFullBars)
     uint32_t g_stage = 0, g_phase = 0;                 // afree parity of the NEXT wait (the first pass over the ring never waits)
     bool g_first = true;
     int pend = 0;
-    uint32_t ps0 = 0, ps1 = 0, ps2 = 0;        // stages of the cp.async groups still in flight (oldest first)
+    uint32_t ps0 = 0, ps1 = 0, ps2 = 0;        // full barriers of the cp.async groups still in flight (oldest first)
 
     struct Special {
       float x, y, z, qx, qy, qz, r, e[4];
     };
-    auto load_src = [&](int tile) -> uint32_t {
+    // Source row of this thread in `tile`, in two steps so that no instruction ever waits for a load inside the
+    // iteration that issued it: issue_idx() starts the index load, resolve_src() (one iteration later) turns the
+    // landed value into the global row b * N + idx.
+    auto issue_idx = [&](int tile) -> int {
+      if (tile < 0 || !p.idx) return 0;
+      const long long R = (long long)tile * 128 + gt;
+      return R < p.total_rows ? ldg_s32_pinned(p.idx + R) : 0;
+    };
+    // point -> (batch, point in batch): a shift when P is a power of two (every stage of the detector), else a division
+    auto batch_of = [&](uint32_t pt) -> uint32_t {
+      return p.log2P >= 0 ? (pt >> p.log2P) : pt / (uint32_t)p.P;
+    };
+    auto resolve_src = [&](int tile, int raw) -> uint32_t {
       if (tile < 0) return kNoRow;
       const long long R = (long long)tile * 128 + gt;
       if (R >= p.total_rows) return kNoRow;
       const uint32_t pt = (uint32_t)(R >> p.log2S);
-      const uint32_t b = pt / (uint32_t)p.P;
-      const uint32_t id = p.idx ? (uint32_t)ldg_s32_pinned(p.idx + R) : (pt - b * (uint32_t)p.P);
+      const uint32_t b = batch_of(pt);
+      const uint32_t id = p.idx ? (uint32_t)raw : (pt - b * (uint32_t)p.P);
       return b * (uint32_t)p.N + id;
     };
+    // 1 / radius of a scalar-radius stage, once per kernel (the per-cluster radius is inverted per row); the
+    // normalised offsets feed a bf16 operand, so multiplying by the reciprocal instead of dividing is far inside
+    // the rounding of the storage format
+    const float inv_radius = (p.normalize && !p.radius_t) ? __frcp_rn(p.radius) : 1.f;
     auto load_special = [&](uint32_t src, int tile, Special& s) {
       s.x = s.y = s.z = s.qx = s.qy = s.qz = 0.f;
       s.r = 1.f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) s.e[e] = 0.f;
       if (src == kNoRow || !p.has_special) return;
-      const long long R = (long long)tile * 128 + gt;
-      const uint32_t pt = (uint32_t)(R >> p.log2S);
       if (p.xyz) {
+        const uint32_t pt = (uint32_t)(((long long)tile * 128 + gt) >> p.log2S);
         const float* a = p.xyz + (size_t)src * 3;
         const float* q = p.new_xyz + (size_t)pt * 3;
         s.x = ldg_f32_pinned(a);
@@ -495,7 +559,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         s.qx = ldg_f32_pinned(q);
         s.qy = ldg_f32_pinned(q + 1);
         s.qz = ldg_f32_pinned(q + 2);
-        if (p.normalize) s.r = p.radius_t ? ldg_f32_pinned(p.radius_t + pt) : p.radius;
+        if (p.normalize && p.radius_t) s.r = ldg_f32_pinned(p.radius_t + pt);
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e)
@@ -511,23 +575,30 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
 
     // next tile of this CTA: static round-robin, or one atomic on the caller-zeroed counter (dynamic: CTAs
     // that start late -- SMs held by another stream's kernel -- simply find less work left)
-    auto fetch_tile = [&](int ord) -> int {
-      long long t;
-      if (p.tile_counter) t = (long long)gridDim.x + atomicAdd(p.tile_counter, 1);
-      else t = (long long)blockIdx.x + (long long)ord * gridDim.x;
-      return t < p.num_tiles ? (int)t : -1;
+    // (raw value now, bounds check when it is consumed: the atomic's round trip stays off this iteration's path)
+    // (fetch_raw returns the atomic's result untouched -- even adding gridDim.x here would make this iteration wait
+    // for the round trip; tile_of_raw finishes the job where the value is consumed)
+    auto fetch_raw = [&](int ord) -> int {
+      if (p.tile_counter) return atomicAdd(p.tile_counter, 1);
+      return ord;
     };
-    int tq0 = (int)blockIdx.x, tq1, tq2, fetched = -1;
+    auto tile_of_raw = [&](int raw) -> int {
+      const long long t = p.tile_counter ? (long long)gridDim.x + raw : (long long)blockIdx.x + (long long)raw * gridDim.x;
+      return (raw >= 0 && t < p.num_tiles) ? (int)t : -1;
+    };
+    int tq0 = (int)blockIdx.x, tq1, tq2;
+    int raw_f = -1;                            // gt == 0: raw tile fetch of ordinal it + 2
     if (gt == 0) {
-      ms->boot[0] = fetch_tile(1);
-      ms->boot[1] = fetch_tile(2);
+      ms->boot[0] = tile_of_raw(fetch_raw(1));
+      raw_f = fetch_raw(2);
+      ms->boot[1] = tile_of_raw(raw_f);
     }
     named_bar_sync(1, kGather);
     tq1 = ms->boot[0];
     tq2 = ms->boot[1];
-    if (gt == 0) fetched = tq2;
-    uint32_t src_cur = load_src(tq0), src_nxt = load_src(tq1);
-    Special sp_cur;
+    uint32_t src_cur = resolve_src(tq0, issue_idx(tq0));
+    int idraw = issue_idx(tq1);                // index of this thread's row in tile tq1 (in flight)
+    Special sp_cur;                            // special-chunk inputs of the tile about to be gathered
     load_special(src_cur, tq0, sp_cur);
     int it = 0;
     for (; tq0 >= 0; ++it) {
@@ -537,16 +608,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
       if (gt == 0) {
         ms->tiles[it & 15] = tq0;
         mbar_arrive(&ms->tfull[it & 15]);
-        ms->fetch[it & 1] = fetched;                      // tile id of ordinal it + 2 (fetched one iteration ago)
+        ms->fetch[it & 1] = tile_of_raw(raw_f);           // tile id of ordinal it + 2 (fetched one iteration ago)
       }
       SAD_LOG(1, 100)
       named_bar_sync(1, kGather);
       SAD_LOG(1, 200)
       tq2 = ms->fetch[it & 1];
-      if (gt == 0) fetched = fetch_tile(it + 3);          // latency hidden behind this tile's gather
-      const uint32_t src_nn = load_src(tq2);              // issued two tiles ahead
-      Special sp_nxt;
-      load_special(src_nxt, tq1, sp_nxt);                 // issued one tile ahead
       for (int kc = 0; kc < chunks0; ++kc) {
         const uint32_t stage = g_stage;
         if (!g_first && !mbar_try_wait(&ms->afree[stage], g_phase)) {
@@ -564,6 +631,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
           else g_phase ^= 1u;
         }
         const uint32_t dst = base + off_a + stage * kChunkBytes;
+        const uint32_t fbar = g_pos++ & (kFullBars - 1);
+        SAD_LOG(1, 400)
         if (kc < nf0 + nf1) {
           if (kc < nf0) {
 #pragma unroll
@@ -584,9 +653,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             }
           }
           cp_async_commit();
-          if (pend == 0) ps0 = stage;
-          else if (pend == 1) ps1 = stage;
-          else ps2 = stage;
+          if (pend == 0) ps0 = fbar;
+          else if (pend == 1) ps1 = fbar;
+          else ps2 = fbar;
           ++pend;
           if (pend == p.depth) {
             if (p.depth == 3) cp_async_wait<2>();
@@ -604,9 +673,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
               float dx = __fsub_rn(sp_cur.x, sp_cur.qx), dy = __fsub_rn(sp_cur.y, sp_cur.qy),
                     dz = __fsub_rn(sp_cur.z, sp_cur.qz);
               if (p.normalize) {
-                dx = __fdiv_rn(dx, sp_cur.r);
-                dy = __fdiv_rn(dy, sp_cur.r);
-                dz = __fdiv_rn(dz, sp_cur.r);
+                const float inv = p.radius_t ? __frcp_rn(sp_cur.r) : inv_radius;
+                dx *= inv;
+                dy *= inv;
+                dz *= inv;
               }
               vals[0] = dx;
               vals[1] = dy;
@@ -620,53 +690,57 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
           }
           st_shared_v4(dst + swz(gt, 0), pack_bf16(vals[0], vals[1]), pack_bf16(vals[2], vals[3]),
                        pack_bf16(vals[4], vals[5]), pack_bf16(vals[6], vals[7]));
+          SAD_LOG(1, 500)
           st_shared_v4(dst + swz(gt, 1), pack_bf16(vals[8], vals[9]), pack_bf16(vals[10], vals[11]),
                        pack_bf16(vals[12], vals[13]), pack_bf16(vals[14], vals[15]));
           fence_proxy_async();
-          mbar_arrive(&ms->afull[stage]);
+          mbar_arrive(&ms->afull[fbar]);
+          SAD_LOG(1, 600)
         }
       }
+      // Prefetches for the next tiles are issued AFTER this tile's chunks are published: the publication fence
+      // (fence.proxy.async = MEMBAR + proxy fence) waits for every load the thread has in flight, so loads issued
+      // before it would put a full L2 / atomic round trip on the path of every chunk.  Issued here they have a whole
+      // iteration to land before the next fence.
+      // Every value consumed here was requested one iteration ago; every request made here is consumed one
+      // iteration later (raw_f at the top, idraw here, sp_cur in the special chunk).
+      if (gt == 0) raw_f = fetch_raw(it + 3);
+      src_cur = resolve_src(tq1, idraw);                  // next tile's source row (its index has landed)
+      idraw = issue_idx(tq2);                             // index two tiles ahead
+      load_special(src_cur, tq1, sp_cur);                 // special-chunk inputs one tile ahead
       SAD_LOG(1, 300)
-      src_cur = src_nxt;
-      src_nxt = src_nn;
-      sp_cur = sp_nxt;
       tq0 = tq1;
       tq1 = tq2;
     }
-    if (gt == 0) {                                        // end marker for the other roles
-      ms->tiles[it & 15] = -1;
+    if (gt == 0) {                                        // end marker for the other roles (two ordinals: each epilogue
+      ms->tiles[it & 15] = -1;                            // warpgroup walks every other ordinal)
       mbar_arrive(&ms->tfull[it & 15]);
+      ms->tiles[(it + 1) & 15] = -1;
+      mbar_arrive(&ms->tfull[(it + 1) & 15]);
     }
     cp_async_wait<0>();
     while (pend > 0) retire_oldest();
   } else {
-    // ================================================================== epilogue warps (thread == TMEM lane)
-    uint32_t d_cnt[2] = {0, 0};      // uses of dfull[s][0]
-    uint32_t t_cnt[2] = {0, 0};      // tiles finished in context s (= uses of each dfull[s][1+blk])
-    const uint32_t lane_t = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int t0 = 0;; t0 += p.nslot) {
-      int ns = p.nslot;
-      int tile_of[2] = {-1, -1};
-      for (int li = 0; li < nl; ++li) {
-        const bool last = (li == nl - 1);
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (s >= ns) break;
-          if (li == 0) {
-            tile_of[s] = get_tile(t0 + s);
-            if (tile_of[s] < 0) {
-              ns = s;
-              break;
-            }
-          }
-          const uint32_t region = lane_t + (uint32_t)(s * p.region_cols);
-          const uint32_t act_s = base + off_act + (uint32_t)(s * p.act_chunks) * kChunkBytes;
-          const long long tile = tile_of[s];
+    // ================================================================== epilogue warpgroups (thread == TMEM lane)
+    // warpgroup s drains tile context s only: the two contexts' epilogues run concurrently, and the MMA warp
+    // (which alternates between the contexts) never finds both of them queued behind one set of warps
+    const int s = warp >> 2;                    // tile context of this warpgroup
+    const int et = tid & (kEpiWG - 1);          // TMEM lane == row of the tile (plain) / output channel (transposed)
+    if (s < p.nslot) {
+      uint32_t d_cnt = 0;            // uses of dfull[s][0]
+      uint32_t t_cnt = 0;            // tiles finished in this context (= uses of each dfull[s][1+blk])
+      const uint32_t region = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * p.region_cols);
+      const uint32_t act_s = base + off_act + (uint32_t)(s * p.act_chunks) * kChunkBytes;
+      for (int t0 = s;; t0 += p.nslot) {
+        const long long tile = get_tile(t0);
+        if (tile < 0) break;
+        for (int li = 0; li < nl; ++li) {
+          const bool last = (li == nl - 1);
           SAD_LOG(0, 100 + li * 10 + s)
           if (!last) {
             // ---- hidden layer: TMEM -> +bias -> ReLU -> bf16 -> swizzled ACT (next layer's operand)
-            mbar_wait(&ms->dfull[s][0], d_cnt[s] & 1u);
-            ++d_cnt[s];
+            mbar_wait(&ms->dfull[s][0], d_cnt & 1u);
+            ++d_cnt;
             tc_fence_after();
             SAD_LOG(0, 200 + li * 10 + s)
             const float* sb = ms->bias[li];
@@ -675,6 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
               tmem_ld32_issue(region + (uint32_t)c0, v0);
               tmem_ld32_issue(region + (uint32_t)c0 + 32u, v1);
               tmem_ld_wait();
+              SAD_LOG(0, 400 + li * 10 + s)
               const uint32_t chunk = act_s + (uint32_t)(c0 >> 6) * kChunkBytes;
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
@@ -682,24 +757,25 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 const int o = (u & 3) * 8;
                 const float4 ba = *reinterpret_cast<const float4*>(sb + c0 + u * 8);
                 const float4 bb = *reinterpret_cast<const float4*>(sb + c0 + u * 8 + 4);
-                st_shared_v4(chunk + swz(tid, u),
+                st_shared_v4(chunk + swz(et, u),
                              pack_bf16_relu(__uint_as_float(v[o + 0]) + ba.x, __uint_as_float(v[o + 1]) + ba.y),
                              pack_bf16_relu(__uint_as_float(v[o + 2]) + ba.z, __uint_as_float(v[o + 3]) + ba.w),
                              pack_bf16_relu(__uint_as_float(v[o + 4]) + bb.x, __uint_as_float(v[o + 5]) + bb.y),
                              pack_bf16_relu(__uint_as_float(v[o + 6]) + bb.z, __uint_as_float(v[o + 7]) + bb.w));
               }
             }
+            SAD_LOG(0, 500 + li * 10 + s)
             fence_proxy_async();
           } else if (p.transposed) {
             // ---- last layer, transposed: thread == output channel, columns == rows; pool over S
             const uint32_t npt = 128u >> p.log2S;
             const uint32_t pt0 = (uint32_t)tile * npt;
-            const uint32_t b0 = pt0 / (uint32_t)p.P, j0 = pt0 - b0 * (uint32_t)p.P;
+            const uint32_t b0 = p.log2P >= 0 ? (pt0 >> p.log2P) : pt0 / (uint32_t)p.P, j0 = pt0 - b0 * (uint32_t)p.P;
             for (int blk = 0; blk < p.nblk; ++blk) {
-              mbar_wait(&ms->dfull[s][1 + blk], t_cnt[s] & 1u);
+              mbar_wait(&ms->dfull[s][1 + blk], t_cnt & 1u);
               tc_fence_after();
               SAD_LOG(0, 200 + li * 10 + s)
-              const int ch = blk * 128 + tid;
+              const int ch = blk * 128 + et;
               const bool ch_ok = ch < c_last;
               const float bias = ms->bias[li][ch_ok ? ch : 0];
               float run = 0.f;
@@ -709,6 +785,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 tmem_ld32_issue(region + (uint32_t)(blk * 128 + g * 32), v0);
                 tmem_ld32_issue(region + (uint32_t)(blk * 128 + g * 32 + 32), v1);
                 tmem_ld_wait();
+                SAD_LOG(0, 400 + li * 10 + s)
                 switch (p.S) {
 #define SAD_EMIT(SS)                                                           \
   case SS:                                                                     \
@@ -729,16 +806,16 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 }
               }
             }
-            ++t_cnt[s];
+            ++t_cnt;
           } else {
             // ---- last layer, plain orientation (S == 1): thread == row; both outputs store coalesced
-            mbar_wait(&ms->dfull[s][0], d_cnt[s] & 1u);
-            ++d_cnt[s];
+            mbar_wait(&ms->dfull[s][0], d_cnt & 1u);
+            ++d_cnt;
             tc_fence_after();
-            const long long R = tile * 128 + tid;
+            const long long R = tile * 128 + et;
             const bool ok = R < p.total_rows;
             const uint32_t pt = ok ? (uint32_t)R : 0u;
-            const uint32_t b = pt / (uint32_t)p.P, j = pt - b * (uint32_t)p.P;
+            const uint32_t b = p.log2P >= 0 ? (pt >> p.log2P) : pt / (uint32_t)p.P, j = pt - b * (uint32_t)p.P;
             const float* sb = ms->bias[li];
             float* ocf = p.out_cf ? p.out_cf + (size_t)b * c_last * p.P + j : nullptr;
             __nv_bfloat16* ocl = p.out_cl ? p.out_cl + (size_t)pt * c_last : nullptr;
@@ -781,13 +858,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
           SAD_LOG(0, 300 + li * 10 + s)
         }
       }
-      if (ns < p.nslot) break;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kWarpMma) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
                  : "memory");
   }
@@ -854,7 +930,7 @@ static int image_rows(int cout, int mode) { return mode == 1 ? 128 : (mode == 2 
 
 #ifdef SAD_MLP_PROFILE
 // tools only: copy the CTA-0 timeline of the last launch to the host and reset it
-extern "C" int sad_mlp_profile_dump(long long* host_log /*4*2048*/, int* host_n /*4*/) {
+extern "C" SAD_API int sad_mlp_profile_dump(long long* host_log /*4*2048*/, int* host_n /*4*/) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(host_log, g_mlp_log, sizeof(long long) * 4 * 2048);
   cudaMemcpyFromSymbol(host_n, g_mlp_logn, sizeof(int) * 4);
@@ -945,7 +1021,12 @@ static bool plan_launch(MlpParams& p, int hidden_max, size_t& smem_out) {
   const char* e_na = getenv("SAD_MLP_NA");
   const char* e_nr = getenv("SAD_MLP_NR");
   const int max_slot = e_slot ? atoi(e_slot) : 2, max_na = e_na ? atoi(e_na) : 4, want_nr = e_nr ? atoi(e_nr) : 2;
-  for (int nslot = (2 * p.region_cols <= 512 && p.num_tiles > 1 && max_slot >= 2) ? 2 : 1; nslot >= 1; --nslot) {
+  int max_pieces = 0;
+  for (int li = 0; li < nl; ++li) max_pieces = p.pieces[li] > max_pieces ? p.pieces[li] : max_pieces;
+  // two contexts = two consumers per ring: the skipped share + 1 + the ring depth must stay inside one period of
+  // the position-indexed full barriers (see kFullBars)
+  const bool two_ok = p.kpad[0] / 64 + 1 + kMaxA <= kFullBars && max_pieces + 1 + kMaxRing <= kFullBars;
+  for (int nslot = (2 * p.region_cols <= 512 && p.num_tiles > 1 && max_slot >= 2 && two_ok) ? 2 : 1; nslot >= 1; --nslot) {
     const long long act = (long long)nslot * p.act_chunks * kChunkBytes;
     for (int na = (max_na < 2 ? 2 : (max_na > 4 ? 4 : max_na)); na >= 2; --na) {
       const long long rest = avail - act - (long long)na * kChunkBytes;
@@ -998,6 +1079,9 @@ extern "C" int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_c
                                   const void* const* w_img, const float* const* bias, const int* c_out, int last_relu,
                                   void* out_cl_bf16, float* out_cf_f32, int* tile_counter, sad_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+#ifdef SAD_TOOLS_ABLATE
+  if (sad_ablate_mask() & 2) return SAD_OK;
+#endif
   SAD_REQUIRE(B >= 0 && N >= 1 && P >= 0 && S >= 1, "shared_mlp: bad sizes B=%d N=%d P=%d S=%d", B, N, P, S);
   SAD_REQUIRE(S == 1 || S == 2 || S == 4 || S == 8 || S == 16 || S == 32 || S == 64 || S == 128,
               "shared_mlp: nsample must be a power of two <= 128 (got %d)", S);
@@ -1018,6 +1102,9 @@ extern "C" int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_c
   MlpParams p = {};
   p.B = B; p.N = N; p.P = P; p.S = S;
   for (p.log2S = 0; (1 << p.log2S) < S; ++p.log2S) {}
+  p.log2P = -1;
+  for (int k = 0; k < 31; ++k)
+    if ((1 << k) == P) p.log2P = k;
   p.total_rows = (long long)B * P * S;
   p.total_points = (uint32_t)((long long)B * P);
   const long long tiles = (p.total_rows + 127) / 128;

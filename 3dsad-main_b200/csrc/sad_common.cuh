@@ -44,6 +44,20 @@ void sad_count_launch(int n);
 
 static inline int sad_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+#ifdef SAD_TOOLS_ABLATE
+// tools/build_variant.py builds only: SAD_ABLATE bit 0 = skip the scene-grid FPS, bit 1 = skip the fused MLP launches,
+// bit 2 = skip the register-resident FPS (pipeline cost attribution; results are garbage by design).
+#include <stdlib.h>
+static inline int sad_ablate_mask() {
+  static int m = -1;
+  if (m < 0) {
+    const char* e = getenv("SAD_ABLATE");
+    m = e ? atoi(e) : 0;
+  }
+  return m;
+}
+#endif
+
 // -------------------------------------------------------------- device side
 #ifdef __CUDACC__
 namespace sad {

@@ -41,6 +41,9 @@ def tlayers(layers):
     (2, 1024, 96, 16, 256, [128, 128, 128], 0.3, True),     # vote aggregation, per-cluster radius
     (1, 500, 37, 8, 64, [64, 192], 0.8, False),             # 2 layers, partial last tile, odd P
     (1, 300, 5, 2, 5, [64, 64, 70], 1.0, False),            # tiny: c_last not a multiple of anything
+    (4, 2048, 1024, 32, 128, [128, 128, 256], 0.6, False),  # SA2 at depth: 7 tiles per CTA, streamed weights, both contexts
+    (8, 1024, 512, 16, 256, [128, 128, 256], 0.9, False),   # SA3 at depth: more K chunks than A-ring stages, 3-4 tiles per CTA
+    (2, 20000, 2048, 64, 1, [64, 64, 128], 0.3, False),     # SA1 at depth: 28 tiles per CTA, everything pinned
 ])
 def test_fused_sa_stage(B, N, P, S, Cf, hidden, radius, adaptive):
     from sad_b200 import mlp as M

@@ -31,11 +31,24 @@ def timeline(tag, fn, first=0, count=60):
     t0 = ev[0][0]
     print(f"== {tag}: {len(ev)} events, CTA-0 span {(ev[-1][0] - t0) / 1.9e3:.1f} us (at 1.9 GHz)")
     for (t, name, e) in ev[first:first + count]:
-        kind = {1: "wait ", 2: "go   ", 3: "done "}[e // 100]
+        kind = {1: "wait ", 2: "go   ", 3: "done ", 4: "ready", 5: "stord", 6: "publ "}[e // 100]
         print(f"  {(t - t0):9d} cyc  {name} {kind} layer {e % 100 // 10} ctx {e % 10}")
 
 
 dev = "cuda"
+if len(sys.argv) > 2 and sys.argv[2] == "real":
+    # SA1 of the benchmarked step on real (synthetic-scene) data: 8 x 40k surface scenes, FPS + ball query indices
+    from sad_b200 import ops
+    from sad_b200.scenes import make_scenes
+    xyz_np, feat_np = make_scenes(8, 40000, "surface")
+    xyz, feat = torch.from_numpy(xyz_np).to(dev), torch.from_numpy(feat_np).to(dev)
+    grid = ops.build_scene_grid(xyz)
+    inds = ops.furthest_point_sample(xyz, 2048, grid)
+    new_xyz = ops.gather_operation(xyz.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
+    idx = ops.ball_query(0.2, 64, xyz, new_xyz, grid)
+    m = layers([4, 64, 64, 128])
+    timeline("SA1 real data", lambda: M.sa_group_mlp(xyz, new_xyz, feat, idx, 0.2, m), first=int(sys.argv[1]), count=70)
+    sys.exit(0)
 shapes = [(40000, 2048 * 8, 64, 0, [64, 64, 128]), (2048, 1024 * 8, 32, 128, [128, 128, 256]),
           (512, 256 * 8, 16, 256, [128, 128, 256])]
 if len(sys.argv) > 2:
