@@ -7,6 +7,8 @@
 // loaded once with 128-bit loads and reused over a chunk of channels; per channel the
 // thread issues 12 independent 4-byte gathers (source rows are L1/L2 resident) and one
 // 128-bit streaming store (a warp writes 512 contiguous bytes).
+#include <stdlib.h>
+
 #include "sad_common.cuh"
 
 namespace {
@@ -126,6 +128,105 @@ interp_fwd_staged_kernel(int C, int m, int quads, int cch, const float* __restri
   if (!waited) mbar_wait(&s_bar, 0);      // never leave with the bulk copy still in flight
 }
 
+// Point-major variant (the fast path).  What bounds the row-staged kernel above is the LSU wavefront rate (~45 per
+// 128 outputs: every 4-byte gather of a warp scatters over a channel row), so this one is built to need ~27:
+//   * the CTA's channel chunk is staged TRANSPOSED, s_f[k][CN] (one known point = one row), the 16-byte units of
+//     every 32-channel segment XOR-swizzled by (k & 7).  Lane = (quarter Q, unit q): a quarter-warp reads one whole
+//     128-byte row segment per gather -- one wavefront per quarter, conflict-free for ANY index pattern;
+//   * Q owns 4 consecutive unknown points (their 12 indices / 12 weights are three 16-byte loads each, shared by the
+//     quarter's lanes through L1), q owns 4 consecutive channels: a lane finishes a 4 x 4 block per half-step;
+//   * the warp's 32-channel x 32-point result is transposed through a swizzled 4 KB shared-memory tile so that the
+//     global stores are whole 128-byte row pieces (a quarter-warp = one row), not 16-byte slivers of 8 rows.
+// Bit-exact like the other variants (same ((w0*f0)+(w1*f1))+(w2*f2), no contraction).
+constexpr int TIP_T = 256;
+constexpr int TIP_TILE = 32 * 32;                            // floats of one warp's transposition tile
+template <int CN>
+__global__ void __launch_bounds__(TIP_T, 2)
+interp_fwd_pm_kernel(int C, int m, int n, int groups_per_cta, const float* __restrict__ features,
+                     const int32_t* __restrict__ idx, const float* __restrict__ weight, float* __restrict__ out) {
+  extern __shared__ __align__(128) float s_dyn[];
+  float* s_t = s_dyn;                                       // [warps][32 channels][32 points], quads swizzled by unit
+  float* s_f = s_dyn + (TIP_T / 32) * TIP_TILE;             // [m][CN], units swizzled inside 32-channel segments
+  constexpr int UNITS = CN / 4;
+  const int b = blockIdx.z, c0 = blockIdx.y * CN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- stage: thread = point k, 8 units (32 channels) per pass: 32 independent coalesced 4-byte loads in flight
+  // (lanes = consecutive k), then eight conflict-free 16-byte stores
+  const float* fb = features + ((size_t)b * C + c0) * m;
+  for (int k = tid; k < m; k += TIP_T) {
+#pragma unroll
+    for (int u0 = 0; u0 < UNITS; u0 += 8) {
+      float v[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = (c0 + 4 * u0 + e < C) ? __ldg(fb + (size_t)(4 * u0 + e) * m + k) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<float4*>(s_f + (size_t)k * CN + 4 * (u0 + (u ^ (k & 7)))) =
+            make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+    }
+  }
+  __syncthreads();
+  // ---- gather: a warp = 32 unknown points x one 32-channel segment per step (two half-steps of 16 points)
+  constexpr int SEGS = CN / 32;
+  const int seg = warp % SEGS;
+  const int Q = lane >> 3, q = lane & 7;
+  const int g_begin = blockIdx.x * groups_per_cta, g_end = min(g_begin + groups_per_cta, (n + 31) >> 5);
+  const int4* ib = reinterpret_cast<const int4*>(idx + (size_t)b * n * 3);
+  const float4* wb = reinterpret_cast<const float4*>(weight + (size_t)b * n * 3);
+  float* tile = s_t + warp * TIP_TILE;
+  const float* fseg = s_f + seg * 32;
+  for (int g = g_begin + warp / SEGS; g < g_end; g += (TIP_T / 32) / SEGS) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int i4 = g * 32 + half * 16 + 4 * Q;              // this lane's 4 points (n % 4 == 0: all in or all out)
+      int id[12];
+      float w[12];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) {
+        id[e] = 0;
+        w[e] = 0.f;
+      }
+      if (i4 < n) {
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+          const int4 a = __ldg(ib + (size_t)(i4 >> 2) * 3 + e);
+          const float4 ww = __ldg(wb + (size_t)(i4 >> 2) * 3 + e);
+          id[4 * e] = a.x; id[4 * e + 1] = a.y; id[4 * e + 2] = a.z; id[4 * e + 3] = a.w;
+          w[4 * e] = ww.x; w[4 * e + 1] = ww.y; w[4 * e + 2] = ww.z; w[4 * e + 3] = ww.w;
+        }
+      }
+      float acc[4][4];
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) {
+        const int r0 = id[3 * pp], r1 = id[3 * pp + 1], r2 = id[3 * pp + 2];
+        const float4 f0 = *reinterpret_cast<const float4*>(fseg + (size_t)r0 * CN + 4 * (q ^ (r0 & 7)));
+        const float4 f1 = *reinterpret_cast<const float4*>(fseg + (size_t)r1 * CN + 4 * (q ^ (r1 & 7)));
+        const float4 f2 = *reinterpret_cast<const float4*>(fseg + (size_t)r2 * CN + 4 * (q ^ (r2 & 7)));
+        const float a0 = w[3 * pp], a1 = w[3 * pp + 1], a2 = w[3 * pp + 2];
+        acc[pp][0] = interp3(a0, f0.x, a1, f1.x, a2, f2.x);
+        acc[pp][1] = interp3(a0, f0.y, a1, f1.y, a2, f2.y);
+        acc[pp][2] = interp3(a0, f0.z, a1, f1.z, a2, f2.z);
+        acc[pp][3] = interp3(a0, f0.w, a1, f1.w, a2, f2.w);
+      }
+      // tile[channel 4q + j][point quad (Q + 4 * half) ^ q]: the 8 lanes of a quarter hit 8 different 16-byte slots
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(tile + (4 * q + j) * 32 + 4 * ((Q + 4 * half) ^ q)) =
+            make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+    }
+    __syncwarp();
+    // ---- rows out: a quarter-warp = one channel row, 8 consecutive point quads = 128 contiguous bytes
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = Q + 4 * it;
+      const float4 v = *reinterpret_cast<const float4*>(tile + row * 32 + 4 * (q ^ ((row >> 2) & 7)));
+      const int c = c0 + seg * 32 + row, i = g * 32 + 4 * q;
+      if (c < C && i < n) __stcs(reinterpret_cast<float4*>(out + ((size_t)b * C + c) * n + i), v);
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(TI_T)
 interp_bwd_kernel(int C, int n, int m, const float* __restrict__ grad_out, const int32_t* __restrict__ idx,
                   const float* __restrict__ weight, float* __restrict__ grad_features) {
@@ -161,6 +262,42 @@ extern "C" int sad_three_interpolate_fwd(int B, int C, int m, int n, const float
   SAD_REQUIRE(features && idx && weight && out, "three_interpolate: null pointer");
   SAD_REQUIRE(B <= 65535 && sad_ceil_div(C, TI_CCH) <= 65535, "three_interpolate: B/C exceed grid limits");
   const bool vec = (n % 4 == 0) && aligned16(idx) && aligned16(weight) && aligned16(out);
+  // point-major staged kernel: rows fit shared memory and are re-read (n * 3 gathers over m rows)
+  // (measured, B = 256, C = 256: n=1024/m=512 58.6 % of the HBM peak vs 57.6 % row-staged; n=512/m=256 51 % vs 53 % --
+  // both kernels sit at ~70 % of the SM's LSU wavefront rate; the point-major kernel takes
+  // the larger-m shapes, where its lower wavefront count per output wins)
+  if (n % 4 == 0 && aligned16(out) && aligned16(idx) && aligned16(weight) && m >= 384 && m <= 1408 && 2LL * n >= m &&
+      !getenv("SAD_INTERP_LEGACY")) {
+    const int cn = (m <= 128 && C > 32) ? 64 : 32;
+    const int ychunks = sad_ceil_div(C, cn);
+    SAD_REQUIRE(ychunks <= 65535, "three_interpolate: C exceeds grid limits");
+    const int groups = sad_ceil_div(n, 32);
+    const int gstep = (TIP_T / 32) / (cn / 32);                         // groups one pass of the CTA covers
+    long long x = sad_ceil_div(444, (long long)ychunks * B);
+    const long long xmax = groups / gstep > 1 ? groups / gstep : 1;     // at least one full pass per CTA
+    if (x > xmax) x = xmax;
+    if (x < 1) x = 1;
+    const int gpc = sad_ceil_div(sad_ceil_div(groups, x), gstep) * gstep;
+    x = sad_ceil_div(groups, gpc);
+    const size_t smem = ((size_t)m * cn + (TIP_T / 32) * TIP_TILE) * sizeof(float);
+    static thread_local int configured_dev_pm = -1;
+    int dev = 0;
+    SAD_CUDA_OK(cudaGetDevice(&dev));
+    if (configured_dev_pm != dev) {
+      SAD_CUDA_OK(cudaFuncSetAttribute(interp_fwd_pm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (1408 * 32 + (TIP_T / 32) * TIP_TILE) * 4));
+      SAD_CUDA_OK(cudaFuncSetAttribute(interp_fwd_pm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (128 * 64 + (TIP_T / 32) * TIP_TILE) * 4));
+      configured_dev_pm = dev;
+    }
+    dim3 g3((unsigned)x, (unsigned)ychunks, (unsigned)B);
+    if (cn == 64)
+      interp_fwd_pm_kernel<64><<<g3, TIP_T, smem, (cudaStream_t)stream>>>(C, m, n, gpc, features, idx, weight, out);
+    else
+      interp_fwd_pm_kernel<32><<<g3, TIP_T, smem, (cudaStream_t)stream>>>(C, m, n, gpc, features, idx, weight, out);
+    SAD_LAUNCH_CHECK("three_interpolate");
+    return SAD_OK;
+  }
   const int cch = (m % 4 == 0 && m <= 4608) ? (18432 / m < 16 ? 18432 / m : 16) : 0;
   if (vec && cch >= 4 && 2LL * n >= m && aligned16(features)) {
     const int quads = n / 4;

@@ -170,7 +170,9 @@ def test_grouping_and_gather_fwd_bwd(ops, B, C_, N, P, S):
 
 
 @pytest.mark.parametrize("B,C_,m,n", [(1, 1, 3, 1), (2, 5, 40, 333), (2, 256, 256, 512), (3, 64, 512, 1024),
-                                      (2, 19, 100, 1026)])
+                                      (2, 19, 100, 1026),
+                                      # point-major staged kernel: channel tails, n % 16 != 0, both chunk widths, largest m
+                                      (2, 6, 384, 1000), (1, 70, 500, 1000), (2, 40, 1408, 2816), (1, 33, 1536, 3072)])
 def test_three_interpolate_fwd_bwd(ops, B, C_, m, n):
     rng = np.random.default_rng(m + n)
     f = rng.standard_normal((B, C_, m)).astype(np.float32)
