@@ -36,6 +36,7 @@ SIGNATURES = {
     "sad_fps_grid_max_points": [],
     "sad_fps_grid_force_cluster": [_c_int],
     "sad_furthest_point_sample_grid_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
+    "sad_furthest_point_sample_grid_policy_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp],
     "sad_mlp_weight_image_bytes": [_c_int, _c_int, _c_int],
     "sad_mlp_pack_weights": [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp],
     "sad_shared_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _c_float, _vp,

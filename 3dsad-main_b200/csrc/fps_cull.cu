@@ -255,14 +255,13 @@ fps_cull_kernel(int N, int npoint, const float* __restrict__ xyz, const uint8_t*
 // best point in shared memory.  A pick costs: one block barrier, a 16-record reduce, the lane-parallel
 // box test, and an L2 round trip for the handful of buckets that survive it (two at a time per warp for
 // latency overlap) -- no cluster, no DSMEM exchange, and 1/4 .. 1/16 of the SMs of the other kernels.
-constexpr int FC1_T = 512;
-constexpr int FC1_NW = FC1_T / 32;
+constexpr int FC1_NW = 16;                // warps of the capacity bound (sad_fps_grid_max_points)
+constexpr int FC1_DEPTH = 4;              // bucket updates (independent L2 round trips) in flight per warp
 
-template <int R>
-__global__ void __launch_bounds__(FC1_T, 1)
+template <int R, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __restrict__ ws, size_t stride,
                  int32_t* __restrict__ out) {
-  constexpr int NW = FC1_NW;
   extern __shared__ __align__(16) float4 s_best[];      // [slot * NW + warp] best point of the bucket {x,y,z,bits(idx)}
   __shared__ __align__(16) float4 s_wrec[2][NW];        // per warp: best point {x,y,z,bits(idx)}
   __shared__ uint32_t s_wval[2][NW];                    // per warp: its min-dist bits
@@ -288,7 +287,13 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
     bidx[r] = kInf;
   }
   // ---- load pass: boxes, and pick 0 applied on the fly (min-dist = min(1e10, d2(p, p0)))
-  for (int s = 0; s < nslots; ++s) {
+  // (register set r as the OUTER, unrolled loop: written as one loop over s with an `if (s >> 5 == r)` chain the
+  // compiler turns the eight state arrays into dynamically indexed local memory)
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+  for (int sl = 0; sl < 32; ++sl) {
+    const int s = r * 32 + sl;
+    if (s >= nslots) break;
     const int k = (s * NW + warp) * 32 + lane;
     const bool ok = k < N;
     float4 p = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInf));
@@ -305,14 +310,12 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
     const uint32_t mx = __reduce_max_sync(FULL, mb);
     const uint32_t ix = __reduce_min_sync(FULL, (ok && mb == mx) ? __float_as_uint(p.w) : kInf);
     if (ok && __float_as_uint(p.w) == ix) s_best[s * NW + warp] = p;
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if ((s >> 5) == r && lane == (s & 31)) {
-        blx[r] = o2f(lx); bly[r] = o2f(ly); blz[r] = o2f(lz);
-        bhx[r] = o2f(hx); bhy[r] = o2f(hy); bhz[r] = o2f(hz);
-        bmax[r] = __uint_as_float(mx);
-        bidx[r] = ix;
-      }
+    if (lane == sl) {
+      blx[r] = o2f(lx); bly[r] = o2f(ly); blz[r] = o2f(lz);
+      bhx[r] = o2f(hx); bhy[r] = o2f(hy); bhz[r] = o2f(hz);
+      bmax[r] = __uint_as_float(mx);
+      bidx[r] = ix;
+    }
   }
   bool changed = true;
 
@@ -376,61 +379,57 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
       }
       uint32_t mask = __ballot_sync(FULL, aff);
       if (mask) changed = true;
-      while (mask) {                                   // two buckets in flight per step (independent L2 round trips)
-        const int b0 = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const bool two = mask != 0u;
-        const int b1 = two ? __ffs(mask) - 1 : b0;
-        if (two) mask &= mask - 1;
-        const int s0 = r * 32 + b0, s1 = r * 32 + b1;
-        const int k0 = (s0 * NW + warp) * 32 + lane, k1 = (s1 * NW + warp) * 32 + lane;
-        const bool ok0 = k0 < N, ok1 = two && (k1 < N);
-        float4 pa = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInf)), pb = pa;
-        float ma = 0.f, mb_ = 0.f;
-        if (ok0) {
-          pa = __ldg(sorted + k0);
-          ma = mind[k0];
+      while (mask) {                                   // FC1_DEPTH buckets in flight per step (independent L2 round trips)
+        int bsel[FC1_DEPTH], kk[FC1_DEPTH];
+        bool okk[FC1_DEPTH], use[FC1_DEPTH];
+        float4 pt[FC1_DEPTH];
+        float md[FC1_DEPTH];
+#pragma unroll
+        for (int u = 0; u < FC1_DEPTH; ++u) {
+          use[u] = mask != 0u;
+          bsel[u] = use[u] ? __ffs(mask) - 1 : 0;
+          if (use[u]) mask &= mask - 1;
+          kk[u] = ((r * 32 + bsel[u]) * NW + warp) * 32 + lane;
+          okk[u] = use[u] && kk[u] < N;
+          pt[u] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInf));
+          md[u] = 0.f;
+          if (okk[u]) {
+            pt[u] = __ldg(sorted + kk[u]);
+            md[u] = mind[kk[u]];
+          }
         }
-        if (ok1) {
-          pb = __ldg(sorted + k1);
-          mb_ = mind[k1];
-        }
-        const float na = fminf(ma, sqdist(pa.x, pa.y, pa.z, qx, qy, qz));
-        const float nb_ = fminf(mb_, sqdist(pb.x, pb.y, pb.z, qx, qy, qz));
-        if (ok0 && na < ma) mind[k0] = na;
-        if (ok1 && nb_ < mb_) mind[k1] = nb_;
-        const uint32_t ua = __float_as_uint(na), ub = __float_as_uint(nb_);      // >= 0: bit order == value order
-        const uint32_t mxa = __reduce_max_sync(FULL, ua), mxb = __reduce_max_sync(FULL, ub);
-        const uint32_t ixa = __reduce_min_sync(FULL, (ok0 && ua == mxa) ? __float_as_uint(pa.w) : kInf);
-        const uint32_t ixb = __reduce_min_sync(FULL, (ok1 && ub == mxb) ? __float_as_uint(pb.w) : kInf);
-        if (ok0 && __float_as_uint(pa.w) == ixa) s_best[s0 * NW + warp] = pa;
-        if (ok1 && __float_as_uint(pb.w) == ixb) s_best[s1 * NW + warp] = pb;
-        if (lane == b0) {
-          bmax[r] = __uint_as_float(mxa);
-          bidx[r] = ixa;
-        }
-        if (two && lane == b1) {
-          bmax[r] = __uint_as_float(mxb);
-          bidx[r] = ixb;
+#pragma unroll
+        for (int u = 0; u < FC1_DEPTH; ++u) {
+          if (!use[u]) break;                            // warp-uniform
+          const float nd = fminf(md[u], sqdist(pt[u].x, pt[u].y, pt[u].z, qx, qy, qz));
+          if (okk[u] && nd < md[u]) mind[kk[u]] = nd;
+          const uint32_t un = __float_as_uint(nd);       // >= 0: bit order == value order
+          const uint32_t mx = __reduce_max_sync(FULL, un);
+          const uint32_t ix = __reduce_min_sync(FULL, (okk[u] && un == mx) ? __float_as_uint(pt[u].w) : kInf);
+          if (okk[u] && __float_as_uint(pt[u].w) == ix) s_best[(r * 32 + bsel[u]) * NW + warp] = pt[u];
+          if (lane == bsel[u]) {
+            bmax[r] = __uint_as_float(mx);
+            bidx[r] = ix;
+          }
         }
       }
     }
   }
 }
 
-template <int R>
+template <int R, int NW>
 int launch_cull1(int B, int N, int npoint, const float* xyz, void* ws, int32_t* idx, cudaStream_t stream) {
-  auto kern = fps_cull1_kernel<R>;
+  auto kern = fps_cull1_kernel<R, NW>;
   const int nb = (N + 31) / 32;
-  const size_t smem = (size_t)sad_ceil_div(nb, FC1_NW) * FC1_NW * sizeof(float4);
+  const size_t smem = (size_t)sad_ceil_div(nb, NW) * NW * sizeof(float4);
   static thread_local int configured_dev = -1;
   int dev = 0;
   SAD_CUDA_OK(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    SAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, R * 32 * FC1_NW * 16));
+    SAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, R * 32 * NW * 16));
     configured_dev = dev;
   }
-  kern<<<B, FC1_T, smem, stream>>>(N, npoint, xyz, static_cast<uint8_t*>(ws), sad::grid_stride(N), idx);
+  kern<<<B, NW * 32, smem, stream>>>(N, npoint, xyz, static_cast<uint8_t*>(ws), sad::grid_stride(N), idx);
   SAD_LAUNCH_CHECK("fps_cull1_kernel");
   return SAD_OK;
 }
@@ -488,7 +487,14 @@ extern "C" int sad_fps_grid_max_points(void) { return 16 * 32 * FC1_NW * 32; }
 
 extern "C" int sad_furthest_point_sample_grid_fwd(int B, int N, int npoint, const float* xyz, void* grid_ws,
                                                   int32_t* idx, sad_stream_t stream_) {
+  return sad_furthest_point_sample_grid_policy_fwd(B, N, npoint, xyz, grid_ws, idx, SAD_FPS_LATENCY, stream_);
+}
+
+extern "C" int sad_furthest_point_sample_grid_policy_fwd(int B, int N, int npoint, const float* xyz, void* grid_ws,
+                                                         int32_t* idx, int policy, sad_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  SAD_REQUIRE(policy == SAD_FPS_LATENCY || policy == SAD_FPS_THROUGHPUT, "furthest_point_sample_grid: bad policy %d", policy);
+  const int force = g_cull_cluster != 0 ? g_cull_cluster : (policy == SAD_FPS_THROUGHPUT ? -1 : 0);
   SAD_REQUIRE(B >= 0 && N >= 1 && npoint >= 1, "furthest_point_sample_grid: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
   if (B == 0) return SAD_OK;
   SAD_REQUIRE(xyz && grid_ws && idx, "furthest_point_sample_grid: null pointer");
@@ -498,7 +504,7 @@ extern "C" int sad_furthest_point_sample_grid_fwd(int B, int N, int npoint, cons
     return SAD_OK;
   }
 #endif
-  if (N > 16 * (FC_MAX_SLOTS * FC_NW * 32) && N <= 204800 && g_cull_cluster == 0)
+  if (N > 16 * (FC_MAX_SLOTS * FC_NW * 32) && N <= 204800 && force == 0)
     return sad_furthest_point_sample_fwd(B, N, npoint, xyz, idx, stream_);   // beyond the cluster capacity the register-resident kernel wins
   if (N > sad_fps_grid_max_points()) {
     sad_set_error("furthest_point_sample_grid: N=%d exceeds the capacity (%d)", N, sad_fps_grid_max_points());
@@ -506,9 +512,9 @@ extern "C" int sad_furthest_point_sample_grid_fwd(int B, int N, int npoint, cons
   }
   const int nbk = (N + 31) / 32;
   const int cap = FC_MAX_SLOTS * FC_NW * 32;           // points per CTA of the cluster kernel
-  if (g_cull_cluster >= 0 && N <= 16 * cap) {
+  if (force >= 0 && N <= 16 * cap) {
     int cs = 1;
-    while (cs < g_cull_cluster && cs < 16) cs <<= 1;
+    while (cs < force && cs < 16) cs <<= 1;
     while (cs * cap < N) cs <<= 1;
     const int slots = sad_ceil_div(sad_ceil_div(nbk, cs), FC_NW);
     switch (cs) {
@@ -519,10 +525,12 @@ extern "C" int sad_furthest_point_sample_grid_fwd(int B, int N, int npoint, cons
       default: return launch_cull<16>(B, N, npoint, xyz, grid_ws, idx, slots, stream);
     }
   }
+  // one SM per scene: 32 warps while two register sets of bucket state per lane suffice (N <= 65536), else 16 warps
+  const int per_lane32 = sad_ceil_div(sad_ceil_div(nbk, 32), 32);
+  if (per_lane32 <= 1) return launch_cull1<1, 32>(B, N, npoint, xyz, grid_ws, idx, stream);
+  if (per_lane32 <= 2) return launch_cull1<2, 32>(B, N, npoint, xyz, grid_ws, idx, stream);
   const int per_lane = sad_ceil_div(sad_ceil_div(nbk, FC1_NW), 32);   // bucket slots per lane
-  if (per_lane <= 1) return launch_cull1<1>(B, N, npoint, xyz, grid_ws, idx, stream);
-  if (per_lane <= 2) return launch_cull1<2>(B, N, npoint, xyz, grid_ws, idx, stream);
-  if (per_lane <= 4) return launch_cull1<4>(B, N, npoint, xyz, grid_ws, idx, stream);
-  if (per_lane <= 8) return launch_cull1<8>(B, N, npoint, xyz, grid_ws, idx, stream);
-  return launch_cull1<16>(B, N, npoint, xyz, grid_ws, idx, stream);
+  if (per_lane <= 6) return launch_cull1<6, FC1_NW>(B, N, npoint, xyz, grid_ws, idx, stream);
+  if (per_lane <= 8) return launch_cull1<8, FC1_NW>(B, N, npoint, xyz, grid_ws, idx, stream);
+  return launch_cull1<16, FC1_NW>(B, N, npoint, xyz, grid_ws, idx, stream);
 }

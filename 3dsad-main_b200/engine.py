@@ -38,8 +38,12 @@ class PipelinedHotPath:
     """
 
     def __init__(self, model, batch: int, n_points: int, feat_dim: int = 1, slots: int = 3,
-                 device: Optional[torch.device] = None, warmup: int = 2):
+                 device: Optional[torch.device] = None, warmup: int = 2, fps_policy: str = "throughput"):
+        """`fps_policy`: "throughput" (default) captures the one-SM-per-scene FPS kernel -- longer per batch, but
+        about half the SM-time, which is what bounds a pipeline with several batches in flight; "latency" captures the
+        cluster kernel (shortest time per batch; right for 1-2 slots)."""
         self.model = model
+        self.fps_policy = fps_policy
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         self.batch, self.n_points, self.feat_dim = batch, n_points, feat_dim
         self.n_clusters = model.agg.sa.npoint
@@ -48,6 +52,16 @@ class PipelinedHotPath:
         self._slots: List[_Slot] = []
         lib = _lib.load()
         dev = self.device
+        from . import modules as _modules
+        saved_policy = _modules.FPS_POLICY[0]
+        _modules.FPS_POLICY[0] = fps_policy
+        try:
+            self._capture(model, batch, n_points, feat_dim, slots, dev, warmup, lib)
+        finally:
+            _modules.FPS_POLICY[0] = saved_policy
+        self.launches_per_batch = self._slots[0].launches
+
+    def _capture(self, model, batch, n_points, feat_dim, slots, dev, warmup, lib):
         with torch.cuda.device(dev), torch.no_grad():
             for _ in range(slots):
                 s = _Slot()
@@ -77,7 +91,6 @@ class PipelinedHotPath:
                 s.launches = int(lib.sad_launch_count() - l0)
                 s.out_host = model.make_host_outputs(batch)
             torch.cuda.synchronize(dev)
-        self.launches_per_batch = self._slots[0].launches
 
     # ------------------------------------------------------------------ submission
     @property

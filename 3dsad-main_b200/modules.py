@@ -29,6 +29,13 @@ from . import mlp as _mlp
 from .config import LAYER_CFG, mlp_channels
 
 
+# How the scene-grid FPS of large scenes is scheduled (ops.FurthestPointSampling `policy`): "latency" = a cluster of SMs
+# per scene (an eager caller waiting for one batch), "throughput" = one SM per scene (engine.PipelinedHotPath switches
+# to it while it captures its graphs: with several batches in flight the step is bound by SM-time, not by any one
+# kernel's latency).  Results are bit-identical.
+FPS_POLICY = ["latency"]
+
+
 class SharedMLP(nn.Module):
     """Stack of 1x1 Conv2d (+BatchNorm2d) + ReLU over (B,C,P,S) [LINEAGE pt_utils.SharedMLP]."""
 
@@ -128,7 +135,7 @@ class PointnetSAModuleVotes(nn.Module):
         if grid is None and inds is None and xyz.shape[1] >= ops.GRID_MIN_POINTS:
             grid = ops.build_scene_grid(xyz)
         if inds is None:
-            inds = ops.furthest_point_sample(xyz, self.npoint, grid)
+            inds = ops.furthest_point_sample(xyz, self.npoint, grid, FPS_POLICY[0])
         if new_xyz is None:
             new_xyz = _gather_xyz(xyz, inds)
         if radius_t is not None:
@@ -215,7 +222,7 @@ class Pointnet2Backbone(nn.Module):
         xyz.record_stream(geo_a)
         with torch.cuda.stream(geo_a):
             grid = ops.build_scene_grid(xyz) if xyz.shape[1] >= ops.GRID_MIN_POINTS else None
-            inds = ops.furthest_point_sample(xyz, self.sa1.npoint, grid)
+            inds = ops.furthest_point_sample(xyz, self.sa1.npoint, grid, FPS_POLICY[0])
             x = _gather_xyz(xyz, inds)
             ev = torch.cuda.Event()
             ev.record(geo_a)

@@ -92,14 +92,16 @@ def build_scene_grid(xyz: torch.Tensor) -> SceneGrid:
 # Scenes at least this large get a scene grid built on the fly by furthest_point_sample / ball_query
 # when the caller passes none (the build costs one short kernel; below it the plain kernels win).
 GRID_MIN_POINTS = 8192
+FPS_POLICIES = {"latency": 0, "throughput": 1}        # include/sad_ops.h SAD_FPS_LATENCY / SAD_FPS_THROUGHPUT
 
 
 class FurthestPointSampling(Function):
     """a1.  xyz (B,N,3) f32 -> (B,npoint) i32; sel[0]=0, ties to the lowest index.
-    Optional `grid` (SceneGrid of the same xyz) selects the exact culled kernel."""
+    Optional `grid` (SceneGrid of the same xyz) selects the exact culled kernel; `policy` picks how it is scheduled
+    ("latency": a cluster of SMs per scene, "throughput": one SM per scene) -- never the result."""
 
     @staticmethod
-    def forward(ctx, xyz, npoint, grid=None):
+    def forward(ctx, xyz, npoint, grid=None, policy="latency"):
         _req(xyz, "xyz", torch.float32, 3, 3)
         B, N, _ = xyz.shape
         npoint = int(npoint)
@@ -112,8 +114,9 @@ class FurthestPointSampling(Function):
         with torch.cuda.device(xyz.device):
             if grid is not None and N <= lib.sad_fps_grid_max_points():
                 grid.check(xyz)
-                _lib.check(lib.sad_furthest_point_sample_grid_fwd(B, N, npoint, _p(xyz), _p(grid.workspace), _p(out),
-                                                                  _stream(xyz)), "furthest_point_sample_grid")
+                _lib.check(lib.sad_furthest_point_sample_grid_policy_fwd(
+                    B, N, npoint, _p(xyz), _p(grid.workspace), _p(out), FPS_POLICIES[policy], _stream(xyz)),
+                    "furthest_point_sample_grid")
             else:
                 _lib.check(lib.sad_furthest_point_sample_fwd(B, N, npoint, _p(xyz), _p(out), _stream(xyz)),
                            "furthest_point_sample")
@@ -122,7 +125,7 @@ class FurthestPointSampling(Function):
 
     @staticmethod
     def backward(ctx, grad=None):
-        return None, None, None
+        return None, None, None, None
 
 
 class GatherOperation(Function):

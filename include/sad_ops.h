@@ -70,6 +70,16 @@ SAD_API int sad_scene_grid_build(int B, int N, const float* xyz, void* workspace
 SAD_API int sad_fps_grid_max_points(void);
 SAD_API int sad_furthest_point_sample_grid_fwd(int B, int N, int npoint, const float* xyz,
                                                void* grid_workspace, int32_t* idx, sad_stream_t stream);
+/* Same result, explicit scheduling policy.  SAD_FPS_LATENCY (what sad_furthest_point_sample_grid_fwd uses): the
+ * fewest-CTA cluster whose shared memory holds the scene -- shortest time per scene (40k points: 4 SMs, 0.70 us per
+ * pick).  SAD_FPS_THROUGHPUT: ONE SM per scene over the L2-resident sorted array (1.5 us per pick, i.e. about half
+ * the SM-time per scene): what a pipelined caller with other kernels to overlap wants (writes the workspace's
+ * min-distance scratch, so two calls must not share a workspace). */
+#define SAD_FPS_LATENCY 0
+#define SAD_FPS_THROUGHPUT 1
+SAD_API int sad_furthest_point_sample_grid_policy_fwd(int B, int N, int npoint, const float* xyz,
+                                                      void* grid_workspace, int32_t* idx, int policy,
+                                                      sad_stream_t stream);
 /* Test / benchmark hook: 0 = default; 1,2,4,8,16 = cluster kernel with at least that many CTAs per
  * scene; -1 = single-CTA kernel.  Results never depend on it. */
 SAD_API void sad_fps_grid_force_cluster(int cluster_size);

@@ -165,3 +165,18 @@ def test_grid_ball_query_duplicates_overflow(ops):
     got = ops.ball_query(0.1, 8, x, cu(q), ops.build_scene_grid(x)).cpu().numpy()
     assert np.array_equal(got, C.ball_query(0.1, 8, p, q))
     assert got[0, 0].tolist() == list(range(8)) and got[0, 1].tolist() == list(range(2500, 2508)) and not got[0, 2].any()
+
+
+@pytest.mark.parametrize("N,npoint", [(9000, 300), (40000, 512), (70001, 128)])
+def test_fps_scheduling_policy_never_changes_the_result(ops, N, npoint):
+    """C ABI sad_furthest_point_sample_grid_policy_fwd: latency (cluster) and throughput (one SM per scene)."""
+    rng = np.random.default_rng(N)
+    xyz = (rng.random((2, N, 3), dtype=np.float32) * np.array([6, 6, 3], np.float32)).astype(np.float32)
+    x = cu(xyz)
+    grid = ops.build_scene_grid(x)
+    want = C.furthest_point_sample(xyz, npoint)
+    for policy in ("latency", "throughput"):
+        got = ops.furthest_point_sample(x, npoint, grid, policy)
+        assert np.array_equal(got.cpu().numpy(), want), policy
+    with pytest.raises(KeyError):
+        ops.furthest_point_sample(x, npoint, grid, "fastest")
