@@ -257,27 +257,41 @@ fps_cull_kernel(int N, int npoint, const float* __restrict__ xyz, const uint8_t*
 // latency overlap) -- no cluster, no DSMEM exchange, and 1/4 .. 1/16 of the SMs of the other kernels.
 constexpr int FC1_NW = 16;                // warps of the capacity bound (sad_fps_grid_max_points)
 constexpr int FC1_DEPTH = 4;              // bucket updates (independent L2 round trips) in flight per warp
+constexpr int FC1_OUT = 2048;             // picks buffered in shared memory between flushes to the output
+constexpr int FC1_MDS_MAX = 46000;        // min-distances in shared memory up to this many points (4.5 B per point)
 
-template <int R, int NW>
+// MDS: the min-distances live in shared memory instead of the workspace scratch (scenes up to FC1_MDS_MAX points), and
+// the picks are buffered in shared memory and written out once per FC1_OUT picks: no global store sits between the
+// two barriers of a pick.  Measured on 8 x 40k points -> 2048: 2.99 ms (3.05 ms with both in global memory).  What a
+// pick costs (ablation build -DSAD_FPS_ABLATE, no bucket updates): ~1.5 k cycles FIXED -- 32 warps x ~100
+// instructions of box tests and bookkeeping issue-bound on the four schedulers, plus the record -> barrier -> one-warp
+// reduce -> barrier chain -- and ~1.5 k cycles for the L2 round trip of the surviving buckets' points.
+template <int R, int NW, bool MDS>
 __global__ void __launch_bounds__(NW * 32, 1)
 fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __restrict__ ws, size_t stride,
                  int32_t* __restrict__ out) {
   extern __shared__ __align__(16) float4 s_best[];      // [slot * NW + warp] best point of the bucket {x,y,z,bits(idx)}
-  __shared__ __align__(16) float4 s_wrec[2][NW];        // per warp: best point {x,y,z,bits(idx)}
-  __shared__ uint32_t s_wval[2][NW];                    // per warp: its min-dist bits
+  // then: int32 s_out[FC1_OUT]; then (MDS) float s_md[N]
+  __shared__ __align__(16) float4 s_wrec[NW];           // per warp: best point {x,y,z,bits(idx)}
+  __shared__ uint32_t s_wval[NW];                       // per warp: its min-dist bits
+  __shared__ __align__(16) float4 s_pick;               // the pick of this round {x,y,z,bits(idx)}, written by warp 0
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   uint8_t* base = ws + (size_t)b * stride;
   const float4* sorted = reinterpret_cast<const float4*>(base + kGridHeaderBytes + kGridCellBytes);
-  float* mind = reinterpret_cast<float*>(base + grid_scratch_offset(N));
   int32_t* o = out + (size_t)b * npoint;
   const int NB = (N + 31) >> 5;
+  int32_t* s_out = reinterpret_cast<int32_t*>(s_best + (size_t)((NB + NW - 1) / NW) * NW);
+  float* mind = MDS ? reinterpret_cast<float*>(s_out + FC1_OUT) : reinterpret_cast<float*>(base + grid_scratch_offset(N));
   const int nslots = NB > warp ? (NB - warp + NW - 1) / NW : 0;      // buckets warp, warp+NW, ...
 
   const float* p0 = xyz + (size_t)b * N * 3;
   float qx = __ldg(p0), qy = __ldg(p0 + 1), qz = __ldg(p0 + 2);       // pick 0 = point 0
-  if (tid == 0) o[0] = 0;
+  if (tid == 0) {
+    s_out[0] = 0;
+    if (npoint == 1) o[0] = 0;            // no pick loop, no flush
+  }
 
   float blx[R], bly[R], blz[R], bhx[R], bhy[R], bhz[R], bmax[R];
   uint32_t bidx[R];
@@ -318,10 +332,16 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
     }
   }
   bool changed = true;
+#ifdef SAD_FPS_PROFILE
+  long long ph[5] = {0, 0, 0, 0, 0}, nupd = 0, nround = 0, tprev = clock64();
+#define SAD_MARK1(i) { const long long tn = clock64(); ph[i] += tn - tprev; tprev = tn; }
+#else
+#define SAD_MARK1(i)
+#endif
 
   for (int j = 1; j < npoint; ++j) {
-    const int buf = j & 1;
-    // ---- this warp's record: its best bucket (recomputed only when one of its buckets changed)
+    // ---- this warp's record: its best bucket (rewritten only when one of its buckets changed; records are read
+    // by warp 0 alone, between the two barriers, so one buffer suffices and an unchanged warp does nothing)
     __syncwarp();
     if (changed) {
       uint32_t v = 0u, vi = kInf;
@@ -341,31 +361,43 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
       const uint32_t widx = __reduce_min_sync(FULL, v == wmax ? vi : kInf);
       if (widx == kInf) {
         if (lane == 0) {
-          s_wval[buf][warp] = 0u;
-          s_wrec[buf][warp] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInf));
+          s_wval[warp] = 0u;
+          s_wrec[warp] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInf));
         }
       } else if (v == wmax && vi == widx) {
-        s_wval[buf][warp] = wmax;
-        s_wrec[buf][warp] = s_best[(vr * 32 + lane) * NW + warp];
+        s_wval[warp] = wmax;
+        s_wrec[warp] = s_best[(vr * 32 + lane) * NW + warp];
       }
-    } else if (lane == 0) {
-      s_wval[buf][warp] = s_wval[buf ^ 1][warp];
-      s_wrec[buf][warp] = s_wrec[buf ^ 1][warp];
+    }
+    SAD_MARK1(0)
+    __syncthreads();
+    SAD_MARK1(1)
+
+    // ---- warp 0 reduces the NW records (max value, ties -> lowest original index) and publishes the pick: one
+    // warp's two redux instead of every warp's (the redux unit is shared; NW redundant reductions queue on it)
+    if (warp == 0) {
+      const uint32_t x = lane < NW ? s_wval[lane] : 0u;
+      const uint32_t id = lane < NW ? __float_as_uint(s_wrec[lane].w) : kInf;
+      const uint32_t gmax = __reduce_max_sync(FULL, x);
+      const uint32_t gidx = __reduce_min_sync(FULL, x == gmax ? id : kInf);
+      if (x == gmax && id == gidx && lane < NW) {
+        s_pick = s_wrec[lane];
+        s_out[j & (FC1_OUT - 1)] = (int32_t)gidx;
+      }
     }
     __syncthreads();
-
-    // ---- every warp reduces the NW records: max value, ties -> lowest original index
-    const uint32_t x = lane < NW ? s_wval[buf][lane] : 0u;
-    const uint32_t id = lane < NW ? __float_as_uint(s_wrec[buf][lane].w) : kInf;
-    const uint32_t gmax = __reduce_max_sync(FULL, x);
-    const uint32_t gidx = __reduce_min_sync(FULL, x == gmax ? id : kInf);
-    const uint32_t gl = __ballot_sync(FULL, x == gmax && id == gidx);
-    const float4 w = s_wrec[buf][gl ? __ffs(gl) - 1 : 0];
-    qx = w.x;
-    qy = w.y;
-    qz = w.z;
-    if (tid == 0) o[j] = (int32_t)gidx;
+    if (((j + 1) & (FC1_OUT - 1)) == 0 || j == npoint - 1) {     // flush the buffered picks (coalesced, rare)
+      const int j0 = j & ~(FC1_OUT - 1);
+      for (int i = tid; j0 + i <= j; i += NW * 32) o[j0 + i] = s_out[i];
+    }
+    {
+      const float4 w = s_pick;
+      qx = w.x;
+      qy = w.y;
+      qz = w.z;
+    }
     if (j == npoint - 1) break;
+    SAD_MARK1(2)
 
     // ---- cull + update: only buckets whose box the pick can reach
     changed = false;
@@ -379,7 +411,16 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
       }
       uint32_t mask = __ballot_sync(FULL, aff);
       if (mask) changed = true;
+#ifdef SAD_FPS_PROFILE
+      nupd += __popc(mask);
+#endif
+#ifdef SAD_FPS_ABLATE
+      mask = 0u;                                       // tools only: no bucket updates at all (wrong picks): the fixed cost per pick
+#endif
       while (mask) {                                   // FC1_DEPTH buckets in flight per step (independent L2 round trips)
+#ifdef SAD_FPS_PROFILE
+        ++nround;
+#endif
         int bsel[FC1_DEPTH], kk[FC1_DEPTH];
         bool okk[FC1_DEPTH], use[FC1_DEPTH];
         float4 pt[FC1_DEPTH];
@@ -414,19 +455,29 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
         }
       }
     }
+    SAD_MARK1(3)
   }
+#ifdef SAD_FPS_PROFILE
+  if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 7 || warp == NW - 1))
+    printf("[fps_cull1 R=%d NW=%d N=%d warp %d] per pick: record %lld  barrier %lld  reduce %lld  box+update %lld cycles  (%.2f buckets, %.2f rounds)\n",
+           R, NW, N, warp, ph[0] / (npoint - 1), ph[1] / (npoint - 1), ph[2] / (npoint - 1), ph[3] / (npoint - 1),
+           (double)nupd / (npoint - 1), (double)nround / (npoint - 1));
+#endif
+#undef SAD_MARK1
 }
 
-template <int R, int NW>
+template <int R, int NW, bool MDS>
 int launch_cull1(int B, int N, int npoint, const float* xyz, void* ws, int32_t* idx, cudaStream_t stream) {
-  auto kern = fps_cull1_kernel<R, NW>;
+  auto kern = fps_cull1_kernel<R, NW, MDS>;
   const int nb = (N + 31) / 32;
-  const size_t smem = (size_t)sad_ceil_div(nb, NW) * NW * sizeof(float4);
+  const size_t smem = (size_t)sad_ceil_div(nb, NW) * NW * sizeof(float4) + FC1_OUT * sizeof(int32_t) +
+                      (MDS ? (size_t)N * sizeof(float) : 0);
   static thread_local int configured_dev = -1;
   int dev = 0;
   SAD_CUDA_OK(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    SAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, R * 32 * NW * 16));
+    SAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     MDS ? 227 * 1024 - 2048 : R * 32 * NW * 16 + FC1_OUT * 4));
     configured_dev = dev;
   }
   kern<<<B, NW * 32, smem, stream>>>(N, npoint, xyz, static_cast<uint8_t*>(ws), sad::grid_stride(N), idx);
@@ -527,10 +578,13 @@ extern "C" int sad_furthest_point_sample_grid_policy_fwd(int B, int N, int npoin
   }
   // one SM per scene: 32 warps while two register sets of bucket state per lane suffice (N <= 65536), else 16 warps
   const int per_lane32 = sad_ceil_div(sad_ceil_div(nbk, 32), 32);
-  if (per_lane32 <= 1) return launch_cull1<1, 32>(B, N, npoint, xyz, grid_ws, idx, stream);
-  if (per_lane32 <= 2) return launch_cull1<2, 32>(B, N, npoint, xyz, grid_ws, idx, stream);
+  if (N <= FC1_MDS_MAX) {                 // min-distances in shared memory
+    if (per_lane32 <= 1) return launch_cull1<1, 32, true>(B, N, npoint, xyz, grid_ws, idx, stream);
+    return launch_cull1<2, 32, true>(B, N, npoint, xyz, grid_ws, idx, stream);
+  }
+  if (per_lane32 <= 2) return launch_cull1<2, 32, false>(B, N, npoint, xyz, grid_ws, idx, stream);
   const int per_lane = sad_ceil_div(sad_ceil_div(nbk, FC1_NW), 32);   // bucket slots per lane
-  if (per_lane <= 6) return launch_cull1<6, FC1_NW>(B, N, npoint, xyz, grid_ws, idx, stream);
-  if (per_lane <= 8) return launch_cull1<8, FC1_NW>(B, N, npoint, xyz, grid_ws, idx, stream);
-  return launch_cull1<16, FC1_NW>(B, N, npoint, xyz, grid_ws, idx, stream);
+  if (per_lane <= 6) return launch_cull1<6, FC1_NW, false>(B, N, npoint, xyz, grid_ws, idx, stream);
+  if (per_lane <= 8) return launch_cull1<8, FC1_NW, false>(B, N, npoint, xyz, grid_ws, idx, stream);
+  return launch_cull1<16, FC1_NW, false>(B, N, npoint, xyz, grid_ws, idx, stream);
 }
