@@ -812,6 +812,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             mbar_wait(&ms->dfull[s][0], d_cnt & 1u);
             ++d_cnt;
             tc_fence_after();
+            SAD_LOG(0, 200 + li * 10 + s)
             const long long R = tile * 128 + et;
             const bool ok = R < p.total_rows;
             const uint32_t pt = ok ? (uint32_t)R : 0u;
@@ -824,6 +825,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
               uint32_t v[32];
               tmem_ld32_issue(region + (uint32_t)c0, v);
               tmem_ld_wait();
+              SAD_LOG(0, 400 + li * 10 + s)
               float y[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
@@ -1052,8 +1054,11 @@ static bool plan_launch(MlpParams& p, int hidden_max, size_t& smem_out) {
       // cp.async groups a gather thread keeps in flight before it publishes the oldest chunk.  Measured (SA2: 80 us
       // at 1, 84 at 2, 92 at 3): publishing every chunk as soon as it lands beats deeper prefetch, because the MMA warp
       // consumes chunks in order and the four gather warps already overlap each other's round trips.
-      p.depth = 1;
-      if (const char* e_d = getenv("SAD_MLP_DEPTH")) p.depth = atoi(e_d) < 1 ? 1 : (atoi(e_d) > p.depth ? p.depth : atoi(e_d));
+      // Exception: the wide point-wise stages (S == 1, K0 >= 384: FP layers) run one tile per CTA, nothing overlaps the
+      // gather, and three groups in flight cut its eight serial L2 round trips (CTA span 20.6 -> 15.9 us).
+      p.depth = (p.S == 1 && p.kpad[0] >= 384) ? 3 : 1;
+      if (const char* e_d = getenv("SAD_MLP_DEPTH")) p.depth = atoi(e_d) < 1 ? 1 : (atoi(e_d) > 3 ? 3 : atoi(e_d));
+      if (p.depth > na - 1) p.depth = na - 1;
       p.n_pinned = n_pinned;
       p.pinned_bytes = (int)pinned;
       p.nr = nr;
