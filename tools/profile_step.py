@@ -25,8 +25,12 @@ def main():
     ap.add_argument("--B", type=int, default=8)
     ap.add_argument("--N", type=int, default=40000)
     ap.add_argument("--calls", action="store_true", help="print CUDA-event time of every C-ABI call (serial, one stream)")
+    ap.add_argument("--fps-policy", default="throughput", choices=["throughput", "latency"],
+                    help="which scene-grid FPS kernel runs (bench.py's pipelined executor captures `throughput`)")
     a = ap.parse_args()
     dev = "cuda:0"
+    from sad_b200 import modules as _modules
+    _modules.FPS_POLICY[0] = a.fps_policy
     model = SADHotPath(1).load_params(make_params(0)).to(dev).eval()
     xyz, feat = make_scenes(a.B, a.N, "surface")
     size = make_sizes(a.B, LAYER_CFG["agg"][0])
