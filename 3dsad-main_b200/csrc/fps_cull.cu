@@ -579,6 +579,15 @@ extern "C" int sad_furthest_point_sample_grid_policy_fwd(int B, int N, int npoin
   // one SM per scene: 32 warps while two register sets of bucket state per lane suffice (N <= 65536), else 16 warps
   const int per_lane32 = sad_ceil_div(sad_ceil_div(nbk, 32), 32);
   if (N <= FC1_MDS_MAX) {                 // min-distances in shared memory
+    // 16 warps per scene: a pick's fixed cost is issue-bound (every warp runs ~180 bookkeeping + box-test
+    // instructions per pick), so 16 warps x 3 register sets beat 32 x 2 (2.83 vs 2.99 ms at 40k points)
+    static const int nw_env = getenv("SAD_FPS1_NW") ? atoi(getenv("SAD_FPS1_NW")) : 16;   // tools: warps per scene
+    if (nw_env != 32) {
+      const int pl = sad_ceil_div(sad_ceil_div(nbk, 16), 32);
+      if (pl <= 1) return launch_cull1<1, 16, true>(B, N, npoint, xyz, grid_ws, idx, stream);
+      if (pl <= 2) return launch_cull1<2, 16, true>(B, N, npoint, xyz, grid_ws, idx, stream);
+      return launch_cull1<3, 16, true>(B, N, npoint, xyz, grid_ws, idx, stream);
+    }
     if (per_lane32 <= 1) return launch_cull1<1, 32, true>(B, N, npoint, xyz, grid_ws, idx, stream);
     return launch_cull1<2, 32, true>(B, N, npoint, xyz, grid_ws, idx, stream);
   }

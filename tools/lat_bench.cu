@@ -56,6 +56,9 @@ int main() {
   run<4>("ffs + add", 32);
   run<5>("__syncthreads (4 warps)", 128);
   run<5>("__syncthreads (16 warps)", 512);
+  run<5>("__syncthreads (32 warps)", 1024);
+  run<0>("redux.max + add (32 warps)", 1024);
+  run<3>("lds + add (32 warps)", 1024);
   run<6>("__syncwarp", 32);
   run<7>("fmin + fadd", 32);
   run<8>("mbarrier arrive+try_wait (1 warp)", 32);
