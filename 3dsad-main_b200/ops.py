@@ -95,6 +95,12 @@ GRID_MIN_POINTS = 8192
 FPS_POLICIES = {"latency": 0, "throughput": 1}        # include/sad_ops.h SAD_FPS_LATENCY / SAD_FPS_THROUGHPUT
 
 
+# Under torch.autocast the differentiable ops run in fp32 (bf16 features are cast on entry, gradients come back in the
+# input's dtype): the point-wise MLPs are the only bf16 consumers of a mixed-precision training step (config 4).
+_amp_fwd = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_amp_bwd = torch.amp.custom_bwd(device_type="cuda")
+
+
 class FurthestPointSampling(Function):
     """a1.  xyz (B,N,3) f32 -> (B,npoint) i32; sel[0]=0, ties to the lowest index.
     Optional `grid` (SceneGrid of the same xyz) selects the exact culled kernel; `policy` picks how it is scheduled
@@ -132,6 +138,7 @@ class GatherOperation(Function):
     """a2.  features (B,C,N) f32, idx (B,npoint) i32 -> (B,C,npoint)."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, features, idx):
         _req(features, "features", torch.float32, 3)
         _req(idx, "idx", torch.int32, 2)
@@ -149,6 +156,7 @@ class GatherOperation(Function):
         return out
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, grad_out):
         (idx,) = ctx.saved_tensors
         grad_out = grad_out.contiguous()
@@ -236,6 +244,7 @@ class GroupingOperation(Function):
     """a5.  features (B,C,N) f32, idx (B,npoint,nsample) i32 -> (B,C,npoint,nsample)."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, features, idx):
         _req(features, "features", torch.float32, 3)
         _req(idx, "idx", torch.int32, 3)
@@ -253,6 +262,7 @@ class GroupingOperation(Function):
         return out
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, grad_out):
         (idx,) = ctx.saved_tensors
         grad_out = grad_out.contiguous()
@@ -295,6 +305,7 @@ class ThreeInterpolate(Function):
     """a9.  features (B,C,m) f32, idx (B,n,3) i32, weight (B,n,3) f32 -> (B,C,n)."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, features, idx, weight):
         _req(features, "features", torch.float32, 3)
         _req(idx, "idx", torch.int32, 3, 3)
@@ -313,6 +324,7 @@ class ThreeInterpolate(Function):
         return out
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, grad_out):
         idx, weight = ctx.saved_tensors
         grad_out = grad_out.contiguous()

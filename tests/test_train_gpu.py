@@ -80,3 +80,23 @@ def test_ddp_wrapped_step_matches_plain_step():
         assert grads[0].numel() > 900_000        # ~3.8 MB of fp32 gradients: the one collective of the path
     finally:
         dist.destroy_process_group()
+
+
+def test_train_step_under_bf16_autocast():
+    """Config 4 asks for a bf16 forward+backward: under autocast the point-wise MLPs run in bf16 while the
+    differentiable library ops take their inputs back to fp32 (ops._amp_fwd) and return fp32 gradients."""
+    import sad_b200  # noqa: F401
+    from sad_b200.config import make_params
+    from sad_b200.modules import SADHotPath
+    torch.manual_seed(0)
+    model = SADHotPath(1).load_params(make_params(0)).to(DEV).train()
+    xyz, feat, size = _batch(B=2, N=2500)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        end = model(xyz, feat, size)
+    _loss({k: (v.float() if torch.is_floating_point(v) else v) for k, v in end.items() if torch.is_tensor(v)}).backward()
+    for name, p in model.named_parameters():
+        assert p.grad is not None and p.grad.dtype == torch.float32 and torch.isfinite(p.grad).all(), name
+    # indices do not depend on the precision of the features
+    model.eval()
+    with torch.no_grad():
+        assert torch.equal(model(xyz, feat, size)["sa1_inds"], end["sa1_inds"])
