@@ -15,20 +15,21 @@ from sad_b200.scenes import make_scenes, make_sizes
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
-    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--steps", type=int, default=48)
+    ap.add_argument("--slots", type=int, default=16)
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     model = SADHotPath(1).load_params(make_params(0)).to(dev).eval()
     rows = []
     for N in (20000, 40000, 80000, 120000, 200000):
-        for B in (1, 8, 32):
+        for B in (1, 8, 32, 64):
             if B * N > 3_300_000:          # keep the sweep within a few GB / seconds
                 continue
             xyz, feat = make_scenes(B, N, "surface")
             size = make_sizes(B, LAYER_CFG["agg"][0])
             d = tuple(torch.from_numpy(t).to(dev) for t in (xyz, feat, size))
-            eng = PipelinedHotPath(model, B, N, slots=4, device=dev)
-            for _ in range(4):
+            eng = PipelinedHotPath(model, B, N, slots=a.slots, device=dev)
+            for _ in range(a.slots):
                 eng.submit_device(*d)
             eng.drain()
             torch.cuda.synchronize()
@@ -62,7 +63,7 @@ def main():
             print(json.dumps(r), flush=True)
             del eng
             torch.cuda.empty_cache()
-    json.dump({"note": "one B200, 4 batches in flight, inputs resident; surface scenes", "rows": rows}, open(a.out, "w"), indent=1)
+    json.dump({"note": f"one B200, {a.slots} batches in flight (throughput FPS policy), inputs resident; surface scenes", "rows": rows}, open(a.out, "w"), indent=1)
 
 
 if __name__ == "__main__":
