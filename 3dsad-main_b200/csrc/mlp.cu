@@ -86,6 +86,8 @@ struct MlpParams {
   // ---- plan (host)
   int transposed;                 // last layer evaluated transposed (S > 1)
   int nslot;                      // tile contexts in flight (2 = ping-pong)
+  int T;                          // tiles per context and phase (super-tile: 2 when every weight piece is pinned and TMEM allows)
+  int region1;                    // TMEM columns of one tile (region_cols = T * region1)
   int na;                         // A-ring stages
   int depth;                      // cp.async groups in flight per gather thread
   int act_chunks;                 // 16 KB chunks per activation buffer (hidden_max / 64)
@@ -122,7 +124,8 @@ struct Misc {
   uint64_t dfull[2][5], actfull[2];
   uint64_t tfull[16];             // tile ordinal k of this CTA published in tiles[k & 15]
   int tiles[16];
-  int boot[2], fetch[2];
+  int boot[4], fetch[2];
+  int fetch2[2][2];               // paired gather: tile ids of the pair two iterations ahead
   uint32_t tmem_base, pad_;
   uint32_t src[2][128];
   alignas(16) float bias[kMaxLayers][kBiasPad];
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
   // carve-up (all offsets multiples of 1024)
   const uint32_t off_a = 0;
   const uint32_t off_act = off_a + (uint32_t)p.na * kChunkBytes;
-  const uint32_t off_pin = off_act + (uint32_t)(p.nslot * p.act_chunks) * kChunkBytes;
+  const uint32_t off_pin = off_act + (uint32_t)(p.nslot * p.T * p.act_chunks) * kChunkBytes;
   const uint32_t off_ring = off_pin + (uint32_t)p.pinned_bytes;
   const uint32_t off_misc = off_ring + (uint32_t)(p.nr * p.ring_slot_bytes);
   Misc* ms = reinterpret_cast<Misc*>(gbase + off_misc);
@@ -370,12 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     // share, so no hand-off between the two warps is needed.
     const int s = warp - kWarpMma;
     if (s < p.nslot) {
-      uint32_t a_pos = 0, a_stage = 0, w_pos = 0, w_slot = 0;      // global ring positions + stage wrap counters
-      auto skip_a = [&](int n) {
-        a_pos += (uint32_t)n;
-        for (int i = 0; i < n; ++i)
-          if (++a_stage == (uint32_t)p.na) a_stage = 0;
-      };
+      uint32_t w_pos = 0, w_slot = 0;      // streamed-weight ring: global position + slot wrap counter
       auto skip_w = [&](int n) {
         w_pos += (uint32_t)n;
         for (int i = 0; i < n; ++i)
@@ -384,8 +382,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
       uint32_t act_cnt = 0;
       bool pinned_ready = false;                                        // pinned pieces are waited for once
       const bool leader = elect_one();
+      const int T = p.T;
       const uint32_t region = tmem_base + (uint32_t)(s * p.region_cols);
-      const uint32_t act_s = base + off_act + (uint32_t)(s * p.act_chunks) * kChunkBytes;
+      const uint32_t act_s = base + off_act + (uint32_t)(s * T * p.act_chunks) * kChunkBytes;
       const int chunks0 = p.kpad[0] / 64;
       // weights of piece (li, i): pinned address or the next ring slot; returns the smem address
       auto weights = [&](int li, int i, bool& streamed, uint32_t& slot) -> uint32_t {
@@ -401,16 +400,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         streamed = true;
         return base + off_ring + slot * (uint32_t)p.ring_slot_bytes;
       };
-      for (int t0 = 0;; t0 += p.nslot) {
+      // A context handles T consecutive tile ordinals per round and phase (a SUPER-TILE): ordinal (round * nslot +
+      // context) * T + t.  T == 2 halves the hand-offs per row (one actfull / dfull round trip per layer for 256
+      // rows); the planner allows it only when every weight piece is pinned (no streamed ring to share).
+      for (int rnd = 0;; ++rnd) {
+        const int t0 = rnd * p.nslot * T;            // first ordinal of the round (context 0)
+        const int k0 = t0 + s * T;                   // this context's first ordinal
         // contexts active in this round (the last round of a CTA may have only context 0).  Context 0 must not ask
-        // for ordinal t0 + 1 before its own layer-0 chunks are consumed: with more K chunks than A-ring stages the
-        // gather warps publish that ordinal only after this warp has freed stages (ns < 0: not known yet).
+        // for context 1's ordinal before its own layer-0 chunks are consumed: with more K chunks than A-ring stages
+        // the gather warps publish that ordinal only after this warp has freed stages (ns < 0: not known yet).
         if (get_tile(t0) < 0) break;
         int ns = -1;
         if (s == 1) {
-          if (get_tile(t0 + 1) < 0) break;
+          if (get_tile(k0) < 0) break;
           ns = 2;
         }
+        int nt = 1;                                  // tiles of this super-tile (the CTA's last one may be short)
+        while (nt < T && get_tile(k0 + nt) >= 0) ++nt;
 #pragma unroll
         for (int li = 0; li < kMaxLayers; ++li) {
           if (li >= nl) break;
@@ -419,14 +425,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
           // streamed pieces of this layer per context (the other context's share is skipped, before or after mine)
           const int lo = p.first_piece[li] > p.n_pinned ? p.first_piece[li] : p.n_pinned;
           const int nstream = p.first_piece[li] + p.pieces[li] > lo ? p.first_piece[li] + p.pieces[li] - lo : 0;
-          if (s == 1) {
-            skip_w(nstream);
-            if (li == 0) skip_a(chunks0);
-          }
+          if (s == 1) skip_w(nstream);
           // the context's TMEM region / activation buffer must have been drained by the epilogue of
           // the previous layer (li > 0) or of the previous tile in this context (li == 0)
           SAD_LOG(2, 100 + li * 10 + s)
-          if (li > 0 || t0 > 0) {
+          if (li > 0 || rnd > 0) {
             mbar_wait(&ms->actfull[s], act_cnt & 1u);
             ++act_cnt;
           }
@@ -435,18 +438,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
           if (!(last && p.transposed)) {
             // D (128 rows x N) = A (rows x K) . W^T ; N = layer width (plain last layer: cpad, split at 256)
             const int ncols = last ? p.cpad_last : p.c[li];
+            for (int t = 0; t < nt; ++t) {
+            const uint32_t region_t = region + (uint32_t)(t * p.region1);
+            const uint32_t act_t = act_s + (uint32_t)(t * p.act_chunks) * kChunkBytes;
             for (int kc = 0; kc < chunks; ++kc) {
               uint32_t a_addr;
               int ksteps = 4;
               uint32_t stage = 0;
               if (li == 0) {
-                stage = a_stage;
+                // A-ring position of chunk kc of ordinal k0 + t (the ring is filled in ordinal order)
+                const uint32_t a_pos = (uint32_t)(k0 + t) * (uint32_t)chunks0 + (uint32_t)kc;
+                stage = a_pos % (uint32_t)p.na;
                 mbar_wait(&ms->afull[a_pos & (kFullBars - 1)], (a_pos / kFullBars) & 1u);
-                skip_a(1);
                 a_addr = base + off_a + stage * kChunkBytes;
                 if (p.has_special && kc == chunks - 1) ksteps = 1;
               } else {
-                a_addr = act_s + (uint32_t)kc * kChunkBytes;
+                a_addr = act_t + (uint32_t)kc * kChunkBytes;
               }
               bool streamed;
               uint32_t slot = 0;
@@ -459,12 +466,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                   const uint32_t idesc = umma_idesc(128, nn);
                   const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr + (uint32_t)n0 * 128u);
                   for (int k = 0; k < ksteps; ++k)     // +2 per 32-byte K step in the (addr >> 4) field
-                    umma_bf16(region + (uint32_t)n0, ad + 2u * k, bd + 2u * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16(region_t + (uint32_t)n0, ad + 2u * k, bd + 2u * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
                 }
                 if (li == 0) umma_commit(&ms->afree[stage]);
                 if (streamed) umma_commit(&ms->wfree[slot]);
-                if (kc == chunks - 1) umma_commit(&ms->dfull[s][0]);
+                if (kc == chunks - 1 && t == nt - 1) umma_commit(&ms->dfull[s][0]);   // once per super-tile
               }
+            }
             }
             __syncwarp();
             SAD_LOG(2, 300 + li * 10 + s)
@@ -472,36 +480,38 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             // transposed last layer: D^T (128 channels x 128 rows) = W_blk . H^T, one commit per block
             const uint32_t idesc = umma_idesc(128, 128);
             for (int blk = 0; blk < p.nblk; ++blk) {
+              for (int t = 0; t < nt; ++t) {
+              const uint32_t region_t = region + (uint32_t)(t * p.region1);
+              const uint32_t act_t = act_s + (uint32_t)(t * p.act_chunks) * kChunkBytes;
               for (int kc = 0; kc < chunks; ++kc) {
                 bool streamed;
                 uint32_t slot = 0;
                 const uint32_t a_addr = weights(li, blk * chunks + kc, streamed, slot);   // W block rows = M
-                const uint32_t b_addr = act_s + (uint32_t)kc * kChunkBytes;               // activations rows = N
+                const uint32_t b_addr = act_t + (uint32_t)kc * kChunkBytes;               // activations rows = N
                 tc_fence_after();
                 SAD_LOG(2, 400 + li * 10 + s)
                 if (leader) {
                   const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma_bf16(region + (uint32_t)(blk * 128), ad + 2u * k, bd + 2u * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16(region_t + (uint32_t)(blk * 128), ad + 2u * k, bd + 2u * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
                   if (streamed) umma_commit(&ms->wfree[slot]);
                   // one barrier per block: never two phases outstanding
-                  if (kc == chunks - 1) umma_commit(&ms->dfull[s][1 + blk]);
+                  if (kc == chunks - 1 && t == nt - 1) umma_commit(&ms->dfull[s][1 + blk]);
                 }
+              }
               }
               __syncwarp();
               SAD_LOG(2, 300 + li * 10 + s)
             }
           }
           if (s == 0) {
-            if (ns < 0) ns = (p.nslot > 1 && get_tile(t0 + 1) >= 0) ? 2 : 1;
-            if (ns == 2) {
-              skip_w(nstream);
-              if (li == 0) skip_a(chunks0);
-            }
+            if (ns < 0) ns = (p.nslot > 1 && get_tile(t0 + T) >= 0) ? 2 : 1;
+            if (ns == 2) skip_w(nstream);
           }
         }
         pinned_ready = true;
+        if (nt < T) break;                           // a short super-tile is the CTA's last
       }
     }
   } else if (warp >= kEpi / 32) {
@@ -586,6 +596,112 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
       const long long t = p.tile_counter ? (long long)gridDim.x + raw : (long long)blockIdx.x + (long long)raw * gridDim.x;
       return (raw >= 0 && t < p.num_tiles) ? (int)t : -1;
     };
+    if (p.T == 2 && chunks0 == 1 && nf0 + nf1 == 0 && p.E <= 4) {
+      // ---------------------------------------------------------------- paired gather (SA1: special chunk only)
+      // Two tiles per iteration, one row of each per thread: the iteration's fixed cost (publication, barrier, ring
+      // bookkeeping, the publication fence) is paid once per 256 rows, which is what lets the gather keep up with
+      // the super-tile consumers.  Same load discipline as the single-tile loop: every value consumed here was
+      // requested one iteration earlier.
+      int ta[2], tb[2], tc[2];                 // tile ids of the current pair, the next, the one after
+      int rawp[2] = {-1, -1};                  // gt == 0: raw fetches of the pair two iterations ahead
+      if (gt == 0) {
+        ms->boot[0] = tile_of_raw(fetch_raw(1));
+        ms->boot[1] = tile_of_raw(fetch_raw(2));
+        ms->boot[2] = tile_of_raw(fetch_raw(3));
+        rawp[0] = fetch_raw(4);
+        rawp[1] = fetch_raw(5);
+      }
+      named_bar_sync(1, kGather);
+      ta[0] = (int)blockIdx.x;
+      ta[1] = ms->boot[0];
+      tb[0] = ms->boot[1];
+      tb[1] = ms->boot[2];
+      uint32_t srcp[2];
+      int idr[2];
+      Special spp[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        srcp[u] = resolve_src(ta[u], issue_idx(ta[u]));
+        load_special(srcp[u], ta[u], spp[u]);
+        idr[u] = issue_idx(tb[u]);
+      }
+      int it2 = 0;
+      for (; ta[0] >= 0; ++it2) {
+        if (gt == 0) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            ms->tiles[(2 * it2 + u) & 15] = ta[u];
+            mbar_arrive(&ms->tfull[(2 * it2 + u) & 15]);
+            ms->fetch2[it2 & 1][u] = tile_of_raw(rawp[u]);       // pair it2 + 2 (fetched one iteration ago)
+          }
+        }
+        SAD_LOG(1, 100)
+        named_bar_sync(1, kGather);
+        SAD_LOG(1, 200)
+        tc[0] = ms->fetch2[it2 & 1][0];
+        tc[1] = ms->fetch2[it2 & 1][1];
+        uint32_t fb[2] = {0, 0};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (ta[u] < 0) continue;                               // warp-uniform: the pair's second tile may not exist
+          const uint32_t stage = g_stage;
+          if (!g_first) mbar_wait(&ms->afree[stage], g_phase);
+          if (++g_stage == (uint32_t)p.na) {
+            g_stage = 0;
+            if (g_first) g_first = false;
+            else g_phase ^= 1u;
+          }
+          const uint32_t dst = base + off_a + stage * kChunkBytes;
+          fb[u] = g_pos++ & (kFullBars - 1);
+          float vals[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vals[i] = 0.f;
+          if (srcp[u] != kNoRow) {
+            if (p.xyz) {
+              float dx = __fsub_rn(spp[u].x, spp[u].qx), dy = __fsub_rn(spp[u].y, spp[u].qy),
+                    dz = __fsub_rn(spp[u].z, spp[u].qz);
+              if (p.normalize) {
+                const float inv = p.radius_t ? __frcp_rn(spp[u].r) : inv_radius;
+                dx *= inv;
+                dy *= inv;
+                dz *= inv;
+              }
+              vals[0] = dx;
+              vals[1] = dy;
+              vals[2] = dz;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) vals[3 + e] = spp[u].e[e];
+          }
+          st_shared_v4(dst + swz(gt, 0), pack_bf16(vals[0], vals[1]), pack_bf16(vals[2], vals[3]),
+                       pack_bf16(vals[4], vals[5]), pack_bf16(vals[6], vals[7]));
+          st_shared_v4(dst + swz(gt, 1), 0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async();                                     // one publication fence for both tiles
+        if (ta[0] >= 0) mbar_arrive(&ms->afull[fb[0]]);
+        if (ta[1] >= 0) mbar_arrive(&ms->afull[fb[1]]);
+        SAD_LOG(1, 600)
+        if (gt == 0) {
+          rawp[0] = fetch_raw(2 * it2 + 6);
+          rawp[1] = fetch_raw(2 * it2 + 7);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          srcp[u] = resolve_src(tb[u], idr[u]);                  // next pair's source rows (their indices have landed)
+          idr[u] = issue_idx(tc[u]);                             // indices two pairs ahead
+          load_special(srcp[u], tb[u], spp[u]);                  // special-chunk inputs one pair ahead
+          ta[u] = tb[u];
+          tb[u] = tc[u];
+        }
+        SAD_LOG(1, 300)
+      }
+      if (gt == 0) {                                             // end markers (see the single-tile loop)
+        for (int e = 0; e <= p.nslot * p.T; ++e) {
+          ms->tiles[(2 * it2 + e) & 15] = -1;
+          mbar_arrive(&ms->tfull[(2 * it2 + e) & 15]);
+        }
+      }
+    } else {
     int tq0 = (int)blockIdx.x, tq1, tq2;
     int raw_f = -1;                            // gt == 0: raw tile fetch of ordinal it + 2
     if (gt == 0) {
@@ -712,14 +828,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
       tq0 = tq1;
       tq1 = tq2;
     }
-    if (gt == 0) {                                        // end marker for the other roles (two ordinals: each epilogue
-      ms->tiles[it & 15] = -1;                            // warpgroup walks every other ordinal)
-      mbar_arrive(&ms->tfull[it & 15]);
-      ms->tiles[(it + 1) & 15] = -1;
-      mbar_arrive(&ms->tfull[(it + 1) & 15]);
+    if (gt == 0) {                                        // end markers for the other roles: a context asks for ordinals
+      for (int e = 0; e <= p.nslot * p.T; ++e) {          // up to one round (nslot * T) past the last tile
+        ms->tiles[(it + e) & 15] = -1;
+        mbar_arrive(&ms->tfull[(it + e) & 15]);
+      }
     }
     cp_async_wait<0>();
     while (pend > 0) retire_oldest();
+    }
   } else {
     // ================================================================== epilogue warpgroups (thread == TMEM lane)
     // warpgroup s drains tile context s only: the two contexts' epilogues run concurrently, and the MMA warp
@@ -729,11 +846,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     if (s < p.nslot) {
       uint32_t d_cnt = 0;            // uses of dfull[s][0]
       uint32_t t_cnt = 0;            // tiles finished in this context (= uses of each dfull[s][1+blk])
-      const uint32_t region = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * p.region_cols);
-      const uint32_t act_s = base + off_act + (uint32_t)(s * p.act_chunks) * kChunkBytes;
-      for (int t0 = s;; t0 += p.nslot) {
-        const long long tile = get_tile(t0);
-        if (tile < 0) break;
+      const int T = p.T;
+      const uint32_t region_s = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * p.region_cols);
+      const uint32_t act_ctx = base + off_act + (uint32_t)(s * T * p.act_chunks) * kChunkBytes;
+      for (int rnd = 0;; ++rnd) {
+        const int k0 = (rnd * p.nslot + s) * T;      // this context's first ordinal of the round (super-tile of T tiles)
+        const int tile_a = get_tile(k0);
+        if (tile_a < 0) break;
+        const int tile_b = T > 1 ? get_tile(k0 + 1) : -1;
+        const int nt = tile_b >= 0 ? 2 : 1;
         for (int li = 0; li < nl; ++li) {
           const bool last = (li == nl - 1);
           SAD_LOG(0, 100 + li * 10 + s)
@@ -744,6 +865,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             tc_fence_after();
             SAD_LOG(0, 200 + li * 10 + s)
             const float* sb = ms->bias[li];
+            for (int t = 0; t < nt; ++t) {
+            const uint32_t region = region_s + (uint32_t)(t * p.region1);
+            const uint32_t act_s = act_ctx + (uint32_t)(t * p.act_chunks) * kChunkBytes;
             for (int c0 = 0; c0 < p.c[li]; c0 += 64) {
               uint32_t v0[32], v1[32];
               tmem_ld32_issue(region + (uint32_t)c0, v0);
@@ -764,17 +888,20 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                              pack_bf16_relu(__uint_as_float(v[o + 6]) + bb.z, __uint_as_float(v[o + 7]) + bb.w));
               }
             }
+            }
             SAD_LOG(0, 500 + li * 10 + s)
             fence_proxy_async();
           } else if (p.transposed) {
             // ---- last layer, transposed: thread == output channel, columns == rows; pool over S
             const uint32_t npt = 128u >> p.log2S;
-            const uint32_t pt0 = (uint32_t)tile * npt;
-            const uint32_t b0 = p.log2P >= 0 ? (pt0 >> p.log2P) : pt0 / (uint32_t)p.P, j0 = pt0 - b0 * (uint32_t)p.P;
             for (int blk = 0; blk < p.nblk; ++blk) {
               mbar_wait(&ms->dfull[s][1 + blk], t_cnt & 1u);
               tc_fence_after();
               SAD_LOG(0, 200 + li * 10 + s)
+              for (int t = 0; t < nt; ++t) {
+              const uint32_t region = region_s + (uint32_t)(t * p.region1);
+              const uint32_t pt0 = (uint32_t)(t == 0 ? tile_a : tile_b) * npt;
+              const uint32_t b0 = p.log2P >= 0 ? (pt0 >> p.log2P) : pt0 / (uint32_t)p.P, j0 = pt0 - b0 * (uint32_t)p.P;
               const int ch = blk * 128 + et;
               const bool ch_ok = ch < c_last;
               const float bias = ms->bias[li][ch_ok ? ch : 0];
@@ -805,14 +932,17 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
 #undef SAD_EMIT
                 }
               }
+              }
             }
             ++t_cnt;
           } else {
-            // ---- last layer, plain orientation (S == 1): thread == row; both outputs store coalesced
+            // ---- last layer, plain orientation (S == 1): thread == row; both outputs store coalesced (T == 1 here)
             mbar_wait(&ms->dfull[s][0], d_cnt & 1u);
             ++d_cnt;
             tc_fence_after();
             SAD_LOG(0, 200 + li * 10 + s)
+            const uint32_t region = region_s;
+            const long long tile = tile_a;
             const long long R = tile * 128 + et;
             const bool ok = R < p.total_rows;
             const uint32_t pt = ok ? (uint32_t)R : 0u;
@@ -859,6 +989,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
           mbar_arrive(&ms->actfull[s]);
           SAD_LOG(0, 300 + li * 10 + s)
         }
+        if (nt < T) break;                           // a short super-tile is the CTA's last
       }
     }
   }
@@ -997,9 +1128,9 @@ static bool plan_launch(MlpParams& p, int hidden_max, size_t& smem_out) {
   p.nblk = p.transposed ? (c_last + 127) / 128 : 0;
   p.cpad_last = p.transposed ? 0 : (c_last + 31) / 32 * 32;
   p.act_chunks = hidden_max / 64;
-  p.region_cols = p.transposed ? (hidden_max > 128 * p.nblk ? hidden_max : 128 * p.nblk)
-                               : (hidden_max > p.cpad_last ? hidden_max : p.cpad_last);
-  if (p.region_cols > 512) return false;
+  p.region1 = p.transposed ? (hidden_max > 128 * p.nblk ? hidden_max : 128 * p.nblk)
+                           : (hidden_max > p.cpad_last ? hidden_max : p.cpad_last);
+  if (p.region1 > 512) return false;
   int np = 0, max_piece = 0;
   long long total_w = 0;
   for (int li = 0; li < nl; ++li) {
@@ -1028,11 +1159,21 @@ static bool plan_launch(MlpParams& p, int hidden_max, size_t& smem_out) {
   // two contexts = two consumers per ring: the skipped share + 1 + the ring depth must stay inside one period of
   // the position-indexed full barriers (see kFullBars)
   const bool two_ok = p.kpad[0] / 64 + 1 + kMaxA <= kFullBars && max_pieces + 1 + kMaxRing <= kFullBars;
-  for (int nslot = (2 * p.region_cols <= 512 && p.num_tiles > 1 && max_slot >= 2 && two_ok) ? 2 : 1; nslot >= 1; --nslot) {
-    const long long act = (long long)nslot * p.act_chunks * kChunkBytes;
+  // super-tiles (T = 2 tiles per context and phase): pooled stages with enough tiles per CTA, two contexts of two
+  // tiles in TMEM, two tiles of layer-1 chunks in the A ring, and EVERY weight piece pinned (SAD_MLP_T: tuning / tests)
+  const char* e_T = getenv("SAD_MLP_T");
+  const bool try_T2 = p.transposed && 4 * p.region1 <= 512 && max_slot >= 2 && two_ok &&
+                      (e_T ? atoi(e_T) == 2 : p.num_tiles >= 1024);
+  for (int T = try_T2 ? 2 : 1; T >= 1; --T)
+  for (int nslot = (2 * T * p.region1 <= 512 && p.num_tiles > 1 && max_slot >= 2 && two_ok) ? 2 : 1; nslot >= 1; --nslot) {
+    if (T == 2 && nslot != 2) continue;
+    p.T = T;
+    p.region_cols = T * p.region1;
+    const long long act = (long long)nslot * T * p.act_chunks * kChunkBytes;
     for (int na = (max_na < 2 ? 2 : (max_na > 4 ? 4 : max_na)); na >= 2; --na) {
       const long long rest = avail - act - (long long)na * kChunkBytes;
       if (rest < 0) continue;
+      if (T == 2 && !(total_w <= rest && np <= kMaxPin && T * (p.kpad[0] / 64) <= na)) continue;
       int n_pinned = 0, nr = 0;
       long long pinned = 0;
       if (total_w <= rest && np <= kMaxPin) {
@@ -1148,8 +1289,8 @@ extern "C" int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_c
     configured_dev = dev;
   }
   if (getenv("SAD_DEBUG_MLP"))
-    fprintf(stderr, "[sad] fused_mlp: rows=%lld tiles=%d S=%d K0=%d c=[%d,%d,%d] nslot=%d na=%d depth=%d pinned=%d/%d "
-            "(%d B) ring=%dx%d tmem=%d smem=%zu\n", p.total_rows, p.num_tiles, S, p.kpad[0], p.c[0], p.c[1], p.c[2], p.nslot,
+    fprintf(stderr, "[sad] fused_mlp: rows=%lld tiles=%d S=%d K0=%d c=[%d,%d,%d] T=%d nslot=%d na=%d depth=%d pinned=%d/%d "
+            "(%d B) ring=%dx%d tmem=%d smem=%zu\n", p.total_rows, p.num_tiles, S, p.kpad[0], p.c[0], p.c[1], p.c[2], p.T, p.nslot,
             p.na, p.depth, p.n_pinned, p.n_pieces, p.pinned_bytes, p.nr, p.ring_slot_bytes, p.tmem_cols, smem);
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   fused_mlp_kernel<<<grid, kThreads, smem, stream>>>(p);

@@ -78,6 +78,26 @@ def test_fused_sa_stage(B, N, P, S, Cf, hidden, radius, adaptive):
     close(comp, want, 2e-2)
 
 
+@pytest.mark.parametrize("B,N,P,S", [(2, 3000, 64, 64), (1, 3000, 37, 64), (3, 4000, 333, 64), (2, 3000, 500, 16)])
+def test_fused_sa_stage_super_tiles(B, N, P, S, monkeypatch):
+    """SAD_MLP_T=2 forces two tiles per context and phase (what SA1 runs at full size) on small shapes: CTAs with one
+    tile, odd tile counts, a partial last tile."""
+    from sad_b200 import mlp as M
+    monkeypatch.setenv("SAD_MLP_T", "2")
+    rng = np.random.default_rng(N + P + S)
+    xyz = (rng.random((B, N, 3), dtype=np.float32) * 3).astype(np.float32)
+    feat = rng.standard_normal((B, 1, N)).astype(np.float32)
+    inds = C.furthest_point_sample(xyz, P)
+    new_xyz = np.stack([xyz[b][inds[b]] for b in range(B)])
+    idx = C.ball_query(0.5, S, xyz, new_xyz)
+    layers = make_layers(rng, [4, 64, 64, 128])
+    x = O.query_and_group(xyz, new_xyz, feat, idx, np.float32(0.5), True, True)
+    want = O.shared_mlp(x, layers, pool=True)
+    got = M.sa_group_mlp(cu(xyz), cu(new_xyz), cu(feat), cu(idx), 0.5, M.prepare_layers(tlayers(layers)))
+    close(got, want, 2e-2)
+
+
+
 @pytest.mark.parametrize("B,n,C_,chans,last_relu", [
     (2, 1024, 256, [256, 256, 259], False),     # voting stack, linear last layer, c_last = 259
     (1, 200, 64, [64, 128], True),
