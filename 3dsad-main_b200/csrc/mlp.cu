@@ -19,6 +19,8 @@
 //                       contexts (A, B) ping-pong: while the epilogue warps drain layer l of tile
 //                       A the tensor core runs layer l of tile B, so neither side waits for the
 //                       other's latency chain.
+//   (SA1-type stages -- all weights pinned, TMEM room for 2 x 2 tiles -- run SUPER-TILES: a context handles two
+//   tile ordinals per phase and the gather a pair of tiles per iteration)
 //   warps 0-7  EPILOGUE two warpgroups, one per tile context (they drain concurrently); thread == TMEM lane.  Hidden layers: tcgen05.ld -> +bias (shared memory)
 //                       -> ReLU fused into cvt.rn.relu.bf16x2 -> swizzled shared memory = the next
 //                       layer's operand.  Last layer, pooled stages (S > 1): evaluated TRANSPOSED
