@@ -440,6 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
           if (!(last && p.transposed)) {
             // D (128 rows x N) = A (rows x K) . W^T ; N = layer width (plain last layer: cpad, split at 256)
             const int ncols = last ? p.cpad_last : p.c[li];
+            const uint32_t idesc_l = umma_idesc(128, ncols <= 256 ? ncols : 256);
             for (int t = 0; t < nt; ++t) {
             const uint32_t region_t = region + (uint32_t)(t * p.region1);
             const uint32_t act_t = act_s + (uint32_t)(t * p.act_chunks) * kChunkBytes;
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
               if (li == 0) {
                 // A-ring position of chunk kc of ordinal k0 + t (the ring is filled in ordinal order)
                 const uint32_t a_pos = (uint32_t)(k0 + t) * (uint32_t)chunks0 + (uint32_t)kc;
-                stage = a_pos % (uint32_t)p.na;
+                stage = (p.na == 4) ? (a_pos & 3u) : (a_pos % (uint32_t)p.na);
                 mbar_wait(&ms->afull[a_pos & (kFullBars - 1)], (a_pos / kFullBars) & 1u);
                 a_addr = base + off_a + stage * kChunkBytes;
                 if (p.has_special && kc == chunks - 1) ksteps = 1;
@@ -463,12 +464,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
               tc_fence_after();
               SAD_LOG(2, 400 + li * 10 + s)
               if (leader) {
+                if (ncols <= 256) {                    // every hidden layer: one N pass, K steps unrolled
+                  const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
+                  umma_bf16(region_t, ad, bd, idesc_l, kc > 0 ? 1u : 0u);
+                  if (ksteps == 4) {
+                    umma_bf16(region_t, ad + 2u, bd + 2u, idesc_l, 1u);     // +2 per 32-byte K step in the (addr >> 4) field
+                    umma_bf16(region_t, ad + 4u, bd + 4u, idesc_l, 1u);
+                    umma_bf16(region_t, ad + 6u, bd + 6u, idesc_l, 1u);
+                  }
+                } else {
                 for (int n0 = 0; n0 < ncols; n0 += 256) {
                   const int nn = min(256, ncols - n0);
                   const uint32_t idesc = umma_idesc(128, nn);
                   const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr + (uint32_t)n0 * 128u);
-                  for (int k = 0; k < ksteps; ++k)     // +2 per 32-byte K step in the (addr >> 4) field
+                  for (int k = 0; k < ksteps; ++k)
                     umma_bf16(region_t + (uint32_t)n0, ad + 2u * k, bd + 2u * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                }
                 }
                 if (li == 0) umma_commit(&ms->afree[stage]);
                 if (streamed) umma_commit(&ms->wfree[slot]);
