@@ -389,15 +389,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
       const uint32_t act_s = base + off_act + (uint32_t)(s * T * p.act_chunks) * kChunkBytes;
       const int chunks0 = p.kpad[0] / 64;
       // weights of piece (li, i): pinned address or the next ring slot; returns the smem address
+      // tcgen05.fence::after_thread_sync is needed only after this thread actually waited on a barrier; measured
+      // (CTA-0 timeline) it costs a few hundred cycles on the issuing warp, so it is not issued per chunk
+      bool waited = false;
       auto weights = [&](int li, int i, bool& streamed, uint32_t& slot) -> uint32_t {
         const int pc = p.first_piece[li] + i;
         if (pc < p.n_pinned) {
-          if (!pinned_ready) mbar_wait(&ms->wpin[pc], 0);
+          if (!pinned_ready) {
+            mbar_wait(&ms->wpin[pc], 0);
+            waited = true;
+          }
           streamed = false;
           return base + off_pin + (uint32_t)p.pin_off[li] + (uint32_t)i * (uint32_t)p.piece_bytes[li];
         }
         slot = w_slot;
         mbar_wait(&ms->wfull[w_pos & (kFullBars - 1)], (w_pos / kFullBars) & 1u);
+        waited = true;
         skip_w(1);
         streamed = true;
         return base + off_ring + slot * (uint32_t)p.ring_slot_bytes;
@@ -453,6 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 const uint32_t a_pos = (uint32_t)(k0 + t) * (uint32_t)chunks0 + (uint32_t)kc;
                 stage = (p.na == 4) ? (a_pos & 3u) : (a_pos % (uint32_t)p.na);
                 mbar_wait(&ms->afull[a_pos & (kFullBars - 1)], (a_pos / kFullBars) & 1u);
+                waited = true;
                 a_addr = base + off_a + stage * kChunkBytes;
                 if (p.has_special && kc == chunks - 1) ksteps = 1;
               } else {
@@ -461,7 +469,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
               bool streamed;
               uint32_t slot = 0;
               const uint32_t b_addr = weights(li, kc, streamed, slot);
-              tc_fence_after();
+              if (waited) {
+                tc_fence_after();
+                waited = false;
+              }
               SAD_LOG(2, 400 + li * 10 + s)
               if (leader) {
                 if (ncols <= 256) {                    // every hidden layer: one N pass, K steps unrolled
@@ -481,9 +492,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                     umma_bf16(region_t + (uint32_t)n0, ad + 2u * k, bd + 2u * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
                 }
                 }
+                SAD_LOG(2, 500 + li * 10 + s)
                 if (li == 0) umma_commit(&ms->afree[stage]);
                 if (streamed) umma_commit(&ms->wfree[slot]);
                 if (kc == chunks - 1 && t == nt - 1) umma_commit(&ms->dfull[s][0]);   // once per super-tile
+                SAD_LOG(2, 600 + li * 10 + s)
               }
             }
             }
@@ -501,7 +514,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 uint32_t slot = 0;
                 const uint32_t a_addr = weights(li, blk * chunks + kc, streamed, slot);   // W block rows = M
                 const uint32_t b_addr = act_t + (uint32_t)kc * kChunkBytes;               // activations rows = N
-                tc_fence_after();
+                if (waited) {
+                  tc_fence_after();
+                  waited = false;
+                }
                 SAD_LOG(2, 400 + li * 10 + s)
                 if (leader) {
                   const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
