@@ -258,7 +258,7 @@ def build_roofline(model, xyz, feat, size, reps=3):
                 "launch_ms": round(top["ms_per_step"] / launches, 4),
                 "note": "FPS is a serial-latency kernel (SURVEY H3: npoint dependent picks, each a block/cluster-wide "
                         "argmax): its HBM fraction is reported as the contract asks, the meaningful unit is picks/s; "
-                        "see `kernels` for the HBM- and tensor-bound ops and `roofline_tensor` for the fused MLP"
+                        "see `kernels` for the HBM- and tensor-bound ops and `roofline.also` for the fused MLP"
                 if top["kernel"].startswith("furthest") else ""}
     mlp = next((k for k in kernels if k["kernel"] == "shared_mlp"), None)
     if mlp is not None and roof["kernel"] != "shared_mlp":
