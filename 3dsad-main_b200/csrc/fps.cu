@@ -103,9 +103,10 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict
         if (m > bv0) { bv0 = m; bp0 = p; }
       }
     }
-    float bv = bv0;
-    int bp = bp0;
-    if (P > 1 && (bv1 > bv0 || (bv1 == bv0 && bp1 < bp0))) { bv = bv1; bp = bp1; }
+    // (selects, not branches: the warp must arrive converged at the redux below, or it takes the slow collective path)
+    const bool second = (P > 1) & ((bv1 > bv0) | ((bv1 == bv0) & (bp1 < bp0)));
+    const float bv = second ? bv1 : bv0;
+    const int bp = second ? bp1 : bp0;
 
     const uint32_t vb = __float_as_uint(bv);
     const uint32_t bk = (uint32_t)((g * P + bp) * 32 + lane);
@@ -128,10 +129,11 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict
 #pragma unroll
     for (int r = 0; r < RPL; ++r) {
       const int s = lane + 32 * r;
-      if (s < NSLOT) {
-        const uint32_t x = __float_as_uint(s_rec[buf][s].x);
-        if (slot == 0xFFFFFFFFu || x > v) { v = x; slot = (uint32_t)s; }
-      }
+      const bool in = s < NSLOT;
+      const uint32_t x = __float_as_uint(s_rec[buf][in ? s : 0].x);
+      const bool take = in & ((slot == 0xFFFFFFFFu) | (x > v));
+      v = take ? x : v;
+      slot = take ? (uint32_t)s : slot;
     }
     const uint32_t gmax = __reduce_max_sync(FULL, v);
     const uint32_t gslot = __reduce_min_sync(FULL, v == gmax ? slot : 0xFFFFFFFFu);

@@ -217,15 +217,15 @@ fps_cull_kernel(int N, int npoint, const float* __restrict__ xyz, const uint8_t*
 #pragma unroll
     for (int r = 0; r < RPL; ++r) {
       const int sl = lane + 32 * r;
-      if (sl < NSLOT) {
-        const uint32_t x = __float_as_uint(s_rec[buf][sl].x);
-        const uint32_t id = s_ridx[buf][sl];
-        if (x > v || (x == v && id < vi)) {
-          v = x;
-          vi = id;
-          vs = (uint32_t)sl;
-        }
-      }
+      const bool in = sl < NSLOT;
+      const int slc = in ? sl : 0;
+      const uint32_t x = __float_as_uint(s_rec[buf][slc].x);
+      const uint32_t id = s_ridx[buf][slc];
+      // branch-free: a divergent compare chain would leave the warp unconverged at the redux below (slow path)
+      const bool take = in & ((x > v) | ((x == v) & (id < vi)));
+      v = take ? x : v;
+      vi = take ? id : vi;
+      vs = take ? (uint32_t)sl : vs;
     }
     const uint32_t gmax = __reduce_max_sync(FULL, v);
     const uint32_t gidx = __reduce_min_sync(FULL, v == gmax ? vi : kInf);
@@ -351,11 +351,12 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
         const bool valid = (r * 32 + lane) < nslots;
         const uint32_t x = valid ? __float_as_uint(bmax[r]) : 0u;
         const uint32_t id = valid ? bidx[r] : kInf;
-        if (x > v || (x == v && id < vi)) {
-          v = x;
-          vi = id;
-          vr = r;
-        }
+        // branch-free on purpose: a divergent compare chain leaves the warp unconverged at the redux below, which
+        // then takes its slow collective path (measured: ~900 instead of ~150 cycles for this block)
+        const bool take = (x > v) | ((x == v) & (id < vi));
+        v = take ? x : v;
+        vi = take ? id : vi;
+        vr = take ? r : vr;
       }
       const uint32_t wmax = __reduce_max_sync(FULL, v);
       const uint32_t widx = __reduce_min_sync(FULL, v == wmax ? vi : kInf);
@@ -375,7 +376,11 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
 
     // ---- warp 0 reduces the NW records (max value, ties -> lowest original index) and publishes the pick: one
     // warp's two redux instead of every warp's (the redux unit is shared; NW redundant reductions queue on it)
+#if defined(SAD_FPS_ABLATE) && SAD_FPS_ABLATE >= 4
+    if (false) {
+#else
     if (warp == 0) {
+#endif
       const uint32_t x = lane < NW ? s_wval[lane] : 0u;
       const uint32_t id = lane < NW ? __float_as_uint(s_wrec[lane].w) : kInf;
       const uint32_t gmax = __reduce_max_sync(FULL, x);
@@ -404,11 +409,13 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       bool aff = false;
+#if !defined(SAD_FPS_ABLATE) || SAD_FPS_ABLATE < 3
       if (r * 32 + lane < nslots) {
         const float ccx = fminf(fmaxf(qx, blx[r]), bhx[r]), ccy = fminf(fmaxf(qy, bly[r]), bhy[r]),
                     ccz = fminf(fmaxf(qz, blz[r]), bhz[r]);
         aff = sqdist(ccx, ccy, ccz, qx, qy, qz) < bmax[r];
       }
+#endif
       uint32_t mask = __ballot_sync(FULL, aff);
       if (mask) changed = true;
 #ifdef SAD_FPS_PROFILE
@@ -416,6 +423,9 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
 #endif
 #ifdef SAD_FPS_ABLATE
       mask = 0u;                                       // tools only: no bucket updates at all (wrong picks): the fixed cost per pick
+#if SAD_FPS_ABLATE >= 2
+      changed = false;                                 // ... and no record rewrite
+#endif
 #endif
       while (mask) {                                   // FC1_DEPTH buckets in flight per step (independent L2 round trips)
 #ifdef SAD_FPS_PROFILE
