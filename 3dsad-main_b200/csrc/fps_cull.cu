@@ -266,18 +266,32 @@ constexpr int FC1_MDS_MAX = 46000;        // min-distances in shared memory up t
 // pick costs (ablation build -DSAD_FPS_ABLATE, no bucket updates): ~1.5 k cycles FIXED -- 32 warps x ~100
 // instructions of box tests and bookkeeping issue-bound on the four schedulers, plus the record -> barrier -> one-warp
 // reduce -> barrier chain -- and ~1.5 k cycles for the L2 round trip of the surviving buckets' points.
-template <int R, int NW, bool MDS>
-__global__ void __launch_bounds__(NW * 32, 1)
-fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __restrict__ ws, size_t stride,
-                 int32_t* __restrict__ out) {
-  extern __shared__ __align__(16) float4 s_best[];      // [slot * NW + warp] best point of the bucket {x,y,z,bits(idx)}
-  // then: int32 s_out[FC1_OUT]; then (MDS) float s_md[N]
-  __shared__ __align__(16) float4 s_wrec[NW];           // per warp: best point {x,y,z,bits(idx)}
-  __shared__ uint32_t s_wval[NW];                       // per warp: its min-dist bits
-  __shared__ __align__(16) float4 s_pick;               // the pick of this round {x,y,z,bits(idx)}, written by warp 0
+// SC: scenes per CTA.  SC == 2 puts two independent scenes (NW warps each, one named barrier each) on one SM, so one
+// scene's L2 round trip hides behind the other's barrier / reduce / record chain; it needs the per-thread state under
+// 64 registers (fewer updates in flight) and keeps the min-distances in the workspace scratch (MDS == false).
+template <int R, int NW, bool MDS, int SC>
+__global__ void __launch_bounds__(SC * NW * 32, 1)
+fps_cull1_kernel(int B, int N, int npoint, const float* __restrict__ xyz, uint8_t* __restrict__ ws, size_t stride,
+                 int32_t* __restrict__ out, size_t scene_smem) {
+  extern __shared__ __align__(16) uint8_t s_dyn1[];
+  __shared__ __align__(16) float4 s_wrec_[SC][NW];      // per warp: best point {x,y,z,bits(idx)}
+  __shared__ uint32_t s_wval_[SC][NW];                  // per warp: its min-dist bits
+  __shared__ __align__(16) float4 s_pick_[SC];          // the pick of this round {x,y,z,bits(idx)}, written by warp 0
+  static_assert(!(MDS && SC > 1), "two scenes per CTA keep the min-distances in global memory");
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x;
+  const int half = SC > 1 ? (int)threadIdx.x / (NW * 32) : 0;
+  const int tid = SC > 1 ? (int)threadIdx.x % (NW * 32) : (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x * SC + half;
+  if (b >= B) return;                                   // odd batch: the second half of the last CTA has no scene
+  auto cta_sync = [&]() {
+    if (SC > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(NW * 32) : "memory");
+    else __syncthreads();
+  };
+  float4* s_best = reinterpret_cast<float4*>(s_dyn1 + (size_t)half * scene_smem);   // [slot * NW + warp] best point of the bucket
+  // then: int32 s_out[FC1_OUT]; then (MDS) float s_md[N]
+  float4* s_wrec = s_wrec_[half];
+  uint32_t* s_wval = s_wval_[half];
+  float4& s_pick = s_pick_[half];
   uint8_t* base = ws + (size_t)b * stride;
   const float4* sorted = reinterpret_cast<const float4*>(base + kGridHeaderBytes + kGridCellBytes);
   int32_t* o = out + (size_t)b * npoint;
@@ -371,7 +385,7 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
       }
     }
     SAD_MARK1(0)
-    __syncthreads();
+    cta_sync();
     SAD_MARK1(1)
 
     // ---- warp 0 reduces the NW records (max value, ties -> lowest original index) and publishes the pick: one
@@ -390,7 +404,7 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
         s_out[j & (FC1_OUT - 1)] = (int32_t)gidx;
       }
     }
-    __syncthreads();
+    cta_sync();
     if (((j + 1) & (FC1_OUT - 1)) == 0 || j == npoint - 1) {     // flush the buffered picks (coalesced, rare)
       const int j0 = j & ~(FC1_OUT - 1);
       for (int i = tid; j0 + i <= j; i += NW * 32) o[j0 + i] = s_out[i];
@@ -431,12 +445,13 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
 #ifdef SAD_FPS_PROFILE
         ++nround;
 #endif
-        int bsel[FC1_DEPTH], kk[FC1_DEPTH];
-        bool okk[FC1_DEPTH], use[FC1_DEPTH];
-        float4 pt[FC1_DEPTH];
-        float md[FC1_DEPTH];
+        constexpr int DEPTH = SC > 1 ? 2 : FC1_DEPTH;
+        int bsel[DEPTH], kk[DEPTH];
+        bool okk[DEPTH], use[DEPTH];
+        float4 pt[DEPTH];
+        float md[DEPTH];
 #pragma unroll
-        for (int u = 0; u < FC1_DEPTH; ++u) {
+        for (int u = 0; u < DEPTH; ++u) {
           use[u] = mask != 0u;
           bsel[u] = use[u] ? __ffs(mask) - 1 : 0;
           if (use[u]) mask &= mask - 1;
@@ -450,7 +465,7 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
           }
         }
 #pragma unroll
-        for (int u = 0; u < FC1_DEPTH; ++u) {
+        for (int u = 0; u < DEPTH; ++u) {
           if (!use[u]) break;                            // warp-uniform
           const float nd = fminf(md[u], sqdist(pt[u].x, pt[u].y, pt[u].z, qx, qy, qz));
           if (okk[u] && nd < md[u]) mind[kk[u]] = nd;
@@ -476,21 +491,23 @@ fps_cull1_kernel(int N, int npoint, const float* __restrict__ xyz, uint8_t* __re
 #undef SAD_MARK1
 }
 
-template <int R, int NW, bool MDS>
+template <int R, int NW, bool MDS, int SC = 1>
 int launch_cull1(int B, int N, int npoint, const float* xyz, void* ws, int32_t* idx, cudaStream_t stream) {
-  auto kern = fps_cull1_kernel<R, NW, MDS>;
+  auto kern = fps_cull1_kernel<R, NW, MDS, SC>;
   const int nb = (N + 31) / 32;
-  const size_t smem = (size_t)sad_ceil_div(nb, NW) * NW * sizeof(float4) + FC1_OUT * sizeof(int32_t) +
-                      (MDS ? (size_t)N * sizeof(float) : 0);
+  const size_t scene_smem = ((size_t)sad_ceil_div(nb, NW) * NW * sizeof(float4) + FC1_OUT * sizeof(int32_t) +
+                             (MDS ? (size_t)N * sizeof(float) : 0) + 15) / 16 * 16;
+  const size_t smem = SC * scene_smem;
   static thread_local int configured_dev = -1;
   int dev = 0;
   SAD_CUDA_OK(cudaGetDevice(&dev));
   if (configured_dev != dev) {
     SAD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     MDS ? 227 * 1024 - 2048 : R * 32 * NW * 16 + FC1_OUT * 4));
+                                     MDS ? 227 * 1024 - 2048 : SC * (R * 32 * NW * 16 + FC1_OUT * 4 + 16)));
     configured_dev = dev;
   }
-  kern<<<B, NW * 32, smem, stream>>>(N, npoint, xyz, static_cast<uint8_t*>(ws), sad::grid_stride(N), idx);
+  kern<<<sad_ceil_div(B, SC), SC * NW * 32, smem, stream>>>(B, N, npoint, xyz, static_cast<uint8_t*>(ws), sad::grid_stride(N), idx,
+                                                       scene_smem);
   SAD_LAUNCH_CHECK("fps_cull1_kernel");
   return SAD_OK;
 }
@@ -591,6 +608,13 @@ extern "C" int sad_furthest_point_sample_grid_policy_fwd(int B, int N, int npoin
   if (N <= FC1_MDS_MAX) {                 // min-distances in shared memory
     // 16 warps per scene: a pick's fixed cost is issue-bound (every warp runs ~180 bookkeeping + box-test
     // instructions per pick), so 16 warps x 3 register sets beat 32 x 2 (2.83 vs 2.99 ms at 40k points)
+    static const int sc_env = getenv("SAD_FPS1_SC") ? atoi(getenv("SAD_FPS1_SC")) : 1;    // tools: scenes per CTA
+    if (sc_env == 2 && B >= 2) {
+      const int pl = sad_ceil_div(sad_ceil_div(nbk, 16), 32);
+      if (pl <= 1) return launch_cull1<1, 16, false, 2>(B, N, npoint, xyz, grid_ws, idx, stream);
+      if (pl <= 2) return launch_cull1<2, 16, false, 2>(B, N, npoint, xyz, grid_ws, idx, stream);
+      return launch_cull1<3, 16, false, 2>(B, N, npoint, xyz, grid_ws, idx, stream);
+    }
     static const int nw_env = getenv("SAD_FPS1_NW") ? atoi(getenv("SAD_FPS1_NW")) : 16;   // tools: warps per scene
     if (nw_env != 32) {
       const int pl = sad_ceil_div(sad_ceil_div(nbk, 16), 32);
