@@ -35,6 +35,7 @@ SIGNATURES = {
     "sad_ball_query_grid_fwd": [_c_int, _c_int, _c_int, _c_float, _vp, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_fps_grid_max_points": [],
     "sad_fps_grid_force_cluster": [_c_int],
+    "sad_mlp_set_tiles_per_cta": [_c_int],
     "sad_furthest_point_sample_grid_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_furthest_point_sample_grid_policy_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp],
     "sad_mlp_weight_image_bytes": [_c_int, _c_int, _c_int],
@@ -44,7 +45,7 @@ SIGNATURES = {
     "sad_three_interpolate_cl_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_cf_to_cl_bf16": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
 }
-_RESTYPES = {"sad_last_error_string": ctypes.c_char_p, "sad_fps_force_cluster_size": None, "sad_fps_grid_force_cluster": None,
+_RESTYPES = {"sad_last_error_string": ctypes.c_char_p, "sad_fps_force_cluster_size": None, "sad_fps_grid_force_cluster": None, "sad_mlp_set_tiles_per_cta": None,
              "sad_launch_count": ctypes.c_ulonglong, "sad_scene_grid_workspace_bytes": ctypes.c_longlong, "sad_mlp_weight_image_bytes": ctypes.c_longlong}
 
 _lib = None

@@ -38,12 +38,14 @@ class PipelinedHotPath:
     """
 
     def __init__(self, model, batch: int, n_points: int, feat_dim: int = 1, slots: int = 3,
-                 device: Optional[torch.device] = None, warmup: int = 2, fps_policy: str = "throughput"):
+                 device: Optional[torch.device] = None, warmup: int = 2, fps_policy: str = "throughput",
+                 mlp_tiles_per_cta: int = 6):
         """`fps_policy`: "throughput" (default) captures the one-SM-per-scene FPS kernel -- longer per batch, but
         about half the SM-time, which is what bounds a pipeline with several batches in flight; "latency" captures the
         cluster kernel (shortest time per batch; right for 1-2 slots)."""
         self.model = model
         self.fps_policy = fps_policy
+        self.mlp_tiles_per_cta = mlp_tiles_per_cta      # narrower fused-MLP grids for the small stages (less SM-time)
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         self.batch, self.n_points, self.feat_dim = batch, n_points, feat_dim
         self.n_clusters = model.agg.sa.npoint
@@ -55,10 +57,12 @@ class PipelinedHotPath:
         from . import modules as _modules
         saved_policy = _modules.FPS_POLICY[0]
         _modules.FPS_POLICY[0] = fps_policy
+        lib.sad_mlp_set_tiles_per_cta(int(mlp_tiles_per_cta))
         try:
             self._capture(model, batch, n_points, feat_dim, slots, dev, warmup, lib)
         finally:
             _modules.FPS_POLICY[0] = saved_policy
+            lib.sad_mlp_set_tiles_per_cta(1)
         self.launches_per_batch = self._slots[0].launches
 
     def _capture(self, model, batch, n_points, feat_dim, slots, dev, warmup, lib):

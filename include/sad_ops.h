@@ -162,6 +162,11 @@ SAD_API int sad_mlp_pack_weights(const float* W, int cout, int cin, const int32_
  *   tile_counter   one device int32 the CALLER ZEROES before every call (stream-ordered): tiles are then
  *                  handed to the persistent CTAs dynamically; NULL = static round-robin
  * bf16 operands, fp32 accumulate/bias/ReLU/max (tolerance 2e-2 vs the fp32 oracle). */
+/* Scheduling hint for the calling thread's sad_shared_mlp_fwd launches (never changes results): at least `tiles`
+ * 128-row tiles per CTA, i.e. a narrower grid for the small stages.  1 (default) = one CTA per SM whenever there are
+ * that many tiles: shortest time for one launch.  A pipelined caller with other streams to fill the SMs wants ~6
+ * (fewer per-CTA prologues, less SM-time; engine.PipelinedHotPath sets it while it captures its graphs). */
+SAD_API void sad_mlp_set_tiles_per_cta(int tiles);
 SAD_API int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_cl, int C0,
                                const void* feat2_cl, int C1in, const float* xyz, const float* new_xyz,
                                const int32_t* idx, float radius, const float* radius_t,
