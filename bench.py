@@ -457,7 +457,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--slots", type=int, default=24, help="batches in flight in the pipelined executor")
+    ap.add_argument("--slots", type=int, default=32, help="batches in flight in the pipelined executor")
     ap.add_argument("--fps-policy", default="throughput", choices=["throughput", "latency"],
                     help="scheduling of the 40k-point FPS (same indices either way)")
     ap.add_argument("--sets", type=int, default=32, help="rotating input sets (32 x 5.1 MB > L2)")
