@@ -8,7 +8,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.environ.get("SAD_B200_LIB") or os.environ.get("SAD_B200_LIB", os.path.join(_HERE, "lib", "libsad_b200.so"))   # env override: tools only (profiling builds)
+SO_PATH = os.environ.get("SAD_B200_LIB") or os.path.join(_HERE, "lib", "libsad_b200.so")   # env override: tools only (profiling builds)
 
 _c_int = ctypes.c_int
 _c_float = ctypes.c_float
@@ -42,11 +42,17 @@ SIGNATURES = {
     "sad_mlp_pack_weights": [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp],
     "sad_shared_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _c_float, _vp,
                            _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp],
+    "sad_sa_mlp_query": [_c_int] * 8,
+    "sad_sa_mlp_image_bytes": [_c_int],
+    "sad_sa_mlp_pack": [_c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp],
+    "sad_sa_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_float, _vp, _c_int, _vp, _c_int, _vp, _vp, _vp,
+                       _c_int, _vp, _vp, _vp, _c_int, _vp],
     "sad_three_interpolate_cl_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_cf_to_cl_bf16": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
 }
 _RESTYPES = {"sad_last_error_string": ctypes.c_char_p, "sad_fps_force_cluster_size": None, "sad_fps_grid_force_cluster": None, "sad_mlp_set_tiles_per_cta": None,
-             "sad_launch_count": ctypes.c_ulonglong, "sad_scene_grid_workspace_bytes": ctypes.c_longlong, "sad_mlp_weight_image_bytes": ctypes.c_longlong}
+             "sad_launch_count": ctypes.c_ulonglong, "sad_scene_grid_workspace_bytes": ctypes.c_longlong, "sad_mlp_weight_image_bytes": ctypes.c_longlong,
+             "sad_sa_mlp_image_bytes": ctypes.c_longlong}
 
 _lib = None
 _lock = threading.Lock()

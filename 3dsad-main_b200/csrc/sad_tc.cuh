@@ -1,0 +1,186 @@
+// tcgen05 / TMEM / TMA / cluster PTX helpers shared by the fused-MLP kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "sad_common.cuh"
+
+#ifdef __CUDACC__
+namespace sad {
+
+// ------------------------------------------------------------------------------------------ misc
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float ldg_nc_f32(const float* p) {      // `volatile`: stays where it is written (prefetch)
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ldg_nc_s32(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int4 ldg_nc_s32x4(const int32_t* p) {
+  int4 v;
+  asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// bf16x2 of (max(lo,0), max(hi,0)): the ReLU rides on the conversion
+__device__ __forceinline__ uint32_t bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// max of N accumulator words as a ternary tree
+template <int N>
+__device__ __forceinline__ float vmax_tree(const uint32_t* v) {
+  if constexpr (N == 1) {
+    return __uint_as_float(v[0]);
+  } else if constexpr (N == 2) {
+    return fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+  } else {
+    constexpr int A = N / 3 + (N % 3 > 0), B = N / 3 + (N % 3 > 1);
+    return fmax3(vmax_tree<A>(v), vmax_tree<B>(v + A), vmax_tree<N - A - B>(v + A + B));
+  }
+}
+// byte offset of (row, 16-byte unit) inside a 128-row x 128-byte K-major SWIZZLE_128B chunk
+__device__ __forceinline__ uint32_t swz128(int row, int unit) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((unit ^ (row & 7)) << 4));
+}
+
+// --------------------------------------------------------------------------- mbarrier, cluster scope
+// wait with acquire.cluster: the barrier also receives arrivals from the peer CTA of the cluster
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa(smem_u32(bar), rank)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------- TMA
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+// gather4: four rows (row coordinates r0..r3 of a 2-D tensor map whose box is {box_cols, 1}) starting at column
+// `col` land as four consecutive 128-byte rows at dst (SWIZZLE_128B applied by the TMA unit).
+__device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const void* tmap, int col, int r0, int r1, int r2, int r3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst_smem), "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------------- tcgen05
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// commit: the barrier (same offset in every CTA of the pair when CG == 2) gets one arrival when every MMA issued so far
+// by this thread has completed
+template <int CG>
+__device__ __forceinline__ void umma_commit_to(uint64_t* bar) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, both operands K-major
+template <int CG>
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major SWIZZLE_128B descriptor (sm_100 format): start >> 4, LBO unused (1), SBO = 1024 B between 8-row groups,
+// version 1 (bit 46), layout type 2 (bits 61-63).  One 32-byte K step further = +2 in the start field.
+__device__ __forceinline__ uint64_t udesc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// K-major, no swizzle ("interleave"), one 16-wide bf16 K step: canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte
+// units; here a core matrix (8 rows x 16 B) is 128 contiguous bytes, the second K unit follows at +128 B (LBO) and
+// 8-row groups are 256 B apart (SBO).
+__device__ __forceinline__ uint64_t udesc_k16(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (8ull << 16) | (16ull << 32) | (1ull << 46);
+}
+// byte offset of (row, 16-byte K unit u in {0,1}) in that layout
+__device__ __forceinline__ uint32_t k16_off(int row, int u) {
+  return (uint32_t)((row >> 3) * 256 + u * 128 + (row & 7) * 16);
+}
+// instruction descriptor kind::f16: D f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at 17, M >> 4 at 24
+__host__ __device__ constexpr uint32_t uidesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_fence() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+}  // namespace sad
+#endif

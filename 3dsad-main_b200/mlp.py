@@ -28,6 +28,46 @@ _VP = ctypes.c_void_p
 # Hand 128-row tiles to the persistent CTAs through an atomic counter (robust when other streams hold SMs).
 DYNAMIC_TILES = True
 
+# Shape-specialised SA kernel (csrc/mlp_sa.cu): True = use it whenever an instance matches the stage, "single" = prefer
+# the instances that run without a CTA pair, False = always the general kernel (tests compare the two).
+FAST_SA = [True]
+# Scheduling hint for the fused-MLP launches issued from Python (never changes results): minimum 128-row tiles per
+# CTA.  engine.PipelinedHotPath raises it while it captures its graphs (narrower grids for the small stages).
+TILES_PER_CTA = [1]
+
+
+class _SchedWords:
+    """Device words the persistent kernels' tile schedulers count in.  A kernel leaves its words zero when it
+    finishes, so one zero-initialised pool serves every launch: eager launches share one slot per stream (they are
+    stream-ordered), every launch recorded into a CUDA graph gets a slot of its own (graphs of different pipeline
+    slots replay concurrently).  No per-launch memset."""
+
+    STRIDE = 64          # int32 words between slots (256 B: separate L2 atomic units)
+
+    def __init__(self):
+        self.pools = {}
+
+    def take(self, dev: torch.device) -> torch.Tensor:
+        key = (dev.type, dev.index)
+        st = self.pools.get(key)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if st is None or st["next"] + self.STRIDE > st["buf"].numel():
+            st = self.pools[key] = {"buf": torch.zeros(self.STRIDE * 4096, dtype=torch.int32, device=dev), "next": 0,
+                                    "by_stream": {}}
+        if capturing:
+            off = st["next"]
+            st["next"] += self.STRIDE
+        else:
+            sid = torch.cuda.current_stream(dev).cuda_stream
+            off = st["by_stream"].get(sid)
+            if off is None:
+                off = st["by_stream"][sid] = st["next"]
+                st["next"] += self.STRIDE
+        return st["buf"][off: off + 2]
+
+
+_SCHED = _SchedWords()
+
 
 def _ptr(t: Optional[torch.Tensor]):
     return _VP(t.data_ptr()) if t is not None else _VP(0)
@@ -140,6 +180,57 @@ class PreparedMLP:
         return self._packed[key]
 
 
+def _fast_instance(mlp: "PreparedMLP", layout: Layout, S: int, P: int) -> int:
+    """Instance id of the shape-specialised kernel for this stage, or -1 (general kernel)."""
+    if not FAST_SA[0] or len(mlp) != 3 or layout.c1 or layout.xyz_cols is None or P & (P - 1) or P < 1:
+        return -1
+    h1, h2, c3 = mlp.c_out
+    return int(_lib.load().sad_sa_mlp_query(layout.c0, h1, h2, c3, S, len(layout.extra_cols), 1,
+                                            1 if FAST_SA[0] == "single" else 0))
+
+
+def _packed_fast(mlp: "PreparedMLP", inst: int, layout: Layout):
+    key = ("fast", inst, layout.key())
+    if key not in mlp._packed:
+        lib = _lib.load()
+        dev = mlp.layers[0][0].device
+        (W1, b1), (W2, b2), (W3, b3) = [(np.ascontiguousarray(W.detach().cpu().numpy(), dtype=np.float32),
+                                         np.ascontiguousarray(b.detach().cpu().numpy(), dtype=np.float32))
+                                        for (W, b) in mlp.layers]
+        c3 = W3.shape[0]
+        perm_feat = np.ascontiguousarray(layout.perm()[: layout.c0], dtype=np.int32) if layout.c0 else np.zeros(1, np.int32)
+        perm_sp = np.full(7, -1, dtype=np.int32)
+        perm_sp[:3] = layout.xyz_cols
+        perm_sp[3: 3 + len(layout.extra_cols)] = layout.extra_cols
+        nbytes = int(lib.sad_sa_mlp_image_bytes(inst))
+        img = np.zeros(nbytes, dtype=np.uint8)
+        _lib.check(lib.sad_sa_mlp_pack(inst, _VP(W1.ctypes.data), int(W1.shape[1]), _VP(perm_feat.ctypes.data),
+                                       _VP(perm_sp.ctypes.data), _VP(b1.ctypes.data), _VP(W2.ctypes.data),
+                                       _VP(W3.ctypes.data), int(c3), _VP(img.ctypes.data)), "sa_mlp_pack")
+        b3p = np.zeros(256, dtype=np.float32)
+        b3p[:c3] = b3
+        mlp._packed[key] = (torch.from_numpy(img).to(dev), torch.from_numpy(b2).to(dev), torch.from_numpy(b3p).to(dev))
+    return mlp._packed[key]
+
+
+def fused_sa_fast(mlp: "PreparedMLP", inst: int, layout: Layout, B, N, P, feat_cl, xyz, new_xyz, idx, radius, radius_t,
+                  normalize_xyz, extra, want_cf=True, want_cl=True):
+    """Launcher of sad_sa_mlp_fwd -> (out_cf (B,C3,P) f32 | None, out_cl (B,P,C3) bf16 | None)."""
+    img, b2, b3p = _packed_fast(mlp, inst, layout)
+    dev = img.device
+    c3 = mlp.c_out[-1]
+    out_cf = torch.empty((B, c3, P), dtype=torch.float32, device=dev) if want_cf else None
+    out_cl = torch.empty((B, P, c3), dtype=torch.bfloat16, device=dev) if want_cl else None
+    sched = _SCHED.take(dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().sad_sa_mlp_fwd(
+            inst, B, N, P, _ptr(feat_cl), _ptr(xyz), _ptr(new_xyz), _ptr(idx), float(radius), _ptr(radius_t),
+            int(bool(normalize_xyz)), _ptr(extra), len(layout.extra_cols), _ptr(img), _ptr(b2), _ptr(b3p), c3,
+            _ptr(out_cl), _ptr(out_cf), _ptr(sched), int(TILES_PER_CTA[0]), _VP(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "sa_mlp")
+    return out_cf, out_cl
+
+
 def prepare_layers(layers) -> PreparedMLP:
     return PreparedMLP(layers)
 
@@ -208,6 +299,11 @@ def sa_group_mlp(xyz, new_xyz, features, idx, radius, mlp: PreparedMLP, use_xyz=
     elif c_feat:
         extra = features.contiguous() if c_feat == 1 else features.transpose(1, 2).contiguous()
     radius_t = radius if torch.is_tensor(radius) else None
+    inst = _fast_instance(mlp, layout, S, P)
+    if inst >= 0:
+        out_cf, out_cl = fused_sa_fast(mlp, inst, layout, B, N, P, feat_cl, xyz, new_xyz, idx,
+                                       0.0 if radius_t is not None else float(radius), radius_t, normalize_xyz, extra)
+        return _attach(out_cf, out_cl)
     out_cf, out_cl = fused_mlp(mlp, layout, B, N, P, S, feat_cl=feat_cl, xyz=xyz if layout.xyz_cols else None,
                                new_xyz=new_xyz, idx=idx, radius=0.0 if radius_t is not None else float(radius),
                                radius_t=radius_t, normalize_xyz=normalize_xyz, extra=extra)

@@ -1,0 +1,97 @@
+"""Shape-specialised fused SA kernel (csrc/mlp_sa.cu) vs the oracle and vs the general kernel.
+
+Every instance the library compiles is exercised: SA1 (one CTA, 4 tile contexts, special K step only), SA2 on one
+CTA and on a CTA pair (TMA gather4, cta_group::2), SA3/SA4 and the vote aggregation (zero-padded outputs,
+per-cluster radius) on CTA pairs; small cases (partial tiles, an odd number of tiles for the pair kernels) and cases
+deep enough that every CTA recycles its tile buffers and contexts several times."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sad_oracle as O
+from oracle import c_port as C
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def close(got, want, tol, floor_frac=0.05, rel=None):
+    got = got.detach().float().cpu().numpy()
+    scale = max(1e-6, float(np.abs(want).max()))
+    err = float(np.abs(got - want).max())
+    assert err <= tol * scale, f"max abs err {err:.4g} vs scale {scale:.4g} (tol {tol})"
+    if rel is not None:      # element-wise relative error above a magnitude floor
+        m = np.abs(want) > floor_frac * scale
+        r = float((np.abs(got - want)[m] / np.abs(want)[m]).max()) if m.any() else 0.0
+        assert r <= rel, f"max element-wise relative err {r:.4g} above {floor_frac} of scale (tol {rel})"
+
+
+def make_layers(rng, chans, bias_std=0.1):
+    return [((rng.standard_normal((co, ci)) / np.sqrt(ci)).astype(np.float32),
+             (rng.standard_normal(co) * bias_std).astype(np.float32)) for ci, co in zip(chans[:-1], chans[1:])]
+
+
+CASES = [
+    # name, mode, B, N, P, S, Cf, hidden, radius, adaptive
+    ("sa1-small", True, 1, 3000, 64, 64, 1, [64, 64, 128], 0.5, False),
+    ("sa1-odd-tiles", True, 1, 3000, 1, 64, 1, [64, 64, 128], 0.5, False),          # half a tile
+    ("sa1-deep", True, 2, 20000, 2048, 64, 1, [64, 64, 128], 0.3, False),           # ~28 tiles per CTA
+    ("sa2-single-small", "single", 2, 2048, 128, 32, 128, [128, 128, 256], 0.6, False),
+    ("sa2-single-deep", "single", 4, 2048, 1024, 32, 128, [128, 128, 256], 0.6, False),
+    ("sa2-pair-small", True, 2, 2048, 128, 32, 128, [128, 128, 256], 0.6, False),
+    ("sa2-pair-odd", True, 1, 2048, 4, 32, 128, [128, 128, 256], 0.6, False),       # one tile: the pair's second CTA idles
+    ("sa2-pair-deep", True, 4, 2048, 1024, 32, 128, [128, 128, 256], 0.6, False),
+    ("sa3-pair-small", True, 1, 1024, 64, 16, 256, [128, 128, 256], 0.9, False),
+    ("sa3-pair-deep", True, 8, 1024, 512, 16, 256, [128, 128, 256], 0.9, False),
+    ("agg-pair", True, 2, 1024, 128, 16, 256, [128, 128, 128], 0.3, True),          # 128 outputs zero-padded, per-cluster radius
+    ("agg-pair-deep", True, 8, 1024, 256, 16, 256, [128, 128, 128], 0.3, True),
+]
+
+
+@pytest.mark.parametrize("name,mode,B,N,P,S,Cf,hidden,radius,adaptive", CASES, ids=[c[0] for c in CASES])
+def test_fast_sa_stage(name, mode, B, N, P, S, Cf, hidden, radius, adaptive):
+    from sad_b200 import mlp as M
+    rng = np.random.default_rng(N + P + S)
+    xyz = (rng.random((B, N, 3), dtype=np.float32) * 3).astype(np.float32)
+    feat = rng.standard_normal((B, Cf, N)).astype(np.float32)
+    inds = C.furthest_point_sample(xyz, P)
+    new_xyz = np.stack([xyz[b][inds[b]] for b in range(B)])
+    if adaptive:
+        rt = (rng.random((B, P), dtype=np.float32) * 0.8 + 0.2).astype(np.float32)
+        idx = C.ball_query_adaptive(rt, S, xyz, new_xyz)
+        rad_o, rad_g = rt, cu(rt)
+    else:
+        idx = C.ball_query(radius, S, xyz, new_xyz)
+        rad_o, rad_g = np.float32(radius), radius
+    layers = make_layers(rng, [Cf + 3] + hidden)
+    x = O.query_and_group(xyz, new_xyz, feat, idx, rad_o, True, True)
+    want = O.shared_mlp(x, layers, pool=True)
+    want_bf = O.shared_mlp(x, layers, pool=True, emulate_bf16=True)
+    mlp = M.prepare_layers([(cu(W), cu(b)) for W, b in layers])
+    args = (cu(xyz), cu(new_xyz), cu(feat), cu(idx), rad_g, mlp)
+    saved = M.FAST_SA[0]
+    try:
+        M.FAST_SA[0] = mode
+        layout = M.sa_layout(Cf, True)
+        inst = M._fast_instance(mlp, layout, S, P)
+        assert inst >= 0, "no specialised instance picked this shape"
+        got = M.sa_group_mlp(*args, use_xyz=True, normalize_xyz=True)
+        torch.cuda.synchronize()
+        got2 = M.sa_group_mlp(*args, use_xyz=True, normalize_xyz=True)      # scheduler words were re-armed by launch 1
+        torch.cuda.synchronize()
+        M.FAST_SA[0] = False
+        ref = M.sa_group_mlp(*args, use_xyz=True, normalize_xyz=True)       # general kernel
+    finally:
+        M.FAST_SA[0] = saved
+    assert tuple(got.shape) == (B, hidden[-1], P) and got.dtype == torch.float32
+    close(got, want, 2e-2)
+    close(got, want_bf, 8e-3, rel=4e-2)
+    assert torch.equal(got, got2), "second launch on the same scheduler words differs"
+    close(got, ref.detach().float().cpu().numpy(), 8e-3)
+    twin = got._sad_cl
+    assert tuple(twin.shape) == (B, P, hidden[-1]) and twin.dtype == torch.bfloat16
+    close(twin.float().transpose(1, 2), want_bf, 1.2e-2)

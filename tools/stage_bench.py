@@ -1,0 +1,96 @@
+"""Fused-MLP stages alone at the benchmark's shapes (B = 8 scenes): general kernel vs the shape-specialised one.
+
+    python tools/stage_bench.py [--tpc 1]      -> one line per stage: us, TFLOP/s, fraction of the measured bf16 peak
+"""
+import argparse, json, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import sad_b200  # noqa
+from sad_b200 import mlp as M
+
+
+def t(fn, it=20, reps=10):
+    """Device time of one call: `reps` calls captured into a CUDA graph (no host overhead between the launches),
+    median / best over `it` replays."""
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            fn()
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        st.synchronize()
+        ts = []
+        for _ in range(it):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st); g.replay(); b.record(st); st.synchronize()
+            ts.append(a.elapsed_time(b) / reps)
+    ts.sort()
+    return 1e3 * ts[len(ts) // 2], 1e3 * ts[0]
+
+
+def layers(ch):
+    g = torch.Generator().manual_seed(0)
+    return M.prepare_layers([((torch.randn(co, ci, generator=g) / ci ** 0.5).cuda(), 0.1 * torch.randn(co, generator=g).cuda())
+                             for ci, co in zip(ch[:-1], ch[1:])])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tpc", type=int, default=1)
+    ap.add_argument("--batch", type=int, default=8)
+    args = ap.parse_args()
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+    except Exception:
+        peak = 1400.0
+    dev, B = "cuda", args.batch
+    M.TILES_PER_CTA[0] = args.tpc
+    from sad_b200 import _lib
+    _lib.load().sad_mlp_set_tiles_per_cta(args.tpc)
+    rows = []
+    stages = [("sa1", 40000, 2048, 64, 1, [64, 64, 128]), ("sa2", 2048, 1024, 32, 128, [128, 128, 256]),
+              ("sa3", 1024, 512, 16, 256, [128, 128, 256]), ("sa4", 512, 256, 16, 256, [128, 128, 256]),
+              ("agg", 1024, 256, 16, 256, [128, 128, 128])]
+    for (name, N, P, S, C, hid) in stages:
+        xyz = torch.rand(B, N, 3, device=dev)
+        new_xyz = torch.rand(B, P, 3, device=dev)
+        idx = torch.randint(0, N, (B, P, S), device=dev, dtype=torch.int32)
+        feat = torch.randn(B, C, N, device=dev)
+        if C >= 64:
+            feat._sad_cl = M.to_cl_bf16(feat)
+        m = layers([C + 3] + hid)
+        flops = 2.0 * B * P * S * sum(a * b for a, b in zip([C + 3] + hid[:-1], hid))
+        for mode in (False, "single", True):
+            M.FAST_SA[0] = mode
+            inst = M._fast_instance(m, M.sa_layout(C, True), S, P) if mode else -1
+            if mode and inst < 0:
+                continue
+            if mode == "single" and inst not in (3,):
+                continue
+            med, best = t(lambda: M.sa_group_mlp(xyz, new_xyz, feat, idx, 0.3, m))
+            rows.append({"stage": name, "kernel": {False: "general", "single": "fast-1cta", True: f"fast(inst {inst})"}[mode],
+                         "us": round(med, 1), "best_us": round(best, 1), "GFLOP": round(flops / 1e9, 2),
+                         "TFLOPs": round(flops / med / 1e6, 1), "frac_of_peak": round(flops / med / 1e6 / peak, 3)})
+            print(rows[-1], flush=True)
+    M.FAST_SA[0] = True
+    # the S == 1 stages (general kernel only, for the total)
+    for (name, n, ch, last_relu) in [("fp1", 512, [512, 256, 256], True), ("fp2", 1024, [512, 256, 256], True),
+                                      ("vote", 1024, [256, 256, 256, 259], False)]:
+        x = torch.randn(B, ch[0], n, device=dev)
+        x._sad_cl = M.to_cl_bf16(x)
+        m = layers(ch)
+        flops = 2.0 * B * n * sum(a * b for a, b in zip(ch[:-1], ch[1:]))
+        med, best = t(lambda: M.pointwise_mlp(x, m, last_relu=last_relu))
+        rows.append({"stage": name, "kernel": "general", "us": round(med, 1), "best_us": round(best, 1), "GFLOP": round(flops / 1e9, 2),
+                     "TFLOPs": round(flops / med / 1e6, 1), "frac_of_peak": round(flops / med / 1e6 / peak, 3)})
+        print(rows[-1], flush=True)
+    print(json.dumps({"tpc": args.tpc, "batch": B, "peak_tflops": peak, "rows": rows}))
+
+
+if __name__ == "__main__":
+    main()
