@@ -44,8 +44,9 @@ SIGNATURES = {
                            _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp],
     "sad_sa_mlp_query": [_c_int] * 8,
     "sad_sa_mlp_image_bytes": [_c_int],
-    "sad_sa_mlp_pack": [_c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_int, _vp],
-    "sad_sa_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_float, _vp, _c_int, _vp, _c_int, _vp, _vp, _vp,
+    "sad_sa_mlp_pack": [_c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp],
+    "sad_pack_xyzw": [_c_int, _c_int, _vp, _vp, _vp, _vp],
+    "sad_sa_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_float, _vp, _c_int, _vp, _c_int, _vp, _vp,
                        _c_int, _vp, _vp, _vp, _c_int, _vp],
     "sad_three_interpolate_cl_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_cf_to_cl_bf16": [_c_int, _c_int, _c_int, _vp, _vp, _vp],

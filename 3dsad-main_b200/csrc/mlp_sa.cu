@@ -11,17 +11,22 @@
 //     weight matrix from each CTA, and the last layer -- evaluated transposed, D^T = W3 . H^T, so that the max-pool is
 //     an in-thread reduction -- gives each CTA 128 of the 256 output channels for BOTH tiles' rows.
 //   * The layer-1 operand of a tile is built in a TILE BUFFER that later holds the tile's hidden activations (the
-//     gathered rows are dead once layer 1 has been issued): channel-last bf16 feature rows land by TMA gather4
-//     (one instruction = 4 rows x 128 B, swizzled by the TMA unit, completion on an mbarrier -- no thread ever touches
-//     them), the relative xyz / scalar features / constant-1 (bias) column form one 16-wide K step written by the
-//     gather warps in the no-swizzle K-major layout (4 KB per tile instead of a 16 KB chunk).
-//   * G = 2 or 4 tile contexts in TMEM; the MMA warp walks them in lockstep (L1 of every context, then L2, then L3),
-//     so the epilogue of context c runs under the MMAs of the others.
+//     gathered rows are dead once layer 1 has completed): channel-last bf16 feature rows by 16-byte cp.async straight
+//     into the tcgen05 K-major SWIZZLE_128B layout (a warp copies its own 32 rows, 8 lanes per row, source rows
+//     exchanged by shuffle: no shared-memory index table, no block barrier), one tile of loads in flight behind the
+//     tile being published; the relative xyz / scalar features / constant 1 form one 16-wide K step in the no-swizzle
+//     K-major layout (4 KB per tile instead of a 16 KB chunk).  NB >= G buffers: the gather runs up to NB tiles ahead.
+//     (TMA gather4 was tried first: ~100 cycles of issue per 4-row instruction, 5x slower than the cp.async path.)
+//   * Biases of layers 1 and 2 ride on the constant-1 column (K index 15) of the tile's special K step: layer 1 has it
+//     as part of its operand, layer 2 issues one extra K = 16 step of the same block against a weight piece that is
+//     zero except for that column, so the hidden epilogues are TMEM -> ReLU/bf16 -> smem only.
+//   * G = 2 or 4 tile contexts in TMEM, walked in two half-groups in anti-phase (L1 A, L1 B, L2 A, L2 B, L3 A, L3 B):
+//     the epilogue of one half runs under the MMAs of the other; per step the MMA warp waits for every barrier of the
+//     half, fences once and issues everything.
 //   * 16 epilogue warps (4 per scheduler): one warpgroup per context, or two splitting its columns.
 //   * cluster rank 1 has no MMAs to issue: its MMA warp RELAYS the local "operand ready" barriers to the leader with
 //     one remote arrive each, in exactly the order the leader consumes them; tcgen05.commit multicasts the
 //     "accumulator ready" / "buffer free" barriers to both CTAs.
-#include <cuda.h>
 #include <string.h>
 
 #include "sad_tc.cuh"
@@ -30,14 +35,15 @@ namespace {
 
 using namespace sad;
 
-constexpr int kWarpGather = 16;          // warps 16-19: special chunk (relative xyz, scalar features)
-constexpr int kWarpMma = 20;             // leader: MMA issue; rank 1: relay
-constexpr int kWarpProd = 21;            // tile scheduler + TMA gather
-constexpr int kThreads = 22 * 32;
+constexpr int kWarpGather = 16;          // warps 16-19: layer-1 operand (feature rows, special K step)
+constexpr int kWarpMma = 20;             // warps 20, 21: one per half of the contexts; leader: MMA issue, rank 1: relay
+constexpr int kWarpProd = 22;            // tile scheduler + pinned weights
+constexpr int kThreads = 23 * 32;        // (registers are allocated for 24 warps either way)
+constexpr int kGatherThreads = 128;
 constexpr int kChunk = 16384;            // 128 rows x 128 B
 constexpr int kSpBytes = 4096;           // 128 rows x 32 B (one 16-wide bf16 K step)
-constexpr int kRing = 16;                // tile-id ring
-constexpr int kAhead = 4;                // tile ids published ahead of the load cursor
+constexpr int kRing = 32;                // tile-id ring
+constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 
 template <int CG_, int NF_, int H_, int C3_, int S_>
 struct Cfg {
@@ -48,15 +54,17 @@ struct Cfg {
   static constexpr int NBLK = C3 / (128 * CG);           // MMA groups of the last layer (M = 128 * CG channels each)
   static constexpr int CW = (H > C3 ? H : C3) <= 128 ? 128 : 256;   // TMEM columns of one context
   static constexpr int G = 512 / CW;                     // contexts
+  static constexpr int HG = G / 2;                       // contexts per half-group
   static constexpr int NP = 4 / G;                       // epilogue warpgroups per context
   static constexpr int HP = H / NP;                      // hidden columns per warpgroup
   static constexpr int NQP = NQ / NP;                    // last-layer blocks per warpgroup
   static constexpr int BUFCH = NF > HC ? NF : HC;        // 16 KB chunks of a tile buffer
-  static constexpr int W1F = NF * WROWS * 128, W1SP = WROWS * 32, W2B = HC * WROWS * 128, W3B = NBLK * HC * kChunk;
-  static constexpr int OFF_W1SP = W1F, OFF_W2 = W1F + W1SP, OFF_W3 = OFF_W2 + W2B;
-  static constexpr int WBYTES = OFF_W3 + W3B;            // weight image of one CTA
+  // weight image of one CTA: W1 feature pieces | W1 special K step | W2 pieces | W2 bias K step | W3 pieces
+  static constexpr int W1F = NF * WROWS * 128, WK16 = WROWS * 32, W2B = HC * WROWS * 128, W3B = NBLK * HC * kChunk;
+  static constexpr int OFF_W1SP = W1F, OFF_W2 = OFF_W1SP + WK16, OFF_W2BIAS = OFF_W2 + W2B, OFF_W3 = OFF_W2BIAS + WK16;
+  static constexpr int WBYTES = OFF_W3 + W3B;
   static constexpr int BUFBYTES = BUFCH * kChunk;
-  static constexpr int kMisc = 4096;
+  static constexpr int kMisc = 2048;
   static constexpr int kBudget = 227 * 1024 - 1024 - kMisc - WBYTES;
   static constexpr int NB_fit = kBudget / (BUFBYTES + kSpBytes);
   static constexpr int NB = NB_fit > 8 ? 8 : NB_fit;     // tile buffers
@@ -70,13 +78,15 @@ struct Cfg {
   static_assert(WBYTES % 1024 == 0, "weight image alignment");
 };
 
-struct alignas(64) SaParams {
-  CUtensorMap tmap;               // (B*N rows) x C0 bf16, box {64, 1}, SWIZZLE_128B (NF > 0)
+struct SaParams {
   int N, P, log2P, log2S;
   long long total_rows;
   uint32_t total_points;
   int num_tiles, num_units;       // unit = tile (CG = 1) or tile pair (CG = 2)
+  const __nv_bfloat16* feat_cl;   // (B*N rows) x C0 bf16 channel-last (NF > 0)
   const float* xyz;               // (B,N,3)
+  const float4* xyzw;             // (B,N) {x, y, z, scalar feature}: one 16-byte load per gathered row instead of 3 + E
+                                  // scattered 4-byte loads (optional; needs E <= 1)
   const float* new_xyz;           // (B,P,3)
   const int32_t* idx;             // (B,P,S)
   const float* radius_t;          // (B,P) or null
@@ -85,31 +95,31 @@ struct alignas(64) SaParams {
   const float* extra;             // (B,N,E) fp32 scalar features, E <= 4
   int E;
   const uint8_t* w_img;           // CG images of WBYTES
-  const float* bias2;             // (H)
   const float* bias3;             // (C3), zero padded
   int c3_real;                    // channels actually stored
   __nv_bfloat16* out_cl;          // (B,P,c3_real) bf16 or null
   float* out_cf;                  // (B,c3_real,P) f32 or null
   int* sched;                     // [0] next unit (zero between launches: the kernel resets it), [1] clusters done
+  int static_sched;               // few units per cluster: unit(ordinal) = cluster + ordinal * clusters, no scheduler
+  int claim;                      // dynamic scheduling: units claimed per atomic
 };
 
-template <class C>
 struct Misc {
   uint64_t wfull, p_wfull;
   uint64_t tfull[kRing];
-  uint64_t bfull[8], sfull[8], bfree[8], p_ready[8];
+  uint64_t full[8], bfree[8], p_ready[8];
   uint64_t dfull[4], actfull[4], p_actfull[4];
   int units[kRing];
-  uint32_t tmem_base, pad_;
-  alignas(16) float bias2[128];
+  uint32_t tmem_base;
+  int gprog;                      // ordinal the gather warps have reached (monotonic: the scheduler's flow control)
   alignas(16) float bias3[256];
 };
 
 #ifdef SAD_MLP_PROFILE
 // tools only: (event, clock) log of one warp per role of CTA 0 (role: 0 epilogue warp 0, 1 gather warp, 2 MMA warp,
-// 3 producer warp, 4 epilogue warp 4)
-__device__ long long g_sa_log[5][2 * 4096];
-__device__ int g_sa_logn[5];
+// 3 scheduler warp, 4 epilogue warp 4, 5 second MMA warp)
+__device__ long long g_sa_log[6][2 * 4096];
+__device__ int g_sa_logn[6];
 #define SALOG(role, ev)                                                         \
   if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && sa_logn < 4095) {           \
     g_sa_log[role][2 * sa_logn] = (ev);                                         \
@@ -120,8 +130,28 @@ __device__ int g_sa_logn[5];
 #define SALOG(role, ev)
 #endif
 
+#ifdef SAD_MLP_PROFILE
+__device__ unsigned long long* g_sa_dbg;     // host-mapped words that survive a trap (tools only)
+#endif
 // mbarrier wait that traps instead of hanging the GPU when a protocol bug leaves it unsatisfied (~2 s)
 __device__ __noinline__ void bar_timeout(uint32_t bar_addr, uint32_t parity) {
+#ifdef SAD_MLP_PROFILE
+  if (g_sa_dbg) {
+    volatile unsigned long long* d = g_sa_dbg;
+    const unsigned slot = atomicAdd((unsigned*)(g_sa_dbg + 63), 1u);
+    if (slot < 15) {
+      d[4 * slot + 0] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+      d[4 * slot + 1] = ((unsigned long long)bar_addr << 32) | parity;
+      d[4 * slot + 2] = clock64();
+      d[4 * slot + 3] = 0xDEADBEEF;
+    }
+    __threadfence_system();
+    // give the other stuck waiters a moment to report too
+    const long long t = clock64();
+    while (clock64() - t < 200000000LL) {
+    }
+  }
+#endif
 #ifdef SAD_MLP_DEBUG
   printf("[sad] sa_mlp: barrier timeout (block %d thread %d bar +%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
          bar_addr & 0xFFFFu, parity);
@@ -129,13 +159,16 @@ __device__ __noinline__ void bar_timeout(uint32_t bar_addr, uint32_t parity) {
   __trap();
 }
 template <int CG>
+__device__ __forceinline__ bool bar_try(uint64_t* bar, uint32_t parity) {
+  return (CG == 2) ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity);
+}
+template <int CG>
 __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   long long t0 = 0;
   for (;;) {
-    const bool ok = (CG == 2) ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity);
-    if (ok) return;
-    if ((++spins & 0xFFFu) == 0) {
+    if ((CG == 2) ? mbar_try_wait_cluster_sleep(bar, parity) : mbar_try_wait_sleep(bar, parity)) return;
+    if ((++spins & 0xFFu) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000LL) bar_timeout(smem_u32(bar), parity);
@@ -143,20 +176,29 @@ __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 template <class C>
 __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_constant__ SaParams p) {
 #ifdef SAD_MLP_PROFILE
   const long long sa_t_entry = clock64();
 #endif
-  constexpr int CG = C::CG, NF = C::NF, H = C::H, G = C::G, NB = C::NB, NP = C::NP;
+  constexpr int CG = C::CG, NF = C::NF, H = C::H, G = C::G, HG = C::HG, NB = C::NB, NP = C::NP;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   constexpr uint32_t off_buf = C::WBYTES;
   constexpr uint32_t off_sp = off_buf + NB * C::BUFBYTES;
   constexpr uint32_t off_misc = off_sp + NB * kSpBytes;
-  Misc<C>* ms = reinterpret_cast<Misc<C>*>(gbase + off_misc);
-  static_assert(sizeof(Misc<C>) <= C::kMisc, "misc area");
+  Misc* ms = reinterpret_cast<Misc*>(gbase + off_misc);
+  static_assert(sizeof(Misc) <= C::kMisc, "misc area");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef SAD_MLP_PROFILE
@@ -171,28 +213,24 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
     mbar_init(&ms->p_wfull, 1);
     for (int i = 0; i < kRing; ++i) mbar_init(&ms->tfull[i], 1);
     for (int i = 0; i < 8; ++i) {
-      mbar_init(&ms->bfull[i], 1);
-      mbar_init(&ms->sfull[i], 4);          // one arrival per gather warp
+      mbar_init(&ms->full[i], kGatherThreads);   // every gather thread: its special-chunk row + its feature copies
       mbar_init(&ms->bfree[i], 1);
       mbar_init(&ms->p_ready[i], 1);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&ms->dfull[i], 1);
-      mbar_init(&ms->actfull[i], 4 * NP);   // one arrival per epilogue warp of the context
+      mbar_init(&ms->actfull[i], 4 * NP);        // one arrival per epilogue warp of the context
       mbar_init(&ms->p_actfull[i], 1);
     }
+    ms->gprog = 0;
     mbar_fence_init();
   }
   if (warp == kWarpMma) tmem_alloc<CG>(&ms->tmem_base, 512);
-  for (int c = tid; c < H; c += kThreads) ms->bias2[c] = __ldg(p.bias2 + c);
   for (int c = tid; c < C::NQ * 128; c += kThreads) {
     // channel of (block q, lane r) of this CTA: CG = 2 -> rank * 128 + r (one block spans both tiles' rows)
     const int q = c >> 7, r = c & 127;
     const int ch = (CG == 2) ? (int)rank * 128 + r : q * 128 + r;
     ms->bias3[c] = __ldg(p.bias3 + ch);
-  }
-  if (warp == kWarpProd && lane == 0) {
-    if constexpr (NF > 0) tma_prefetch_desc(&p.tmap);
   }
   tc_fence_before_sync();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -209,14 +247,18 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
 
   // unit of ordinal o (tile / tile pair), -1 = no more work
   auto get_unit = [&](int o) -> int {
-    bar_wait<CG>(&ms->tfull[o & (kRing - 1)], (uint32_t)((o >> 4) & 1));
+    if (p.static_sched) {
+      const long long u = (long long)cluster_id + (long long)o * num_clusters;
+      return u < p.num_units ? (int)u : -1;
+    }
+    bar_wait<CG>(&ms->tfull[o & (kRing - 1)], (uint32_t)((o / kRing) & 1));
     return *reinterpret_cast<volatile int*>(&ms->units[o & (kRing - 1)]);
   };
   auto tile_of = [&](int unit) -> long long { return (CG == 2) ? 2LL * unit + rank : (long long)unit; };
 
   if (warp == kWarpProd) {
-    // ============================================================ tile scheduler + weight / gather TMA
-    if (lane == 0) {      // pinned weights: this CTA's image
+    // ============================================================ tile scheduler + pinned weights
+    if (lane == 0) {      // this CTA's weight image
       mbar_arrive_expect_tx(&ms->wfull, (uint32_t)C::WBYTES);
       const uint8_t* src = p.w_img + (size_t)rank * C::WBYTES;
       for (int o = 0; o < C::WBYTES; o += 32768) {
@@ -233,250 +275,316 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
         mbar_arrive_remote(&ms->tfull[s], 1);
       }
     };
-    auto unit_of_raw = [&](int raw) -> int {
-      const long long u = (long long)num_clusters + raw;
-      return u < p.num_units ? (int)u : -1;
-    };
-    int pub = 0;            // next ordinal to publish (leader, lane 0)
-    bool ended = false;
-    int raw_next = 0;
-    if (leader && lane == 0) {
-      // ordinals 0..kAhead: the cluster's own first unit, then independent atomics (their round trips overlap)
-      int raw[kAhead + 1];
-#pragma unroll
-      for (int i = 0; i <= kAhead; ++i) raw[i] = atomicAdd(p.sched, 1);
-      publish(0, cluster_id < p.num_units ? cluster_id : -1);
-      ended = !(cluster_id < p.num_units);
-      pub = 1;
-#pragma unroll
-      for (int i = 0; i < kAhead; ++i) {
-        const int u = ended ? -1 : unit_of_raw(raw[i]);
+    // Only lane 0 of the leader schedules.  Flow control is a monotonic counter, never a parity wait: the scheduler
+    // may fall arbitrarily far behind the pipeline (a slow atomic), and a parity wait that is two phases late
+    // deadlocks.  Every consumer, in both CTAs of a pair, has read ordinal x once the gather warps have passed the
+    // "buffer free" wait of ordinal x + NB, so the ring slot of x may be rewritten (ordinal x + kRing) then.
+    if (leader && lane == 0 && !p.static_sched) {
+      constexpr int kEndMarks = G > 7 ? G : 7;      // -1 marks past the last unit (every role's look-ahead)
+      int pub = 0, n_end = 0;
+      bool ended = false;
+      auto push = [&](int u) {
+        while (pub > *reinterpret_cast<volatile int*>(&ms->gprog) + (kRing - 1 - NB)) __nanosleep(64);
         publish(pub++, u);
-        if (u < 0) ended = true;
-      }
-      raw_next = raw[kAhead];
-    }
-    int L = 0;
-    for (;; ++L) {
-      if (leader && lane == 0) {
-        // ordinal L + kAhead + 1 from the atomic issued one iteration ago; the next atomic goes out now
-        const int u = ended ? -1 : unit_of_raw(raw_next);
-        publish(pub++, u);
-        if (u < 0) ended = true;
-        if (!ended) raw_next = atomicAdd(p.sched, 1);
-      }
-      const int unit = get_unit(L);
-      if (unit < 0) break;
-      const int b = L % NB;
-      SALOG(3, 100 + L)
-      if (L >= NB) bar_wait<CG>(&ms->bfree[b], (uint32_t)((L / NB - 1) & 1));
-      SALOG(3, 200 + L)
-      if constexpr (NF > 0) {
-        const long long R0 = tile_of(unit) * 128 + 4 * lane;
-        int4 id = make_int4(0, 0, 0, 0);
-        if (R0 + 3 < p.total_rows) {
-          id = ldg_nc_s32x4(p.idx + R0);
-        } else {
-          if (R0 + 0 < p.total_rows) id.x = __ldg(p.idx + R0);
-          if (R0 + 1 < p.total_rows) id.y = __ldg(p.idx + R0 + 1);
-          if (R0 + 2 < p.total_rows) id.z = __ldg(p.idx + R0 + 2);
+        if (u < 0) {
+          ended = true;
+          ++n_end;
         }
-        const long long Rc = R0 < p.total_rows ? R0 : 0;
-        const int rowbase = (int)((uint32_t)(Rc >> p.log2S) >> p.log2P) * p.N;
-        if (lane == 0) mbar_arrive_expect_tx(&ms->bfull[b], (uint32_t)(NF * kChunk));
-        __syncwarp();
-        const uint32_t dst = base + off_buf + (uint32_t)b * C::BUFBYTES + (uint32_t)lane * 512u;
-#pragma unroll
-        for (int kc = 0; kc < NF; ++kc)
-          tma_gather4(dst + kc * kChunk, &p.tmap, kc * 64, rowbase + id.x, rowbase + id.y, rowbase + id.z, rowbase + id.w,
-                      &ms->bfull[b]);
+      };
+      // The cluster's own first unit, then units claimed `claim` at a time from the global counter.  One atomic per
+      // unit would cap the whole GPU at one tile per ~11 cycles (same-address atomics serialise in L2: 8192 tiles of
+      // SA1 = 47 us) and every cluster at one unit per atomic round trip; two claims are kept in flight.
+      const int claim = p.claim;
+      int raw_a = atomicAdd(p.sched, claim), raw_b = atomicAdd(p.sched, claim);
+      push(cluster_id < p.num_units ? cluster_id : -1);
+      long long cur = (long long)num_clusters + raw_a;
+      int rem = claim;
+      while (n_end < kEndMarks) {
+        if (!ended && rem == 0) {
+          cur = (long long)num_clusters + raw_b;
+          rem = claim;
+          raw_b = atomicAdd(p.sched, claim);      // next round trip under the publications of this chunk
+        }
+        push((ended || cur >= p.num_units) ? -1 : (int)cur);
+        ++cur;
+        --rem;
       }
+      const int raw_next = raw_b;
+      // every atomic of this cluster has returned before the cluster reports "done" (the last cluster out re-zeroes
+      // the scheduler words)
+      asm volatile("" ::"r"(raw_next) : "memory");
     }
-    // tail: the last "buffer free" commits are multicast to both CTAs of a pair; each CTA sees its own copies complete
-    // before it may leave (an arrival must never target the shared memory of a CTA that has exited)
-    for (int b = 0; b < NB; ++b) {
-      const int uses = (L - b + NB - 1) / NB;          // ordinals o < L with o % NB == b
-      if (L > b && uses >= 1) bar_wait<CG>(&ms->bfree[b], (uint32_t)((uses - 1) & 1));
-    }
-  } else if (warp == kWarpMma) {
+  } else if (warp == kWarpMma || warp == kWarpMma + 1) {
     // ============================================================ MMA issue (leader) / barrier relay (rank 1)
+    // One warp per half of the contexts: the two halves are independent pipelines (each waits only for its own
+    // contexts' operands and epilogues), so their wait -> fence -> issue sequences overlap and the tensor pipe is fed
+    // from two instruction streams.
+    const int half = warp - kWarpMma;
     const bool issuer = elect_one();
     // wait for a local barrier; the leader of a pair also waits for the peer's relayed copy, the peer relays
+    // (The generic -> async proxy fence for operands written with st.shared / cp.async sits HERE, on the consumer
+    // side: the waiting thread has observed the writes through the barrier and fences before it issues the MMAs that
+    // read them -- or, in the peer CTA, before it relays the barrier.  A fence on the writer side costs every gather
+    // thread a full L2 round trip per tile, because it also waits for the thread's prefetch loads in flight.)
     auto ready = [&](uint64_t* local, uint64_t* mirror, uint32_t parity) {
       bar_wait<CG>(local, parity);
       if constexpr (CG == 2) {
-        if (leader) bar_wait<CG>(mirror, parity);
-        else if (issuer) mbar_arrive_remote(mirror, 0);
+        if (leader) {
+          bar_wait<CG>(mirror, parity);
+        } else {
+          fence_proxy_async_smem();
+          if (issuer) mbar_arrive_remote(mirror, 0);
+        }
       }
     };
-    ready(&ms->wfull, &ms->p_wfull, 0);
+    if (half == 0) ready(&ms->wfull, &ms->p_wfull, 0);
+    else bar_wait<CG>(&ms->wfull, 0);              // (the pair's second copy is relayed once, by half 0)
+    if constexpr (CG == 2) {
+      if (half == 1 && leader) bar_wait<CG>(&ms->p_wfull, 0);
+    }
     constexpr uint32_t idesc_h = uidesc_bf16(128 * CG, H);            // hidden layers: N = H
     constexpr uint32_t idesc_t = uidesc_bf16(128 * CG, 128 * CG);     // transposed last layer: N = rows of the unit
     const uint32_t w_base = base;
+    const int c_lo = half * HG;
+    int last_valid = -1;
     for (int round = 0;; ++round) {
       const int o0 = round * G;
-      int nact = 0;
+      int nact = 0;                                 // contexts of this half with a unit in this round
 #pragma unroll
-      for (int c = 0; c < G; ++c)
-        if (nact == c && get_unit(o0 + c) >= 0) nact = c + 1;
+      for (int cc = 0; cc < HG; ++cc)
+        if (nact == cc && get_unit(o0 + c_lo + cc) >= 0) nact = cc + 1;
       if (nact == 0) break;
-      // ---- layer 1: gathered feature chunks + the special K step
+      last_valid = o0 + c_lo + nact - 1;
 #pragma unroll
-      for (int c = 0; c < G; ++c) {
-        if (c >= nact) break;
-        const int o = o0 + c, b = o % NB;
-        const uint32_t use = (uint32_t)(o / NB) & 1u;
-        if (round > 0) ready(&ms->actfull[c], &ms->p_actfull[c], (uint32_t)(3 * round - 1) & 1u);   // TMEM drained
-        bar_wait<CG>(&ms->sfull[b], use);
-        if constexpr (NF > 0) bar_wait<CG>(&ms->bfull[b], use);
-        if constexpr (CG == 2) {
-          if (leader) bar_wait<CG>(&ms->p_ready[b], use);
-          else if (issuer) mbar_arrive_remote(&ms->p_ready[b], 0);
-        }
-        tc_fence_after_sync();
-        SALOG(2, 1000 + 10 * round + c)
-        if (leader && issuer) {
-          const uint32_t d = tmem_base + (uint32_t)(c * C::CW);
-          const uint32_t buf = base + off_buf + (uint32_t)b * C::BUFBYTES;
+      for (int phase = 0; phase < 3; ++phase) {
+        // one context per step (wait -> fence -> issue): the epilogue of a context runs under the step of the other
 #pragma unroll
-          for (int kc = 0; kc < NF; ++kc) {
-            const uint64_t ad = udesc_sw128(buf + kc * kChunk), bd = udesc_sw128(w_base + kc * (C::WROWS * 128));
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16<CG>(d, ad + 2u * k, bd + 2u * k, idesc_h, (kc | k) ? 1u : 0u);
+        for (int cc = 0; cc < HG; ++cc) {
+          if (cc >= nact) break;
+          const int c = c_lo + cc;
+          const int o = o0 + c, b = o % NB;
+          SALOG(2 + 3 * half, 10000 * (phase + 1) + 10 * round + cc)
+          if (phase == 0) {
+            if (round > 0) ready(&ms->actfull[c], &ms->p_actfull[c], (uint32_t)(3 * round - 1) & 1u);   // TMEM drained
+            ready(&ms->full[b], &ms->p_ready[b], (uint32_t)(o / NB) & 1u);                              // layer-1 operand
+          } else {
+            ready(&ms->actfull[c], &ms->p_actfull[c], (uint32_t)(3 * round + phase - 1) & 1u);          // activations
           }
-          umma_f16<CG>(d, udesc_k16(base + off_sp + (uint32_t)b * kSpBytes), udesc_k16(w_base + C::OFF_W1SP), idesc_h,
-                       NF > 0 ? 1u : 0u);
-          umma_commit_to<CG>(&ms->dfull[c]);
-        }
-        __syncwarp();
-      }
-      // ---- layer 2
+          fence_proxy_async_smem();
+          tc_fence_after_sync();
+          SALOG(2 + 3 * half, 10000 * (phase + 1) + 10 * round + cc + 2)
+          if (leader && issuer) {
+            const uint32_t buf = base + off_buf + (uint32_t)b * C::BUFBYTES;
+            if (phase == 0) {
+              // layer 1: gathered feature chunks + the special K step (relative xyz, scalar features, bias)
+              const uint32_t d = tmem_base + (uint32_t)(c * C::CW);
 #pragma unroll
-      for (int c = 0; c < G; ++c) {
-        if (c >= nact) break;
-        const int o = o0 + c, b = o % NB;
-        ready(&ms->actfull[c], &ms->p_actfull[c], (uint32_t)(3 * round) & 1u);
-        tc_fence_after_sync();
-        SALOG(2, 2000 + 10 * round + c)
-        if (leader && issuer) {
-          const uint32_t d = tmem_base + (uint32_t)(c * C::CW);
-          const uint32_t buf = base + off_buf + (uint32_t)b * C::BUFBYTES;
+              for (int kc = 0; kc < NF; ++kc) {
+                const uint64_t ad = udesc_sw128(buf + kc * kChunk), bd = udesc_sw128(w_base + kc * (C::WROWS * 128));
 #pragma unroll
-          for (int kc = 0; kc < C::HC; ++kc) {
-            const uint64_t ad = udesc_sw128(buf + kc * kChunk), bd = udesc_sw128(w_base + C::OFF_W2 + kc * (C::WROWS * 128));
+                for (int k = 0; k < 4; ++k) umma_f16<CG>(d, ad + 2u * k, bd + 2u * k, idesc_h, (kc | k) ? 1u : 0u);
+              }
+              umma_f16<CG>(d, udesc_k16(base + off_sp + (uint32_t)b * kSpBytes), udesc_k16(w_base + C::OFF_W1SP), idesc_h,
+                           NF > 0 ? 1u : 0u);
+              umma_commit_to<CG>(&ms->dfull[c]);
+            } else if (phase == 1) {
+              // layer 2 (+ bias: the special K step again, against a piece that is zero except for the ones column)
+              const uint32_t d = tmem_base + (uint32_t)(c * C::CW);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16<CG>(d, ad + 2u * k, bd + 2u * k, idesc_h, (kc | k) ? 1u : 0u);
-          }
-          umma_commit_to<CG>(&ms->dfull[c]);
-        }
-        __syncwarp();
-      }
-      // ---- layer 3, transposed: D^T (channels x rows) = W3 . H^T
+              for (int kc = 0; kc < C::HC; ++kc) {
+                const uint64_t ad = udesc_sw128(buf + kc * kChunk), bd = udesc_sw128(w_base + C::OFF_W2 + kc * (C::WROWS * 128));
 #pragma unroll
-      for (int c = 0; c < G; ++c) {
-        if (c >= nact) break;
-        const int o = o0 + c, b = o % NB;
-        SALOG(2, 30000 + 10 * round + c)
-        ready(&ms->actfull[c], &ms->p_actfull[c], (uint32_t)(3 * round + 1) & 1u);
-        SALOG(2, 31000 + 10 * round + c)
-        tc_fence_after_sync();
-        SALOG(2, 3000 + 10 * round + c)
-        if (leader && issuer) {
-          const uint32_t buf = base + off_buf + (uint32_t)b * C::BUFBYTES;
+                for (int k = 0; k < 4; ++k) umma_f16<CG>(d, ad + 2u * k, bd + 2u * k, idesc_h, (kc | k) ? 1u : 0u);
+              }
+              umma_f16<CG>(d, udesc_k16(base + off_sp + (uint32_t)b * kSpBytes), udesc_k16(w_base + C::OFF_W2BIAS), idesc_h, 1u);
+              umma_commit_to<CG>(&ms->dfull[c]);
+            } else {
+              // layer 3, transposed: D^T (channels x rows) = W3 . H^T
 #pragma unroll
-          for (int blk = 0; blk < C::NBLK; ++blk) {
-            const uint32_t d = tmem_base + (uint32_t)(c * C::CW + blk * 128 * CG);
+              for (int blk = 0; blk < C::NBLK; ++blk) {
+                const uint32_t d = tmem_base + (uint32_t)(c * C::CW + blk * 128 * CG);
 #pragma unroll
-            for (int kc = 0; kc < C::HC; ++kc) {
-              const uint64_t ad = udesc_sw128(w_base + C::OFF_W3 + (blk * C::HC + kc) * kChunk), bd = udesc_sw128(buf + kc * kChunk);
+                for (int kc = 0; kc < C::HC; ++kc) {
+                  const uint64_t ad = udesc_sw128(w_base + C::OFF_W3 + (blk * C::HC + kc) * kChunk), bd = udesc_sw128(buf + kc * kChunk);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16<CG>(d, ad + 2u * k, bd + 2u * k, idesc_t, (kc | k) ? 1u : 0u);
+                  for (int k = 0; k < 4; ++k) umma_f16<CG>(d, ad + 2u * k, bd + 2u * k, idesc_t, (kc | k) ? 1u : 0u);
+                }
+              }
+              umma_commit_to<CG>(&ms->dfull[c]);
+              umma_commit_to<CG>(&ms->bfree[b]);      // the tile buffer (and its special chunk) may be refilled
             }
           }
-          SALOG(2, 32000 + 10 * round + c)
-          umma_commit_to<CG>(&ms->dfull[c]);
-          umma_commit_to<CG>(&ms->bfree[b]);      // the tile buffer (and its special chunk) may be refilled
+          __syncwarp();
+          SALOG(2 + 3 * half, 10000 * (phase + 1) + 10 * round + cc + 4)
         }
-        SALOG(2, 33000 + 10 * round + c)
-        __syncwarp();
-        SALOG(2, 3500 + 10 * round + c)
       }
-      if (nact < G) break;
+      if (nact < HG) break;
+    }
+    if (half == 0) {
+      // tail: the last "buffer free" commits are multicast to both CTAs of a pair; each CTA sees its own copies
+      // complete before it may leave (an arrival must never target the shared memory of a CTA that has exited).  This
+      // warp has never waited on these barriers, and their final completion is the one asked for: no phase is skipped.
+      int n_total = last_valid + 1;                  // valid ordinals form a prefix
+      while (get_unit(n_total) >= 0) ++n_total;
+      for (int b = 0; b < NB; ++b) {
+        const int uses = (n_total - b + NB - 1) / NB;      // ordinals o < n_total with o % NB == b
+        if (n_total > b && uses >= 1) bar_wait<CG>(&ms->bfree[b], (uint32_t)((uses - 1) & 1));
+      }
     }
   } else if (warp >= kWarpGather) {
-    // ============================================================ special K step: relative xyz, scalar features, 1
-    const int gt = tid - kWarpGather * 32;      // row of the tile
+    // ============================================================ layer-1 operand: feature rows + special K step
+    const int gt = tid - kWarpGather * 32;      // row of the tile this thread owns
+    const int wrow0 = (gt >> 5) * 32;           // first row of this warp
+    const int unit = lane & 7, rsub = lane >> 3;
     struct Sp {
       float x, y, z, qx, qy, qz, r, e[4];
     };
-    auto issue_idx = [&](int unit) -> int {
-      if (unit < 0) return 0;
-      const long long R = tile_of(unit) * 128 + gt;
+    auto issue_idx = [&](int unit_id) -> int {
+      if (unit_id < 0) return 0;
+      const long long R = tile_of(unit_id) * 128 + gt;
       return R < p.total_rows ? ldg_nc_s32(p.idx + R) : 0;
     };
-    auto load_sp = [&](int unit, int raw, Sp& s, bool& valid) {
+    // source row (b * N + idx) of this thread's row, kNoRow past the end; starts the loads of the special K step
+    auto load_sp = [&](int unit_id, int raw, Sp& s) -> uint32_t {
       s.x = s.y = s.z = s.qx = s.qy = s.qz = 0.f;
       s.r = 1.f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) s.e[e] = 0.f;
-      valid = false;
-      if (unit < 0) return;
-      const long long R = tile_of(unit) * 128 + gt;
-      if (R >= p.total_rows) return;
-      valid = true;
+      if (unit_id < 0) return kNoRow;
+      const long long R = tile_of(unit_id) * 128 + gt;
+      if (R >= p.total_rows) return kNoRow;
       const uint32_t pt = (uint32_t)(R >> p.log2S);
-      const size_t src = (size_t)(pt >> p.log2P) * p.N + (uint32_t)raw;
-      const float* a = p.xyz + src * 3;
+      const uint32_t src = (pt >> p.log2P) * (uint32_t)p.N + (uint32_t)raw;
       const float* q = p.new_xyz + (size_t)pt * 3;
-      s.x = ldg_nc_f32(a);
-      s.y = ldg_nc_f32(a + 1);
-      s.z = ldg_nc_f32(a + 2);
+      if (p.xyzw) {
+        const float4 v = ldg_nc_f32x4(p.xyzw + src);
+        s.x = v.x;
+        s.y = v.y;
+        s.z = v.z;
+        if (p.E > 0) s.e[0] = v.w;
+      } else {
+        const float* a = p.xyz + (size_t)src * 3;
+        s.x = ldg_nc_f32(a);
+        s.y = ldg_nc_f32(a + 1);
+        s.z = ldg_nc_f32(a + 2);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (e < p.E) s.e[e] = ldg_nc_f32(p.extra + (size_t)src * p.E + e);
+      }
       s.qx = ldg_nc_f32(q);
       s.qy = ldg_nc_f32(q + 1);
       s.qz = ldg_nc_f32(q + 2);
       if (p.radius_t) s.r = ldg_nc_f32(p.radius_t + pt);
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (e < p.E) s.e[e] = ldg_nc_f32(p.extra + src * p.E + e);
+      return src;
     };
-    int u_cur = get_unit(0), u_nxt = get_unit(1);
-    Sp sp;
-    bool valid;
-    load_sp(u_cur, issue_idx(u_cur), sp, valid);
-    int idraw = issue_idx(u_nxt);
-    for (int o = 0; u_cur >= 0; ++o) {
-      const int b = o % NB;
-      if (o >= NB) bar_wait<CG>(&ms->bfree[b], (uint32_t)((o / NB - 1) & 1));
-      float v[8];
+    auto publish = [&](int b) {                 // this thread's stores / copies of buffer b are complete
+      mbar_arrive(&ms->full[b]);                // (release; the proxy fence is the consumer's, see the MMA warp)
+    };
+    // Software pipeline over tiles: two dependent L2 round trips per row (neighbour index, then xyz / features at
+    // that index), each requested kDepth tiles before its result is needed -- the inputs of the special K step of
+    // tiles o .. o + 2 sit in registers, the indices of tiles o + 3 .. o + 5 are in flight.  Nothing in the loop waits
+    // for a load issued less than three iterations ago.
+    constexpr int kDepth = 3;
+    Sp sp[kDepth];
+    uint32_t src[kDepth];
+    int uq[kDepth];                             // units of tiles o .. o + 2 (slot = tile % 3)
+    int ui[kDepth], idxq[kDepth];               // units / neighbour indices (in flight) of tiles o + 3 .. o + 5
+    {
+      int raw[kDepth];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      if (valid) {
-        float dx = __fsub_rn(sp.x, sp.qx), dy = __fsub_rn(sp.y, sp.qy), dz = __fsub_rn(sp.z, sp.qz);
-        if (p.normalize) {
-          const float inv = p.radius_t ? __frcp_rn(sp.r) : p.inv_radius;
-          dx *= inv;
-          dy *= inv;
-          dz *= inv;
-        }
-        v[0] = dx;
-        v[1] = dy;
-        v[2] = dz;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[3 + e] = sp.e[e];
+      for (int k = 0; k < kDepth; ++k) {
+        uq[k] = get_unit(k);
+        raw[k] = issue_idx(uq[k]);
       }
-      const uint32_t dst = base + off_sp + (uint32_t)b * kSpBytes;
-      sts_v4(dst + k16_off(gt, 0), bf16x2_rn(v[0], v[1]), bf16x2_rn(v[2], v[3]), bf16x2_rn(v[4], v[5]), bf16x2_rn(v[6], v[7]));
-      sts_v4(dst + k16_off(gt, 1), 0u, 0u, 0u, 0x3F800000u);   // K index 15 = 1.0 (bf16, high half): the bias column
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ms->sfull[b]);
-      SALOG(1, 100 + o)
-      // loads for the next tiles, issued after this tile's publication (each has an iteration to land)
-      const int u_n2 = get_unit(o + 2);
-      load_sp(u_nxt, idraw, sp, valid);
-      idraw = issue_idx(u_n2);
-      u_cur = u_nxt;
-      u_nxt = u_n2;
+#pragma unroll
+      for (int k = 0; k < kDepth; ++k) {
+        ui[k] = get_unit(kDepth + k);
+        idxq[k] = issue_idx(ui[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < kDepth; ++k) src[k] = load_sp(uq[k], raw[k], sp[k]);
+    }
+    int pend_b = -1;                            // buffer whose cp.async group is still in flight (published one tile later)
+    int o = 0;
+    for (bool more = true; more;) {
+#pragma unroll
+      for (int k = 0; k < kDepth; ++k, ++o) {
+        if (uq[k] < 0) {
+          more = false;
+          break;
+        }
+        const int b = o % NB;
+        if (o >= NB) {
+          const uint32_t par = (uint32_t)((o / NB - 1) & 1);
+          if (!__all_sync(FULL, bar_try<CG>(&ms->bfree[b], par))) {
+            // about to block: publish what is in flight first (the MMAs that free this buffer may be waiting for it)
+            if (pend_b >= 0) {
+              cp_async_wait<0>();
+              publish(pend_b);
+              pend_b = -1;
+            }
+            bar_wait<CG>(&ms->bfree[b], par);
+          }
+        }
+        if (gt == 0) *reinterpret_cast<volatile int*>(&ms->gprog) = o;
+        SALOG(1, 1000 + o)
+        // ---- special K step: [dx, dy, dz, e0..e3, 0 x 8, 1]
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        if (src[k] != kNoRow) {
+          float dx = __fsub_rn(sp[k].x, sp[k].qx), dy = __fsub_rn(sp[k].y, sp[k].qy), dz = __fsub_rn(sp[k].z, sp[k].qz);
+          if (p.normalize) {
+            const float inv = p.radius_t ? __frcp_rn(sp[k].r) : p.inv_radius;
+            dx *= inv;
+            dy *= inv;
+            dz *= inv;
+          }
+          v[0] = dx;
+          v[1] = dy;
+          v[2] = dz;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[3 + e] = sp[k].e[e];
+        }
+        const uint32_t dsp = base + off_sp + (uint32_t)b * kSpBytes;
+        sts_v4(dsp + k16_off(gt, 0), bf16x2_rn(v[0], v[1]), bf16x2_rn(v[2], v[3]), bf16x2_rn(v[4], v[5]), bf16x2_rn(v[6], v[7]));
+        sts_v4(dsp + k16_off(gt, 1), 0u, 0u, 0u, 0x3F800000u);   // K index 15 = 1.0 (bf16, high half): the bias column
+        SALOG(1, 2000 + o)
+        if constexpr (NF > 0) {
+          // ---- feature rows: this warp's 32 rows, 8 lanes per row (one 128-byte line per row and chunk)
+          const uint32_t dbuf = base + off_buf + (uint32_t)b * C::BUFBYTES;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t sj = __shfl_sync(FULL, src[k], 4 * j + rsub);
+            const int row = wrow0 + 4 * j + rsub;
+            const __nv_bfloat16* g = p.feat_cl + (size_t)(sj == kNoRow ? 0u : sj) * (NF * 64) + unit * 8;
+            const uint32_t nbytes = sj == kNoRow ? 0u : 16u;
+            const uint32_t d = dbuf + swz128(row, unit);
+#pragma unroll
+            for (int kc = 0; kc < NF; ++kc) cp_async16(d + kc * kChunk, g + kc * 64, nbytes);
+          }
+          cp_async_commit();
+          if (pend_b >= 0) {
+            cp_async_wait<1>();                   // the previous tile's group has landed
+            publish(pend_b);
+          }
+          pend_b = b;
+        } else {
+          publish(b);
+        }
+        SALOG(1, 100 + o)
+        // refill this slot with tile o + 3 (its index landed long ago), request the index of tile o + 6
+        uq[k] = ui[k];
+        src[k] = load_sp(ui[k], idxq[k], sp[k]);
+        SALOG(1, 3000 + o)
+        ui[k] = get_unit(o + 2 * kDepth);
+        SALOG(1, 4000 + o)
+        idxq[k] = issue_idx(ui[k]);
+      }
+    }
+    if (pend_b >= 0) {
+      cp_async_wait<0>();
+      publish(pend_b);
     }
   } else {
     // ============================================================ epilogue warpgroups
@@ -485,41 +593,34 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
     const int row = (warp & 3) * 32 + lane;                         // TMEM lane
     const uint32_t tctx = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(c * C::CW);
     auto done_phase = [&]() {
-      if (warp == 0) { SALOG(0, 70000) }
       tc_fence_before_sync();
-      if (warp == 0) { SALOG(0, 71000) }
       __syncwarp();
       if (lane == 0) mbar_arrive(&ms->actfull[c]);
     };
-    // hidden layer: TMEM -> (+bias) -> ReLU -> bf16 -> swizzled activation chunk (= the next layer's operand)
-    auto hidden = [&](uint32_t buf, const float* bias) {
+    // hidden layer: TMEM -> ReLU -> bf16 -> swizzled activation chunk (= the next layer's operand); the bias is
+    // already in the accumulator.  16 columns at a time, the next load in flight under the conversion.
+    auto hidden = [&](uint32_t buf) {
+      constexpr int NG = C::HP / 16;
+      const int c0 = part * C::HP;
+      uint32_t v[2][16];
+      tmem_ld_x16(tctx + (uint32_t)c0, v[0]);
+      tmem_ld_fence();
 #pragma unroll
-      for (int i = 0; i < C::HP / 64; ++i) {
-        const int c0 = part * C::HP + i * 64;
-        const uint32_t chunk = buf + (uint32_t)(c0 >> 6) * kChunk;
+      for (int g = 0; g < NG; ++g) {
+        if (g + 1 < NG) tmem_ld_x16(tctx + (uint32_t)(c0 + (g + 1) * 16), v[(g + 1) & 1]);
+        const uint32_t* w = v[g & 1];
+        const int col = c0 + g * 16;
+        const uint32_t chunk = buf + (uint32_t)(col >> 6) * kChunk;
+        const int u0 = (col & 63) >> 3;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          tmem_ld_x32(tctx + (uint32_t)(c0 + h * 32), v);
-          tmem_ld_fence();
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float f[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[u * 8 + k]);
-            if (bias) {
-              const float4 ba = *reinterpret_cast<const float4*>(bias + c0 + h * 32 + u * 8);
-              const float4 bb = *reinterpret_cast<const float4*>(bias + c0 + h * 32 + u * 8 + 4);
-              f[0] += ba.x; f[1] += ba.y; f[2] += ba.z; f[3] += ba.w;
-              f[4] += bb.x; f[5] += bb.y; f[6] += bb.z; f[7] += bb.w;
-            }
-            sts_v4(chunk + swz128(row, h * 4 + u), bf16x2_relu(f[0], f[1]), bf16x2_relu(f[2], f[3]), bf16x2_relu(f[4], f[5]),
-                   bf16x2_relu(f[6], f[7]));
-          }
-        }
+        for (int u = 0; u < 2; ++u)
+          sts_v4(chunk + swz128(row, u0 + u),
+                 bf16x2_relu(__uint_as_float(w[u * 8 + 0]), __uint_as_float(w[u * 8 + 1])),
+                 bf16x2_relu(__uint_as_float(w[u * 8 + 2]), __uint_as_float(w[u * 8 + 3])),
+                 bf16x2_relu(__uint_as_float(w[u * 8 + 4]), __uint_as_float(w[u * 8 + 5])),
+                 bf16x2_relu(__uint_as_float(w[u * 8 + 6]), __uint_as_float(w[u * 8 + 7])));
+        if (g + 1 < NG) tmem_ld_fence();
       }
-      if (warp == 0) { SALOG(0, 60000) }
-      fence_proxy_async_smem();
     };
     for (int t = 0;; ++t) {
       const int o = t * G + c;
@@ -527,16 +628,15 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
       if (unit < 0) break;
       const uint32_t buf = base + off_buf + (uint32_t)(o % NB) * C::BUFBYTES;
       bar_wait<CG>(&ms->dfull[c], (uint32_t)(3 * t) & 1u);
-      if (warp == 0) { SALOG(0, 50000 + 10 * t) }
       tc_fence_after_sync();
       if (warp == 0 || warp == 4) { SALOG(warp, 1000 + 10 * t) }
-      hidden(buf, nullptr);                     // layer-1 bias rides on the constant-1 column of the special K step
+      hidden(buf);
       done_phase();
       if (warp == 0 || warp == 4) { SALOG(warp, 1500 + 10 * t) }
       bar_wait<CG>(&ms->dfull[c], (uint32_t)(3 * t + 1) & 1u);
       tc_fence_after_sync();
       if (warp == 0 || warp == 4) { SALOG(warp, 2000 + 10 * t) }
-      hidden(buf, ms->bias2);
+      hidden(buf);
       done_phase();
       if (warp == 0 || warp == 4) { SALOG(warp, 2500 + 10 * t) }
       bar_wait<CG>(&ms->dfull[c], (uint32_t)(3 * t + 2) & 1u);
@@ -550,21 +650,17 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
         const int ch = (CG == 2) ? (int)rank * 128 + row : q * 128 + row;
         const float bias = ms->bias3[q * 128 + row];
         float y[C::PTS];
+        uint32_t v[2][16];
+        tmem_ld_x16(tctx + (uint32_t)(q * 128), v[0]);
+        tmem_ld_fence();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t v[32];
-          tmem_ld_x32(tctx + (uint32_t)(q * 128 + g * 32), v);
-          tmem_ld_fence();
-          if constexpr (C::S == 64) {
-            const float m = vmax_tree<32>(v);
-            if (g & 1) y[g >> 1] = fmaxf(y[g >> 1], m);
-            else y[g >> 1] = m;
-          } else if constexpr (C::S == 32) {
-            y[g] = vmax_tree<32>(v);
-          } else {
-            y[2 * g] = vmax_tree<16>(v);
-            y[2 * g + 1] = vmax_tree<16>(v + 16);
-          }
+        for (int g = 0; g < 8; ++g) {
+          if (g + 1 < 8) tmem_ld_x16(tctx + (uint32_t)(q * 128 + (g + 1) * 16), v[(g + 1) & 1]);
+          const float m = vmax_tree<16>(v[g & 1]);
+          constexpr int GP = C::S / 16;                 // 16-column groups per point
+          if (g % GP == 0) y[g / GP] = m;
+          else y[g / GP] = fmaxf(y[g / GP], m);
+          if (g + 1 < 8) tmem_ld_fence();
         }
         const uint32_t pt0 = (uint32_t)(tile * C::PTS);
         if (ch < p.c3_real && pt0 < p.total_points) {
@@ -620,21 +716,6 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------ host side
-using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeFn encode_fn() {
-  static EncodeFn fn = []() -> EncodeFn {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<EncodeFn>(f);
-  }();
-  return fn;
-}
-
 struct Instance {
   int id, CG, NF, H, C3, S, wbytes, smem;
   void (*launch)(const SaParams&, int grid, cudaStream_t);
@@ -672,14 +753,18 @@ using CfgSA3 = Cfg<2, 4, 128, 256, 16>;     // SA3 / SA4 / vote aggregation (128
 using CfgSA2s = Cfg<1, 2, 128, 256, 32>;    // SA2 on one CTA (no cluster): bring-up / comparison
 
 const Instance* instances(int* n) {
-  static const Instance tab[] = {make_inst<CfgSA1>(0), make_inst<CfgSA2>(1), make_inst<CfgSA3>(2), make_inst<CfgSA2s>(3)};
+  // order = preference among instances that fit the same stage (SA2: the single-CTA instance measures 51 us against
+  // 58 us for the pair at 8 x 1024 x 32 rows -- the relayed barriers cost more than the halved weight footprint buys)
+  static const Instance tab[] = {make_inst<CfgSA1>(0), make_inst<CfgSA2s>(3), make_inst<CfgSA2>(1), make_inst<CfgSA3>(2)};
   *n = 4;
   return tab;
 }
 const Instance* instance_by_id(int id) {
   int n;
   const Instance* t = instances(&n);
-  return (id >= 0 && id < n) ? &t[id] : nullptr;
+  for (int i = 0; i < n; ++i)
+    if (t[i].id == id) return &t[i];
+  return nullptr;
 }
 
 uint16_t bf16_bits(float w) {
@@ -702,28 +787,32 @@ void put_k16(uint8_t* piece, int r, int kk, float w) {             // element (r
 }  // namespace
 
 #ifdef SAD_MLP_PROFILE
-extern "C" SAD_API int sad_sa_profile_dump(long long* host_log /*5*8192*/, int* host_n /*5*/) {
+extern "C" SAD_API int sad_sa_debug_buffer(void* host_mapped_64_words) {
+  return (int)cudaMemcpyToSymbol(g_sa_dbg, &host_mapped_64_words, sizeof(void*));
+}
+extern "C" SAD_API int sad_sa_profile_dump(long long* host_log /*6*8192*/, int* host_n /*6*/) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(host_log, g_sa_log, sizeof(long long) * 5 * 8192);
-  cudaMemcpyFromSymbol(host_n, g_sa_logn, sizeof(int) * 5);
-  int z[5] = {0, 0, 0, 0, 0};
+  cudaMemcpyFromSymbol(host_log, g_sa_log, sizeof(long long) * 6 * 8192);
+  cudaMemcpyFromSymbol(host_n, g_sa_logn, sizeof(int) * 6);
+  int z[6] = {0, 0, 0, 0, 0, 0};
   cudaMemcpyToSymbol(g_sa_logn, z, sizeof(z));
   return 0;
 }
 #endif
 
-// Instance that runs (NF gathered chunks, hidden widths h1 == h2, c3 outputs, nsample S, E scalar features), or -1.
-// `single_cta` != 0 asks for a non-cluster instance where one exists (tools / tests).
-extern "C" int sad_sa_mlp_query(int C0, int h1, int h2, int c3, int S, int E, int has_xyz, int single_cta) {
+// Instance that runs (C0 gathered channels, hidden widths h1 == h2, c3 outputs, nsample S, E scalar features), or -1.
+// `prefer`: 0 = the library's choice, 1 = an instance that runs on single CTAs, 2 = on CTA pairs, where one exists
+// (tools / tests).
+extern "C" int sad_sa_mlp_query(int C0, int h1, int h2, int c3, int S, int E, int has_xyz, int prefer) {
   if (C0 % 64 || h1 != h2 || E < 0 || E > 4 || !has_xyz || c3 < 8 || c3 % 8) return -1;
-  int n, fallback = -1;
+  int n, first = -1;
   const Instance* t = instances(&n);
   for (int i = 0; i < n; ++i) {
     if (t[i].NF != C0 / 64 || t[i].H != h1 || t[i].S != S || c3 > t[i].C3) continue;
-    if ((t[i].CG == 1) == (single_cta != 0)) return t[i].id;
-    if (fallback < 0) fallback = t[i].id;
+    if (prefer == 0 || (prefer == 1) == (t[i].CG == 1)) return t[i].id;      // the table is in order of preference
+    if (first < 0) first = t[i].id;
   }
-  return fallback;
+  return first;
 }
 
 extern "C" long long sad_sa_mlp_image_bytes(int instance) {
@@ -732,18 +821,19 @@ extern "C" long long sad_sa_mlp_image_bytes(int instance) {
 }
 
 // Pack the stage's weights into the per-CTA shared-memory images (bf16).  W1 (h x cin1) with
-//   perm_feat[NF*64]: source column of gathered-feature K index k (-1 = zero), perm_sp[7]: source columns of
-//   [dx, dy, dz, e0..e3] (-1 = zero); b1 goes into the constant-1 column.  W2 (h x h), W3 (c3 x h).
+//   perm_feat[C0]: source column of gathered-feature K index k (-1 = zero), perm_sp[7]: source columns of
+//   [dx, dy, dz, e0..e3] (-1 = zero); b1 and b2 go into constant-1 K columns.  W2 (h x h), W3 (c3 x h).
 extern "C" int sad_sa_mlp_pack(int instance, const float* W1, int cin1, const int32_t* perm_feat, const int32_t* perm_sp,
-                               const float* b1, const float* W2, const float* W3, int c3, void* out_image) {
+                               const float* b1, const float* W2, const float* b2, const float* W3, int c3, void* out_image) {
   const Instance* in = instance_by_id(instance);
   SAD_REQUIRE(in, "sa_mlp_pack: unknown instance %d", instance);
-  SAD_REQUIRE(W1 && perm_sp && b1 && W2 && W3 && out_image && (in->NF == 0 || perm_feat), "sa_mlp_pack: null pointer");
+  SAD_REQUIRE(W1 && perm_sp && b1 && W2 && b2 && W3 && out_image && (in->NF == 0 || perm_feat), "sa_mlp_pack: null pointer");
   SAD_REQUIRE(c3 >= 1 && c3 <= in->C3, "sa_mlp_pack: c3 out of range");
   const int CG = in->CG, NF = in->NF, H = in->H, HC = H / 64, WROWS = H / CG, NBLK = in->C3 / (128 * CG);
   uint8_t* img = static_cast<uint8_t*>(out_image);
   memset(img, 0, (size_t)CG * in->wbytes);
-  const int off_w1sp = NF * WROWS * 128, off_w2 = off_w1sp + WROWS * 32, off_w3 = off_w2 + HC * WROWS * 128;
+  const int off_w1sp = NF * WROWS * 128, off_w2 = off_w1sp + WROWS * 32, off_w2b = off_w2 + HC * WROWS * 128,
+            off_w3 = off_w2b + WROWS * 32;
   for (int r = 0; r < CG; ++r) {
     uint8_t* im = img + (size_t)r * in->wbytes;
     for (int nl = 0; nl < WROWS; ++nl) {
@@ -762,6 +852,7 @@ extern "C" int sad_sa_mlp_pack(int instance, const float* W1, int cin1, const in
       }
       put_k16(im + off_w1sp, nl, 15, b1[n]);
       for (int k = 0; k < H; ++k) put_sw128(im + off_w2 + (size_t)(k >> 6) * WROWS * 128, nl, k & 63, W2[(size_t)n * H + k]);
+      put_k16(im + off_w2b, nl, 15, b2[n]);
     }
     for (int blk = 0; blk < NBLK; ++blk)
       for (int row = 0; row < 128; ++row) {
@@ -774,17 +865,37 @@ extern "C" int sad_sa_mlp_pack(int instance, const float* W1, int cin1, const in
   return SAD_OK;
 }
 
-// tools / tests: grid width override is not needed here; the scheduling hint below mirrors sad_mlp_set_tiles_per_cta
-extern "C" int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* feat_cl, const float* xyz, const float* new_xyz,
-                              const int32_t* idx, float radius, const float* radius_t, int normalize_xyz, const float* extra,
-                              int E, const void* w_image, const float* bias2, const float* bias3_padded, int c3,
-                              void* out_cl_bf16, float* out_cf_f32, int* sched, int tiles_per_cta, sad_stream_t stream_) {
+// (B,N,3) coordinates (+ one scalar feature per point) -> (B,N) float4 {x, y, z, feature | 0}: the gathered source of the
+// special K step as one aligned 16-byte row
+__global__ void __launch_bounds__(256) pack_xyzw_kernel(long long rows, const float* __restrict__ xyz,
+                                                        const float* __restrict__ extra, float4* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= rows) return;
+  out[i] = make_float4(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), extra ? __ldg(extra + i) : 0.f);
+}
+
+extern "C" int sad_pack_xyzw(int B, int N, const float* xyz, const float* extra1, void* out_xyzw, sad_stream_t stream) {
+  SAD_REQUIRE(B >= 0 && N >= 1, "pack_xyzw: bad sizes");
+  if (B == 0) return SAD_OK;
+  SAD_REQUIRE(xyz && out_xyzw && (reinterpret_cast<uintptr_t>(out_xyzw) & 15) == 0, "pack_xyzw: null / misaligned pointer");
+  const long long rows = (long long)B * N;
+  pack_xyzw_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, xyz, extra1, static_cast<float4*>(out_xyzw));
+  SAD_LAUNCH_CHECK("pack_xyzw_kernel");
+  return SAD_OK;
+}
+
+extern "C" int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* feat_cl, const float* xyz, const void* xyzw,
+                              const float* new_xyz, const int32_t* idx, float radius, const float* radius_t,
+                              int normalize_xyz, const float* extra, int E, const void* w_image, const float* bias3_padded, int c3, void* out_cl_bf16,
+                              float* out_cf_f32, int* sched, int tiles_per_cta, sad_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const Instance* in = instance_by_id(instance);
   SAD_REQUIRE(in, "sa_mlp: unknown instance %d", instance);
   SAD_REQUIRE(B >= 0 && N >= 1 && P >= 0, "sa_mlp: bad sizes B=%d N=%d P=%d", B, N, P);
-  SAD_REQUIRE(xyz && new_xyz && idx && w_image && bias2 && bias3_padded && sched, "sa_mlp: null pointer");
+  SAD_REQUIRE(xyz && new_xyz && idx && w_image && bias3_padded && sched, "sa_mlp: null pointer");
+  SAD_REQUIRE(!xyzw || (E <= 1 && (reinterpret_cast<uintptr_t>(xyzw) & 15) == 0), "sa_mlp: xyzw needs E <= 1 and 16-byte alignment");
   SAD_REQUIRE((in->NF == 0) == (feat_cl == nullptr), "sa_mlp: gathered source / instance mismatch");
+  SAD_REQUIRE((reinterpret_cast<uintptr_t>(feat_cl) & 15) == 0, "sa_mlp: feat_cl must be 16-byte aligned");
   SAD_REQUIRE(E >= 0 && E <= 4 && (E == 0 || extra), "sa_mlp: 0..4 scalar features");
   SAD_REQUIRE(c3 >= 1 && c3 <= in->C3 && c3 % 8 == 0, "sa_mlp: bad output width %d", c3);
   SAD_REQUIRE(out_cl_bf16 || out_cf_f32, "sa_mlp: no output requested");
@@ -805,32 +916,20 @@ extern "C" int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* fea
   SAD_REQUIRE(tiles < 0x3FFFFFFFLL, "sa_mlp: too many rows");
   p.num_tiles = (int)tiles;
   p.num_units = (int)((tiles + in->CG - 1) / in->CG);
-  p.xyz = xyz; p.new_xyz = new_xyz; p.idx = idx; p.radius_t = radius_t;
+  p.feat_cl = static_cast<const __nv_bfloat16*>(feat_cl);
+  p.xyz = xyz; p.xyzw = static_cast<const float4*>(xyzw); p.new_xyz = new_xyz; p.idx = idx; p.radius_t = radius_t;
   p.normalize = normalize_xyz;
   p.inv_radius = (normalize_xyz && !radius_t) ? 1.0f / radius : 1.0f;
   p.extra = extra; p.E = E;
   p.w_img = static_cast<const uint8_t*>(w_image);
-  p.bias2 = bias2; p.bias3 = bias3_padded; p.c3_real = c3;
+  p.bias3 = bias3_padded; p.c3_real = c3;
   p.out_cl = static_cast<__nv_bfloat16*>(out_cl_bf16); p.out_cf = out_cf_f32;
   p.sched = sched;
-  if (in->NF > 0) {
-    EncodeFn enc = encode_fn();
-    SAD_REQUIRE(enc, "sa_mlp: cuTensorMapEncodeTiled unavailable");
-    SAD_REQUIRE((reinterpret_cast<uintptr_t>(feat_cl) & 15) == 0, "sa_mlp: feat_cl must be 16-byte aligned");
-    const cuuint64_t dims[2] = {(cuuint64_t)(in->NF * 64), (cuuint64_t)((long long)B * N)};
-    const cuuint64_t strides[1] = {(cuuint64_t)(in->NF * 64 * 2)};
-    const cuuint32_t box[2] = {64, 1};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(feat_cl), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SAD_REQUIRE(r == CUDA_SUCCESS, "sa_mlp: cuTensorMapEncodeTiled failed (%d)", (int)r);
-  }
 
   int dev = 0, sms = 0;
   SAD_CUDA_OK(cudaGetDevice(&dev));
   SAD_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  static thread_local unsigned configured = 0;       // bit per instance (per host thread; devices share the attribute call)
+  static thread_local unsigned configured = 0;       // bit per instance
   static thread_local int configured_dev = -1;
   if (configured_dev != dev) {
     configured = 0;
@@ -844,6 +943,13 @@ extern "C" int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* fea
   int clusters = sad_ceil_div(p.num_units, tpc);
   const int max_clusters = sms / in->CG;
   if (clusters > max_clusters) clusters = max_clusters;
+  // Few units per cluster: a fixed assignment (no scheduler round trips, and no cluster that claims units ahead of
+  // need while others idle).  Many: units are handed out dynamically, a few ahead of use.
+  p.static_sched = (long long)clusters * 8 >= p.num_units ? 1 : 0;
+  {
+    const long long fair = p.num_units / clusters;      // units per cluster if all ran equally fast
+    p.claim = (int)(fair / 6 < 1 ? 1 : (fair / 6 > 8 ? 8 : fair / 6));
+  }
   in->launch(p, clusters * in->CG, stream);
   SAD_LAUNCH_CHECK("sa_mlp_kernel");
   return SAD_OK;

@@ -54,15 +54,17 @@ class PipelinedHotPath:
         self._slots: List[_Slot] = []
         lib = _lib.load()
         dev = self.device
-        from . import modules as _modules
+        from . import modules as _modules, mlp as _mlp
         saved_policy = _modules.FPS_POLICY[0]
         _modules.FPS_POLICY[0] = fps_policy
         lib.sad_mlp_set_tiles_per_cta(int(mlp_tiles_per_cta))
+        _mlp.TILES_PER_CTA[0] = int(mlp_tiles_per_cta)
         try:
             self._capture(model, batch, n_points, feat_dim, slots, dev, warmup, lib)
         finally:
             _modules.FPS_POLICY[0] = saved_policy
             lib.sad_mlp_set_tiles_per_cta(1)
+            _mlp.TILES_PER_CTA[0] = 1
         self.launches_per_batch = self._slots[0].launches
 
     def _capture(self, model, batch, n_points, feat_dim, slots, dev, warmup, lib):

@@ -28,12 +28,14 @@ _VP = ctypes.c_void_p
 # Hand 128-row tiles to the persistent CTAs through an atomic counter (robust when other streams hold SMs).
 DYNAMIC_TILES = True
 
-# Shape-specialised SA kernel (csrc/mlp_sa.cu): True = use it whenever an instance matches the stage, "single" = prefer
-# the instances that run without a CTA pair, False = always the general kernel (tests compare the two).
+# Shape-specialised SA kernel (csrc/mlp_sa.cu): True = use it whenever an instance matches the stage, "single" / "pair"
+# = prefer the instances that run on single CTAs / CTA pairs, False = always the general kernel (tests compare them).
 FAST_SA = [True]
 # Scheduling hint for the fused-MLP launches issued from Python (never changes results): minimum 128-row tiles per
 # CTA.  engine.PipelinedHotPath raises it while it captures its graphs (narrower grids for the small stages).
 TILES_PER_CTA = [1]
+# tools: skip the (B,C,P) f32 output of the specialised SA stages (only the channel-last bf16 twin is written)
+_WANT_CF = [True]
 
 
 class _SchedWords:
@@ -186,7 +188,7 @@ def _fast_instance(mlp: "PreparedMLP", layout: Layout, S: int, P: int) -> int:
         return -1
     h1, h2, c3 = mlp.c_out
     return int(_lib.load().sad_sa_mlp_query(layout.c0, h1, h2, c3, S, len(layout.extra_cols), 1,
-                                            1 if FAST_SA[0] == "single" else 0))
+                                            {"single": 1, "pair": 2}.get(FAST_SA[0], 0)))
 
 
 def _packed_fast(mlp: "PreparedMLP", inst: int, layout: Layout):
@@ -206,26 +208,33 @@ def _packed_fast(mlp: "PreparedMLP", inst: int, layout: Layout):
         img = np.zeros(nbytes, dtype=np.uint8)
         _lib.check(lib.sad_sa_mlp_pack(inst, _VP(W1.ctypes.data), int(W1.shape[1]), _VP(perm_feat.ctypes.data),
                                        _VP(perm_sp.ctypes.data), _VP(b1.ctypes.data), _VP(W2.ctypes.data),
-                                       _VP(W3.ctypes.data), int(c3), _VP(img.ctypes.data)), "sa_mlp_pack")
+                                       _VP(b2.ctypes.data), _VP(W3.ctypes.data), int(c3), _VP(img.ctypes.data)),
+                   "sa_mlp_pack")
         b3p = np.zeros(256, dtype=np.float32)
         b3p[:c3] = b3
-        mlp._packed[key] = (torch.from_numpy(img).to(dev), torch.from_numpy(b2).to(dev), torch.from_numpy(b3p).to(dev))
+        mlp._packed[key] = (torch.from_numpy(img).to(dev), torch.from_numpy(b3p).to(dev))
     return mlp._packed[key]
 
 
 def fused_sa_fast(mlp: "PreparedMLP", inst: int, layout: Layout, B, N, P, feat_cl, xyz, new_xyz, idx, radius, radius_t,
                   normalize_xyz, extra, want_cf=True, want_cl=True):
     """Launcher of sad_sa_mlp_fwd -> (out_cf (B,C3,P) f32 | None, out_cl (B,P,C3) bf16 | None)."""
-    img, b2, b3p = _packed_fast(mlp, inst, layout)
+    img, b3p = _packed_fast(mlp, inst, layout)
     dev = img.device
     c3 = mlp.c_out[-1]
     out_cf = torch.empty((B, c3, P), dtype=torch.float32, device=dev) if want_cf else None
     out_cl = torch.empty((B, P, c3), dtype=torch.bfloat16, device=dev) if want_cl else None
     sched = _SCHED.take(dev)
+    E = len(layout.extra_cols)
+    xyzw = None
     with torch.cuda.device(dev):
+        if E <= 1:      # gathered source of the special K step as one 16-byte row per point
+            xyzw = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+            _lib.check(_lib.load().sad_pack_xyzw(B, N, _ptr(xyz), _ptr(extra if E else None), _ptr(xyzw), _stream(xyzw)),
+                       "pack_xyzw")
         rc = _lib.load().sad_sa_mlp_fwd(
-            inst, B, N, P, _ptr(feat_cl), _ptr(xyz), _ptr(new_xyz), _ptr(idx), float(radius), _ptr(radius_t),
-            int(bool(normalize_xyz)), _ptr(extra), len(layout.extra_cols), _ptr(img), _ptr(b2), _ptr(b3p), c3,
+            inst, B, N, P, _ptr(feat_cl), _ptr(xyz), _ptr(xyzw), _ptr(new_xyz), _ptr(idx), float(radius), _ptr(radius_t),
+            int(bool(normalize_xyz)), _ptr(extra), len(layout.extra_cols), _ptr(img), _ptr(b3p), c3,
             _ptr(out_cl), _ptr(out_cf), _ptr(sched), int(TILES_PER_CTA[0]), _VP(torch.cuda.current_stream(dev).cuda_stream))
     _lib.check(rc, "sa_mlp")
     return out_cf, out_cl
@@ -302,8 +311,9 @@ def sa_group_mlp(xyz, new_xyz, features, idx, radius, mlp: PreparedMLP, use_xyz=
     inst = _fast_instance(mlp, layout, S, P)
     if inst >= 0:
         out_cf, out_cl = fused_sa_fast(mlp, inst, layout, B, N, P, feat_cl, xyz, new_xyz, idx,
-                                       0.0 if radius_t is not None else float(radius), radius_t, normalize_xyz, extra)
-        return _attach(out_cf, out_cl)
+                                       0.0 if radius_t is not None else float(radius), radius_t, normalize_xyz, extra,
+                                       want_cf=_WANT_CF[0])
+        return _attach(out_cf, out_cl) if out_cf is not None else out_cl
     out_cf, out_cl = fused_mlp(mlp, layout, B, N, P, S, feat_cl=feat_cl, xyz=xyz if layout.xyz_cols else None,
                                new_xyz=new_xyz, idx=idx, radius=0.0 if radius_t is not None else float(radius),
                                radius_t=radius_t, normalize_xyz=normalize_xyz, extra=extra)

@@ -163,28 +163,32 @@ SAD_API int sad_mlp_pack_weights(const float* W, int cout, int cin, const int32_
  *                  handed to the persistent CTAs dynamically; NULL = static round-robin
  * bf16 operands, fp32 accumulate/bias/ReLU/max (tolerance 2e-2 vs the fp32 oracle). */
 /* ---- a6, shape-specialised fast path (csrc/mlp_sa.cu): the pooled SA stages of the detector, compiled per shape.
- * All weights pinned in shared memory (CTA pairs / cta_group::2 for the 128-wide stages), feature rows by TMA
- * gather4, 2-4 tiles in flight in TMEM.  Same math and tolerance as sad_shared_mlp_fwd; layer-1 and hidden biases
+ * All weights pinned in shared memory (CTA pairs / cta_group::2 for the 128-wide stages), feature rows by cp.async
+ * straight into the swizzled operand layout, 2-4 tiles in flight in TMEM.  Same math and tolerance as sad_shared_mlp_fwd; layer-1 and hidden biases
  * are rounded to bf16 where they ride on a constant-1 K column.
  *   sad_sa_mlp_query        instance id for (C0 gathered channels, hidden widths h1 == h2, c3 outputs, nsample S,
  *                           E <= 4 scalar features, relative xyz present), or -1: use sad_shared_mlp_fwd.
- *                           single_cta != 0 prefers an instance that runs without a CTA pair (tools / tests).
+ *                           prefer: 0 = the library's choice, 1 = a single-CTA instance, 2 = a CTA-pair instance,
+ *                           where one exists (tools / tests).
  *   sad_sa_mlp_image_bytes  size of the packed weight image of an instance
- *   sad_sa_mlp_pack         HOST: fp32 W1 (h x cin1), W2 (h x h), W3 (c3 x h), b1 -> image.  perm_feat[C0]: source
+ *   sad_sa_mlp_pack         HOST: fp32 W1 (h x cin1), W2 (h x h), W3 (c3 x h), b1, b2 -> image.  perm_feat[C0]: source
  *                           column of gathered K index k (-1 = zero); perm_sp[7]: source columns of dx,dy,dz,e0..e3
+ *   sad_pack_xyzw           (B,N,3) xyz (+ optional (B,N) scalar feature) -> (B,N) float4 {x,y,z,f}: optional gathered
+ *                           source of sad_sa_mlp_fwd (`xyzw`, needs E <= 1): one 16-byte load per neighbour row
  *   sad_sa_mlp_fwd          launch.  bias3_padded has the instance's full output width (zero padded);
  *                           npoint P must be a power of two; `sched` = 2 device int32 that are ZERO before the first
  *                           launch that uses them (the kernel re-zeroes them when it finishes; launches sharing the
  *                           words must be stream-ordered); tiles_per_cta = scheduling hint (>= 1, never changes
  *                           results): minimum tiles per CTA, i.e. a narrower grid for small stages. */
-SAD_API int sad_sa_mlp_query(int C0, int h1, int h2, int c3, int S, int E, int has_xyz, int single_cta);
+SAD_API int sad_sa_mlp_query(int C0, int h1, int h2, int c3, int S, int E, int has_xyz, int prefer);
 SAD_API long long sad_sa_mlp_image_bytes(int instance);
 SAD_API int sad_sa_mlp_pack(int instance, const float* W1, int cin1, const int32_t* perm_feat, const int32_t* perm_sp,
-                            const float* b1, const float* W2, const float* W3, int c3, void* out_image);
-SAD_API int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* feat_cl, const float* xyz, const float* new_xyz,
-                           const int32_t* idx, float radius, const float* radius_t, int normalize_xyz, const float* extra,
-                           int E, const void* w_image, const float* bias2, const float* bias3_padded, int c3,
-                           void* out_cl_bf16, float* out_cf_f32, int* sched, int tiles_per_cta, sad_stream_t stream);
+                            const float* b1, const float* W2, const float* b2, const float* W3, int c3, void* out_image);
+SAD_API int sad_pack_xyzw(int B, int N, const float* xyz, const float* extra1, void* out_xyzw, sad_stream_t stream);
+SAD_API int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* feat_cl, const float* xyz, const void* xyzw,
+                           const float* new_xyz, const int32_t* idx, float radius, const float* radius_t,
+                           int normalize_xyz, const float* extra, int E, const void* w_image, const float* bias3_padded, int c3, void* out_cl_bf16,
+                           float* out_cf_f32, int* sched, int tiles_per_cta, sad_stream_t stream);
 
 /* Scheduling hint for the calling thread's sad_shared_mlp_fwd launches (never changes results): at least `tiles`
  * 128-row tiles per CTA, i.e. a narrower grid for the small stages.  1 (default) = one CTA per SM whenever there are

@@ -42,9 +42,9 @@ CASES = [
     ("sa1-deep", True, 2, 20000, 2048, 64, 1, [64, 64, 128], 0.3, False),           # ~28 tiles per CTA
     ("sa2-single-small", "single", 2, 2048, 128, 32, 128, [128, 128, 256], 0.6, False),
     ("sa2-single-deep", "single", 4, 2048, 1024, 32, 128, [128, 128, 256], 0.6, False),
-    ("sa2-pair-small", True, 2, 2048, 128, 32, 128, [128, 128, 256], 0.6, False),
-    ("sa2-pair-odd", True, 1, 2048, 4, 32, 128, [128, 128, 256], 0.6, False),       # one tile: the pair's second CTA idles
-    ("sa2-pair-deep", True, 4, 2048, 1024, 32, 128, [128, 128, 256], 0.6, False),
+    ("sa2-pair-small", "pair", 2, 2048, 128, 32, 128, [128, 128, 256], 0.6, False),
+    ("sa2-pair-odd", "pair", 1, 2048, 4, 32, 128, [128, 128, 256], 0.6, False),       # one tile: the pair's second CTA idles
+    ("sa2-pair-deep", "pair", 4, 2048, 1024, 32, 128, [128, 128, 256], 0.6, False),
     ("sa3-pair-small", True, 1, 1024, 64, 16, 256, [128, 128, 256], 0.9, False),
     ("sa3-pair-deep", True, 8, 1024, 512, 16, 256, [128, 128, 256], 0.9, False),
     ("agg-pair", True, 2, 1024, 128, 16, 256, [128, 128, 128], 0.3, True),          # 128 outputs zero-padded, per-cluster radius

@@ -11,7 +11,7 @@ from sad_b200 import mlp as M, _lib
 lib = _lib.load()
 dump = lib.sad_sa_profile_dump
 dump.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-ROLES = ["epi0", "gath", "mma ", "prod", "epi4"]
+ROLES = ["epi0", "gath", "mmaA", "prod", "epi4", "mmaB"]
 
 
 def layers(ch):
@@ -20,9 +20,27 @@ def layers(ch):
                              for ci, co in zip(ch[:-1], ch[1:])])
 
 
+dbg = torch.zeros(64, dtype=torch.int64).pin_memory()
+lib.sad_sa_debug_buffer.argtypes = [ctypes.c_void_p]
+lib.sad_sa_debug_buffer(dbg.data_ptr())
+
+
+def report_dbg():
+    n = int(dbg[63]) & 0xFFFFFFFF
+    print(f"barrier timeouts reported: {n}; misc base offsets: see Misc layout")
+    for i in range(min(n, 15)):
+        a, b = int(dbg[4 * i]), int(dbg[4 * i + 1])
+        print(f"  block {a >> 32} thread {a & 0xFFFFFFFF} (warp {(a & 0xFFFFFFFF) >> 5}) bar smem addr {(b >> 32) & 0xFFFFFFFF:#x} parity {b & 0xFFFFFFFF}")
+
+
 def timeline(tag, fn, first=0, count=120):
-    fn(); torch.cuda.synchronize()
-    log = np.zeros((5, 8192), dtype=np.int64); n = np.zeros(5, dtype=np.int32)
+    try:
+        fn(); torch.cuda.synchronize()
+    except Exception as e:
+        print("FAILED:", str(e).splitlines()[0])
+        report_dbg()
+        raise
+    log = np.zeros((6, 8192), dtype=np.int64); n = np.zeros(6, dtype=np.int32)
     dump(log.ctypes.data, n.ctypes.data)
     fn(); torch.cuda.synchronize()
     dump(log.ctypes.data, n.ctypes.data)

@@ -43,6 +43,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tpc", type=int, default=1)
     ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--no-cf", action="store_true")
     args = ap.parse_args()
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
@@ -50,6 +51,7 @@ def main():
         peak = 1400.0
     dev, B = "cuda", args.batch
     M.TILES_PER_CTA[0] = args.tpc
+    M._WANT_CF[0] = not args.no_cf
     from sad_b200 import _lib
     _lib.load().sad_mlp_set_tiles_per_cta(args.tpc)
     rows = []
@@ -65,15 +67,15 @@ def main():
             feat._sad_cl = M.to_cl_bf16(feat)
         m = layers([C + 3] + hid)
         flops = 2.0 * B * P * S * sum(a * b for a, b in zip([C + 3] + hid[:-1], hid))
-        for mode in (False, "single", True):
+        seen = set()
+        for mode in (False, "single", "pair"):
             M.FAST_SA[0] = mode
             inst = M._fast_instance(m, M.sa_layout(C, True), S, P) if mode else -1
-            if mode and inst < 0:
+            if mode and (inst < 0 or inst in seen):
                 continue
-            if mode == "single" and inst not in (3,):
-                continue
+            seen.add(inst)
             med, best = t(lambda: M.sa_group_mlp(xyz, new_xyz, feat, idx, 0.3, m))
-            rows.append({"stage": name, "kernel": {False: "general", "single": "fast-1cta", True: f"fast(inst {inst})"}[mode],
+            rows.append({"stage": name, "kernel": "general" if not mode else f"fast(inst {inst})",
                          "us": round(med, 1), "best_us": round(best, 1), "GFLOP": round(flops / 1e9, 2),
                          "TFLOPs": round(flops / med / 1e6, 1), "frac_of_peak": round(flops / med / 1e6 / peak, 3)})
             print(rows[-1], flush=True)
