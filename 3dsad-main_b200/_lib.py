@@ -21,6 +21,7 @@ SIGNATURES = {
     "sad_fps_force_cluster_size": [_c_int],
     "sad_launch_count": [],
     "sad_furthest_point_sample_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
+    "sad_furthest_point_sample_prefix_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_gather_operation_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_gather_operation_bwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_ball_query_fwd": [_c_int, _c_int, _c_int, _c_float, _c_int, _vp, _vp, _vp, _vp],
@@ -43,6 +44,7 @@ SIGNATURES = {
     "sad_shared_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _c_float, _vp,
                            _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp],
     "sad_sa_mlp_query": [_c_int] * 8,
+    "sad_sa_mlp_instance_info": [_c_int, _vp],
     "sad_sa_mlp_image_bytes": [_c_int],
     "sad_sa_mlp_pack": [_c_int, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp],
     "sad_pack_xyzw": [_c_int, _c_int, _vp, _vp, _vp, _vp],

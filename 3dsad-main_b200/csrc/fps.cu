@@ -35,7 +35,7 @@ __device__ __forceinline__ void st_async_v4(uint32_t raddr, float a, float b, fl
 
 template <int T, int P, int CS>
 __global__ void __launch_bounds__(T, 1)
-fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict__ out) {
+fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict__ out, const int* __restrict__ skip) {
   constexpr int NW = T / 32;
   constexpr int NSLOT = CS * NW;
   constexpr int RPL = (NSLOT + 31) / 32;                 // records per lane in the final reduce
@@ -47,6 +47,9 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict
   const uint32_t rank = (CS > 1) ? cluster_ctarank() : 0u;
   const int g = (int)rank * NW + warp;                    // slot id == ascending index range id
   const int b = blockIdx.x / CS;
+  // prefix-ordered input whose guard passed (sad_furthest_point_sample_prefix_fwd): the answer is already written.
+  // Uniform over the scene's cluster, and before its first cluster barrier.
+  if (skip != nullptr && skip[b] != 0) return;
   const float* pts = xyz + (size_t)b * N * 3;
   int32_t* o = out + (size_t)b * npoint;
 
@@ -147,7 +150,7 @@ fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict
 }
 
 template <int T, int P, int CS>
-int launch_fps(int B, int N, int npoint, const float* xyz, int32_t* idx, cudaStream_t stream) {
+int launch_fps(int B, int N, int npoint, const float* xyz, int32_t* idx, const int* skip, cudaStream_t stream) {
   auto kern = fps_kernel<T, P, CS>;
   const size_t smem = (size_t)P * T * sizeof(float4);
   static thread_local int configured_dev = -1;   // per (T,P,CS) instantiation and thread
@@ -170,7 +173,7 @@ int launch_fps(int B, int N, int npoint, const float* xyz, int32_t* idx, cudaStr
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (CS > 1) ? 1 : 0;
-  SAD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, xyz, N, npoint, idx));
+  SAD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, xyz, N, npoint, idx, skip));
   sad_count_launch(1);
   return SAD_OK;
 }
@@ -184,11 +187,11 @@ int round_p(int p) {
 }
 
 template <int T, int CS>
-int dispatch_p(int P, int B, int N, int npoint, const float* xyz, int32_t* idx, cudaStream_t s) {
+int dispatch_p(int P, int B, int N, int npoint, const float* xyz, int32_t* idx, const int* skip, cudaStream_t s) {
   switch (P) {
 #define SAD_FPS_CASE(PP) \
   case PP:               \
-    return launch_fps<T, PP, CS>(B, N, npoint, xyz, idx, s);
+    return launch_fps<T, PP, CS>(B, N, npoint, xyz, idx, skip, s);
     SAD_FPS_CASE(1)
     SAD_FPS_CASE(2)
     SAD_FPS_CASE(3)
@@ -210,16 +213,16 @@ int dispatch_p(int P, int B, int N, int npoint, const float* xyz, int32_t* idx, 
 }
 
 // Large scenes only: wider CTAs at the maximum cluster size.
-int dispatch_big(int T, int P, int B, int N, int npoint, const float* xyz, int32_t* idx, cudaStream_t s) {
+int dispatch_big(int T, int P, int B, int N, int npoint, const float* xyz, int32_t* idx, const int* skip, cudaStream_t s) {
   if (T == 256) {
     switch (P) {
-      case 24: return launch_fps<256, 24, 16>(B, N, npoint, xyz, idx, s);
-      case 32: return launch_fps<256, 32, 16>(B, N, npoint, xyz, idx, s);
-      case 40: return launch_fps<256, 40, 16>(B, N, npoint, xyz, idx, s);
-      case 48: return launch_fps<256, 48, 16>(B, N, npoint, xyz, idx, s);
+      case 24: return launch_fps<256, 24, 16>(B, N, npoint, xyz, idx, skip, s);
+      case 32: return launch_fps<256, 32, 16>(B, N, npoint, xyz, idx, skip, s);
+      case 40: return launch_fps<256, 40, 16>(B, N, npoint, xyz, idx, skip, s);
+      case 48: return launch_fps<256, 48, 16>(B, N, npoint, xyz, idx, skip, s);
     }
   } else if (T == 512 && P == 25) {
-    return launch_fps<512, 25, 16>(B, N, npoint, xyz, idx, s);
+    return launch_fps<512, 25, 16>(B, N, npoint, xyz, idx, skip, s);
   }
   sad_set_error("fps: no large-scene kernel for T=%d P=%d", T, P);
   return SAD_EUNSUPPORTED;
@@ -236,9 +239,7 @@ __global__ void ablate_strided_idx_plain(int N, int npoint, int32_t* idx) {
 static thread_local int g_force_cs = 0;
 extern "C" void sad_fps_force_cluster_size(int cs) { g_force_cs = cs; }
 
-extern "C" int sad_furthest_point_sample_fwd(int B, int N, int npoint, const float* xyz, int32_t* idx,
-                                             sad_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int fps_plain(int B, int N, int npoint, const float* xyz, int32_t* idx, const int* skip, cudaStream_t stream) {
   SAD_REQUIRE(B >= 0 && N >= 1 && npoint >= 1, "furthest_point_sample: bad sizes B=%d N=%d npoint=%d", B, N,
               npoint);
   if (B == 0) return SAD_OK;
@@ -257,9 +258,9 @@ extern "C" int sad_furthest_point_sample_fwd(int B, int N, int npoint, const flo
   if ((long long)N > 16LL * T * PMAX) {   // > 98304 points: wider CTAs, cluster of 16
     if ((long long)N <= 16LL * 256 * PMAX) {
       return dispatch_big(256, round_p(sad_ceil_div(N, 16 * 256)) < 24 ? 24 : round_p(sad_ceil_div(N, 16 * 256)), B,
-                          N, npoint, xyz, idx, stream);
+                          N, npoint, xyz, idx, skip, stream);
     }
-    return dispatch_big(512, 25, B, N, npoint, xyz, idx, stream);
+    return dispatch_big(512, 25, B, N, npoint, xyz, idx, skip, stream);
   }
   int cs = g_force_cs;
   if (cs == 0) {
@@ -275,10 +276,75 @@ extern "C" int sad_furthest_point_sample_fwd(int B, int N, int npoint, const flo
   while (cs < 16 && (long long)cs * T * PMAX < N) cs <<= 1;   // capacity: P <= 48 points / thread
   const int P = round_p(sad_ceil_div(N, (long long)cs * T));
   switch (cs) {
-    case 1: return dispatch_p<T, 1>(P, B, N, npoint, xyz, idx, stream);
-    case 2: return dispatch_p<T, 2>(P, B, N, npoint, xyz, idx, stream);
-    case 4: return dispatch_p<T, 4>(P, B, N, npoint, xyz, idx, stream);
-    case 8: return dispatch_p<T, 8>(P, B, N, npoint, xyz, idx, stream);
-    default: return dispatch_p<T, 16>(P, B, N, npoint, xyz, idx, stream);
+    case 1: return dispatch_p<T, 1>(P, B, N, npoint, xyz, idx, skip, stream);
+    case 2: return dispatch_p<T, 2>(P, B, N, npoint, xyz, idx, skip, stream);
+    case 4: return dispatch_p<T, 4>(P, B, N, npoint, xyz, idx, skip, stream);
+    case 8: return dispatch_p<T, 8>(P, B, N, npoint, xyz, idx, skip, stream);
+    default: return dispatch_p<T, 16>(P, B, N, npoint, xyz, idx, skip, stream);
   }
+}
+
+extern "C" int sad_furthest_point_sample_fwd(int B, int N, int npoint, const float* xyz, int32_t* idx,
+                                             sad_stream_t stream) {
+  return fps_plain(B, N, npoint, xyz, idx, nullptr, (cudaStream_t)stream);
+}
+
+// ---- a1 over PREFIX-ORDERED input (SURVEY.md H3 side note) ---------------------------------------
+// If row k of `xyz` is the k-th pick of a farthest-point sampling of some superset (the previous SA stage's new_xyz),
+// then sampling its first rows again returns the identity: by induction the min-distances of the rows are the
+// superset's, the k-th pick of the superset is row k and every smaller row has min-distance 0 -- UNLESS a pick itself
+// had min-distance 0 (it duplicates an earlier pick: the superset ran out of distinct points), where the lowest-index
+// rule picks differently in the two orders.  The guard below checks exactly that, with the contract's arithmetic
+// (d2(row k, row j) == 0 for some j < k < npoint), per scene; scenes that pass get arange, the others run the sampler.
+namespace {
+__global__ void __launch_bounds__(1024) fps_prefix_guard_kernel(const float* __restrict__ xyz, int N, int npoint,
+                                                                int32_t* __restrict__ out, int* __restrict__ flags) {
+  extern __shared__ __align__(16) float4 s_p[];      // the first npoint rows
+  __shared__ int s_bad;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* pts = xyz + (size_t)b * N * 3;
+  if (tid == 0) s_bad = 0;
+  for (int k = tid; k < npoint; k += blockDim.x) s_p[k] = make_float4(__ldg(pts + 3 * k), __ldg(pts + 3 * k + 1), __ldg(pts + 3 * k + 2), 0.f);
+  __syncthreads();
+  // row k against every earlier row; a thread takes rows r and npoint - 1 - r (equal work per thread)
+  int bad = 0;
+  for (int r = tid; 2 * r < npoint; r += blockDim.x) {
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const int k = side == 0 ? r : npoint - 1 - r;
+      if (side == 1 && k == r) continue;
+      const float4 q = s_p[k];
+      for (int j = 0; j < k; ++j) {
+        const float4 a = s_p[j];
+        bad |= (sqdist(q.x, q.y, q.z, a.x, a.y, a.z) == 0.f) ? 1 : 0;
+      }
+    }
+  }
+  if (bad) s_bad = 1;
+  __syncthreads();
+  const int ok = s_bad == 0;
+  if (tid == 0) flags[b] = ok;
+  if (ok)
+    for (int k = tid; k < npoint; k += blockDim.x) out[(size_t)b * npoint + k] = k;
+}
+}  // namespace
+
+extern "C" int sad_furthest_point_sample_prefix_fwd(int B, int N, int npoint, const float* xyz, int32_t* idx, int* flags,
+                                                    sad_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SAD_REQUIRE(B >= 0 && N >= 1 && npoint >= 1 && npoint <= N, "furthest_point_sample_prefix: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
+  if (B == 0) return SAD_OK;
+  SAD_REQUIRE(xyz && idx && flags, "furthest_point_sample_prefix: null pointer");
+  if (npoint > 8192) return fps_plain(B, N, npoint, xyz, idx, nullptr, stream);      // guard table would not fit: plain sampler
+  const size_t smem = (size_t)npoint * sizeof(float4);
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  SAD_CUDA_OK(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    SAD_CUDA_OK(cudaFuncSetAttribute(fps_prefix_guard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
+    configured_dev = dev;
+  }
+  fps_prefix_guard_kernel<<<B, 1024, smem, stream>>>(xyz, N, npoint, idx, flags);
+  SAD_LAUNCH_CHECK("fps_prefix_guard_kernel");
+  return fps_plain(B, N, npoint, xyz, idx, flags, stream);
 }

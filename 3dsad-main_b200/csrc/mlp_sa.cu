@@ -815,6 +815,13 @@ extern "C" int sad_sa_mlp_query(int C0, int h1, int h2, int c3, int S, int E, in
   return first;
 }
 
+extern "C" int sad_sa_mlp_instance_info(int instance, int* out5) {
+  const Instance* in = instance_by_id(instance);
+  SAD_REQUIRE(in && out5, "sa_mlp_instance_info: unknown instance %d", instance);
+  out5[0] = in->CG; out5[1] = in->NF; out5[2] = in->H; out5[3] = in->C3; out5[4] = in->S;
+  return SAD_OK;
+}
+
 extern "C" long long sad_sa_mlp_image_bytes(int instance) {
   const Instance* in = instance_by_id(instance);
   return in ? (long long)in->CG * in->wbytes : -1;

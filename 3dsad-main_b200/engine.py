@@ -114,11 +114,19 @@ class PipelinedHotPath:
 
     @torch.no_grad()
     def submit_device(self, xyz, feat, size, after: Optional[torch.cuda.Event] = None, to_host: bool = False) -> int:
-        """Inputs already resident in HBM: device-to-device copy into the slot, then the graph."""
+        """Inputs already resident in HBM: device-to-device copy into the slot, then the graph.  The slot's stream is
+        ordered after the caller's current stream (or after `after`, an event the caller recorded once the inputs were
+        valid), and the inputs are kept alive for the copy (record_stream), so tensors produced just before the call
+        or dropped right after it are safe."""
         i, s = self._acquire()
+        if after is None:
+            after = torch.cuda.Event()
+            after.record(torch.cuda.current_stream(self.device))
+        for t in (xyz, feat, size):
+            if t.is_cuda:
+                t.record_stream(s.stream)
         with torch.cuda.stream(s.stream):
-            if after is not None:
-                s.stream.wait_event(after)
+            s.stream.wait_event(after)
             s.xyz.copy_(xyz, non_blocking=True)
             s.feat.copy_(feat, non_blocking=True)
             s.size.copy_(size, non_blocking=True)

@@ -49,10 +49,23 @@ class SharedMLP(nn.Module):
             self.convs.append(nn.Conv2d(cin, cout, kernel_size=1, bias=not bn))
             self.bns.append(nn.BatchNorm2d(cout) if bn else nn.Identity())
         self._folded = None
+        self._folded_key = None
 
     def train(self, mode: bool = True):
         self._folded = None
         return super().train(mode)
+
+    def _fold_key(self):
+        """Identity of everything the folded weights depend on: device / dtype moves, load_state_dict, optimizer or
+        in-place updates and BN-statistic changes all change a data pointer or a version counter."""
+        key = []
+        for conv, bn in zip(self.convs, self.bns):
+            ts = [conv.weight, conv.bias]
+            if isinstance(bn, nn.BatchNorm2d):
+                ts += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+            for t in ts:
+                key.append(None if t is None else (t.data_ptr(), t._version, t.device, t.dtype))
+        return tuple(key)
 
     @torch.no_grad()
     def load_folded(self, layers):
@@ -72,8 +85,11 @@ class SharedMLP(nn.Module):
 
     @torch.no_grad()
     def folded(self) -> List[Tuple[torch.Tensor, torch.Tensor]]:
-        """Eval-mode BN folded into (W, b) per layer (cached until train()/load_folded())."""
-        if self._folded is None:
+        """Eval-mode BN folded into (W, b) per layer.  Cached, and rebuilt whenever a parameter / buffer it was
+        derived from has changed (see _fold_key); graphs captured by engine.PipelinedHotPath bake the weights of
+        capture time in and must be re-captured after a weight update."""
+        key = self._fold_key()
+        if self._folded is None or self._folded_key != key:
             out = []
             for conv, bn in zip(self.convs, self.bns):
                 W = conv.weight.detach().flatten(1).float()
@@ -84,6 +100,7 @@ class SharedMLP(nn.Module):
                     b = (b - bn.running_mean) * s + bn.bias.detach()
                 out.append((W.contiguous(), b.contiguous()))
             self._folded = _mlp.prepare_layers(out)
+            self._folded_key = key
         return self._folded
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -124,6 +141,9 @@ class PointnetSAModuleVotes(nn.Module):
         super().__init__()
         self.npoint, self.radius, self.nsample = npoint, radius, nsample
         self.use_xyz, self.normalize_xyz = use_xyz, normalize_xyz
+        # set by a caller that feeds this stage the previous stage's new_xyz (farthest-point order): the sampling is
+        # then the identity behind a device-side duplicate guard (ops.furthest_point_sample prefix_ordered)
+        self.prefix_ordered_input = False
         ch = list(mlp)
         if use_xyz:
             ch[0] += 3
@@ -135,7 +155,7 @@ class PointnetSAModuleVotes(nn.Module):
         if grid is None and inds is None and xyz.shape[1] >= ops.GRID_MIN_POINTS:
             grid = ops.build_scene_grid(xyz)
         if inds is None:
-            inds = ops.furthest_point_sample(xyz, self.npoint, grid, FPS_POLICY[0])
+            inds = ops.furthest_point_sample(xyz, self.npoint, grid, FPS_POLICY[0], self.prefix_ordered_input)
         if new_xyz is None:
             new_xyz = _gather_xyz(xyz, inds)
         if radius_t is not None:
@@ -196,6 +216,8 @@ class Pointnet2Backbone(nn.Module):
         self.sa4 = PointnetSAModuleVotes(*c["sa4"], mlp=[256] + ch["sa4"][1:], bn=bn)
         self.fp1 = PointnetFPModule(ch["fp1"], bn=bn)
         self.fp2 = PointnetFPModule(ch["fp2"], bn=bn)
+        for m in (self.sa2, self.sa3, self.sa4):
+            m.prefix_ordered_input = True
 
     overlap_geometry = True     # run the coordinate-only chain (FPS, three_nn) on a side stream
 
@@ -233,7 +255,8 @@ class Pointnet2Backbone(nn.Module):
         geo_b.wait_event(ev)
         with torch.cuda.stream(geo_b):
             for name in ("sa2", "sa3", "sa4"):
-                inds = ops.furthest_point_sample(x, getattr(self, name).npoint)
+                # x is the previous stage's new_xyz, i.e. already in farthest-point order (SURVEY H3 side note)
+                inds = ops.furthest_point_sample(x, getattr(self, name).npoint, None, "latency", True)
                 x = _gather_xyz(x, inds)
                 ev = torch.cuda.Event()
                 ev.record(geo_b)

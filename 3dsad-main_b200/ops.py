@@ -107,7 +107,7 @@ class FurthestPointSampling(Function):
     ("latency": a cluster of SMs per scene, "throughput": one SM per scene) -- never the result."""
 
     @staticmethod
-    def forward(ctx, xyz, npoint, grid=None, policy="latency"):
+    def forward(ctx, xyz, npoint, grid=None, policy="latency", prefix_ordered=False):
         _req(xyz, "xyz", torch.float32, 3, 3)
         B, N, _ = xyz.shape
         npoint = int(npoint)
@@ -115,6 +115,15 @@ class FurthestPointSampling(Function):
             raise ValueError("furthest_point_sample: need N >= 1 and npoint >= 1")
         lib = _lib.load()
         out = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+        if prefix_ordered and npoint <= N:
+            # xyz is in farthest-point order already (the previous stage's new_xyz): identity behind a device-side
+            # duplicate guard, the sampler only for scenes that fail it -- same result either way
+            flags = torch.empty((B,), dtype=torch.int32, device=xyz.device)
+            with torch.cuda.device(xyz.device):
+                _lib.check(lib.sad_furthest_point_sample_prefix_fwd(B, N, npoint, _p(xyz), _p(out), _p(flags),
+                                                                    _stream(xyz)), "furthest_point_sample_prefix")
+            ctx.mark_non_differentiable(out)
+            return out
         if grid is None and GRID_MIN_POINTS <= N <= lib.sad_fps_grid_max_points():
             grid = SceneGrid(xyz)
         with torch.cuda.device(xyz.device):
@@ -131,7 +140,7 @@ class FurthestPointSampling(Function):
 
     @staticmethod
     def backward(ctx, grad=None):
-        return None, None, None, None
+        return None, None, None, None, None
 
 
 class GatherOperation(Function):

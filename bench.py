@@ -15,7 +15,9 @@ scenes, no data-path collective).  metric = scenes/s, whole job.
   e2e   : the same metric through PipelinedHotPath.submit_host / result with HOST (pinned)
           buffers: H2D of xyz/features/sizes and D2H of the cluster centres + features inside
           the timed region, host wall clock, every result read on the host.
-  roofline     : dominant kernel of the step, measured live with CUDA events (serial, one stream).
+  roofline     : the fused gather + MLP + max-pool launches (tensor roofline; they own the largest share of the step's
+                 SM-time), measured live with CUDA events; `fps` = the sampling chain in picks/s; `hbm_kernels` = the
+                 grouping / interpolation kernels against the HBM roofline at B = 64 / 256.
   cpu_baseline : the oracle's C/OpenMP port + NumPy MLP ("port") on the box's host cores,
                  bounded sample, rank 0 at N=1 only.
   --impl reference : the reference arm.  The mounted reference is a README (no code), so
@@ -41,6 +43,17 @@ B_PER_GPU = 8
 N_POINTS = 40000
 WORKLOAD = "configs[1]: VoteNet-style backbone (4 SA + 2 FP) + voting + size-adaptive vote aggregation, " \
            "B=8 x 40k-point synthetic ScanNet-shape (surface) scenes per GPU"
+
+
+def workload_config(n_gpus):
+    """`config` of the JSON line: the workload only, identical in both arms (what differs between the arms -- pipeline
+    depth, FPS scheduling, dtypes of the MLP -- is in `run`)."""
+    return {"workload": WORKLOAD, "scenes_per_gpu_per_step": B_PER_GPU, "points_per_scene": N_POINTS,
+            "scene_kind": "surface (floor + walls + 12 boxes, 5 mm noise), seeded", "input_feature": "height (1 channel)",
+            "layers": "SA1 2048x64 r0.2 [4,64,64,128] | SA2 1024x32 r0.4 [131,128,128,256] | SA3 512x16 r0.8 [259,128,128,256] | "
+                      "SA4 256x16 r1.2 [259,128,128,256] | FP1,FP2 [512,256,256] | vote [256,256,256,259] | "
+                      "agg 256x16 adaptive radius [259,128,128,128]",
+            "parallelism": f"scene-data-parallel x{n_gpus}, no collective"}
 
 
 def host_threads():
@@ -105,7 +118,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(times), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference mount is README-only; CPU oracle port is the reference path"},
+        "config": workload_config(args.gpus),
+        "run": {"note": "reference mount is README-only; the CPU oracle port (C/OpenMP + NumPy MLP, fp32) is the reference path",
+                "fps_threads": f"FPS parallelises over scenes only: {n_scenes} of the {threads} host threads busy in the dominant phase"},
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -200,6 +215,19 @@ def call_cost(name, a):
     if name == "sad_cf_to_cl_bf16":
         B, C, N = v[:3]
         return B * C * N * 6, 0
+    if name == "sad_sa_mlp_fwd":
+        # specialised fused SA stage: (inst, B, N, P, feat_cl, xyz, xyzw, new_xyz, idx, radius, radius_t, norm, extra, E, ...)
+        from sad_b200 import _lib as _L
+        import ctypes as _ct
+        info = (_ct.c_int * 5)()
+        _L.load().sad_sa_mlp_instance_info(int(a[0]), info)
+        _, NF, H, _, S = list(info)
+        B, N, P, E, c3 = v[1], v[2], v[3], v[13], v[16]
+        rows = B * P * S
+        cin0 = NF * 64 + 3 + E
+        flops = 2 * rows * (cin0 * H + H * H + H * c3)
+        nbytes = rows * 4 + B * min(N, P * S) * (NF * 128 + 12 + E * 4) + B * P * c3 * 6
+        return nbytes, flops
     if name == "sad_shared_mlp_fwd":
         # fused stage: bytes = idx + distinct gathered rows (bf16) + outputs; flops = 2*rows*sum(Cin*Cout)
         B, N, P, S, C0, C1in, E, nl = v[0], v[1], v[2], v[3], v[5], v[7], v[15], v[16]
@@ -218,17 +246,26 @@ def build_roofline(model, xyz, feat, size, reps=3):
     from sad_b200 import _lib
     peaks = measured_peaks()
     agg = {}
+    stages = {}
     for _ in range(reps):
         with _lib.CallProfiler() as prof:
             with torch.no_grad():
+                torch.cuda._sleep(60000000)      # ~30 ms: every launch of the forward is queued before the first one runs
                 model(xyz, feat, size)
         for name, a, ms in prof.rows():
             name = name.replace("_grid_policy_fwd", "_grid_fwd")      # same op, explicit scheduling policy
+            name = name.replace("_prefix_fwd", "_fwd")                # same op over prefix-ordered input
             nbytes, flops = call_cost(name, a)
             key = name.replace("sad_", "").replace("_fwd", "")
+            picks = 0
             if name in ("sad_furthest_point_sample_fwd", "sad_furthest_point_sample_grid_fwd"):
                 key += f"[N={a[1]}]"
-            d = agg.setdefault(key, {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
+                picks = int(a[2])
+            d = agg.setdefault(key, {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0, "picks": picks})
+            if flops:      # one row per fused-MLP launch, in call order (SA1..SA4, FP1, FP2, voting, aggregation)
+                sk = (name, tuple(x for x in a[:4] if isinstance(x, int)))
+                st = stages.setdefault(sk, {"ms": 0.0, "flops": flops, "order": len(stages)})
+                st["ms"] += ms / reps
             d["ms"] += ms / reps
             d["bytes"] += nbytes / reps
             d["flops"] += flops / reps
@@ -244,30 +281,111 @@ def build_roofline(model, xyz, feat, size, reps=3):
             row.update(GFLOP_per_step=round(d["flops"] / 1e9, 2), TFLOPs=round(tfs, 1),
                        tensor_frac=round(tfs / peaks["tensor"], 4))
         kernels.append(row)
-    top = kernels[0]
-    launches = max(1.0, top["launches_per_step"])
-    if "TFLOPs" in top:
-        roof = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["TFLOPs"], "peak": peaks["tensor"],
-                "unit": "TFLOP/s", "frac": top["tensor_frac"], "traffic": None, "peak_source": peaks["src"],
-                "alg_flops_per_launch": round(top["GFLOP_per_step"] * 1e9 / launches),
-                "launch_ms": round(top["ms_per_step"] / launches, 4), "note": "bf16 sustained cuBLAS peak"}
-    else:
-        roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["GBps"], "peak": peaks["hbm"], "unit": "GB/s",
-                "frac": top["hbm_frac"], "traffic": None, "peak_source": peaks["src"],
-                "alg_bytes_per_launch": round(top["alg_MB_per_step"] * 1e6 / launches),
-                "launch_ms": round(top["ms_per_step"] / launches, 4),
-                "note": "FPS is a serial-latency kernel (SURVEY H3: npoint dependent picks, each a block/cluster-wide "
-                        "argmax): its HBM fraction is reported as the contract asks, the meaningful unit is picks/s; "
-                        "see `kernels` for the HBM- and tensor-bound ops and `roofline.also` for the fused MLP"
-                if top["kernel"].startswith("furthest") else ""}
-    mlp = next((k for k in kernels if k["kernel"] == "shared_mlp"), None)
-    if mlp is not None and roof["kernel"] != "shared_mlp":
-        n = max(1.0, mlp["launches_per_step"])
-        roof["also"] = {"bound": "tensor", "kernel": "shared_mlp (8 fused gather+MLP+max-pool launches per step)",
-                        "achieved": mlp["TFLOPs"], "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": mlp["tensor_frac"],
-                        "alg_flops_per_launch": round(mlp["GFLOP_per_step"] * 1e9 / n),
-                        "launch_ms": round(mlp["ms_per_step"] / n, 4), "peak_source": peaks["src"]}
-    return roof, kernels
+    # ---- headline: the fused gather + MLP + max-pool launches (tensor roofline).  They own the largest share of the
+    # step's SM-time; the FPS chain is a serial-latency kernel and is reported in its honest unit below.
+    mlp_rows = [k for k in kernels if k["kernel"] in ("shared_mlp", "sa_mlp")]
+    flops = sum(agg[k["kernel"]]["flops"] for k in mlp_rows)
+    ms = sum(agg[k["kernel"]]["ms"] for k in mlp_rows)
+    n_l = sum(agg[k["kernel"]]["launches"] for k in mlp_rows)
+    tfs = flops / ms / 1e9 if ms > 0 else 0.0
+    roof = {"bound": "tensor", "kernel": f"fused gather + shared MLP + max-pool ({n_l:.0f} launches per step: "
+                                         "5 specialised SA stages [sa_mlp_kernel], FP1/FP2/voting [fused_mlp_kernel])",
+            "achieved": round(tfs, 1), "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": round(tfs / peaks["tensor"], 4),
+            "traffic": None, "peak_source": peaks["src"], "alg_flops_per_launch": round(flops / max(1.0, n_l)),
+            "launch_ms": round(ms / max(1.0, n_l), 4), "ms_per_step_all_launches": round(ms, 4),
+            "note": "bf16 operands, fp32 accumulate; peak = sustained cuBLAS bf16 (MEASURED_PEAKS.json); algorithmic flops = "
+                    "2 * rows * sum(Cin*Cout) with the real (unpadded) channel counts; device time by CUDA events, launches "
+                    "queued behind a busy stream so no host gap is inside an event pair"}
+    per_stage = []
+    for k in mlp_rows:
+        per_stage.append({"kernel": k["kernel"], "ms": k["ms_per_step"], "GFLOP": k.get("GFLOP_per_step"),
+                          "TFLOPs": k.get("TFLOPs"), "frac": k.get("tensor_frac")})
+    roof["by_kernel"] = per_stage
+    names = ["SA1", "SA2", "SA3", "SA4", "FP1", "FP2", "voting", "aggregation"]
+    roof["by_launch"] = []
+    for i, (sk, st) in enumerate(sorted(stages.items(), key=lambda kv: kv[1]["order"])):
+        t = st["flops"] / st["ms"] / 1e9 if st["ms"] > 0 else 0.0
+        roof["by_launch"].append({"stage": names[i] if i < len(names) else str(i), "entry": sk[0].replace("sad_", ""),
+                                  "dims": list(sk[1]), "us": round(1e3 * st["ms"], 1), "GFLOP": round(st["flops"] / 1e9, 2),
+                                  "TFLOPs": round(t, 1), "frac": round(t / peaks["tensor"], 4)})
+    # ---- FPS in its own unit: dependent picks per second
+    fps_rows = []
+    for k in kernels:
+        if k["kernel"].startswith("furthest_point_sample"):
+            d = agg[k["kernel"]]
+            picks = d.get("picks", 0)
+            fps_rows.append({"kernel": k["kernel"], "ms": k["ms_per_step"], "picks_per_scene": picks,
+                             "us_per_pick": round(1e3 * d["ms"] / max(1, picks), 4),
+                             "picks_per_s_per_scene": round(picks / (d["ms"] / 1e3)) if d["ms"] > 0 else None})
+    return roof, kernels, fps_rows
+
+
+def hbm_kernel_block(dev):
+    """north_star's HBM bar, measured in this run: grouping_operation fwd at the SA2/SA3/SA4/vote shapes and
+    three_interpolate fwd (drop-in fp32 and the channel-last bf16 variant of the product path) at the FP1/FP2
+    shapes, B = 64 and 256 scenes per launch (working sets > L2), `reps` launches per event pair."""
+    import ctypes
+    import torch
+    import sad_b200 as S
+    from sad_b200 import _lib
+    peaks = measured_peaks()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    rows = []
+
+    def timeit(fn, reps=4, iters=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(2000000)           # launches queue behind a busy stream: no host gap inside the pair
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / reps)
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    def rec(name, ms, alg):
+        gbs = alg / ms / 1e6
+        rows.append({"op": name, "ms": round(ms, 4), "alg_MB": round(alg / 1e6, 1), "GBps": round(gbs, 1),
+                     "frac": round(gbs / peaks["hbm"], 4)})
+
+    for (tag, C, N, P, Sn) in (("SA2", 131, 2048, 1024, 32), ("SA3", 259, 1024, 512, 16), ("SA4", 259, 512, 256, 16),
+                               ("vote", 259, 1024, 256, 16)):
+        for B in (64, 256):
+            if B * C * P * Sn * 4 > 5e9:
+                continue
+            f = torch.randn(B, C, N, device=dev)
+            idx = torch.randint(0, N, (B, P, Sn), generator=g, dtype=torch.int32).to(dev)
+            alg = B * (P * Sn * 4 + P * Sn * C * 4 + min(N, P * Sn) * C * 4)
+            rec(f"grouping_operation fwd {tag} shape B={B}", timeit(lambda: S.grouping_operation(f, idx)), alg)
+            del f, idx
+    lib = _lib.load()
+    vp = ctypes.c_void_p
+    for (tag, n, m, C) in (("FP1", 512, 256, 256), ("FP2", 1024, 512, 256)):
+        for B in (64, 256):
+            u = torch.rand(B, n, 3, device=dev) * 6
+            k = torch.rand(B, m, 3, device=dev) * 6
+            d, i = S.three_nn(u, k)
+            w = 1.0 / (d + 1e-8)
+            w = (w / w.sum(-1, keepdim=True)).contiguous()
+            f = torch.randn(B, C, m, device=dev)
+            rec(f"three_interpolate fwd {tag} shape B={B}", timeit(lambda: S.three_interpolate(f, i, w)),
+                B * (n * 3 * 8 + n * C * 4 + m * C * 4))
+            fcl = f.transpose(1, 2).contiguous().to(torch.bfloat16)
+            o = torch.empty(B, n, C, device=dev, dtype=torch.bfloat16)
+            st = vp(torch.cuda.current_stream().cuda_stream)
+            rec(f"three_interpolate_cl (bf16 channel-last) fwd {tag} shape B={B}",
+                timeit(lambda: lib.sad_three_interpolate_cl_fwd(B, C, m, n, vp(fcl.data_ptr()), vp(i.data_ptr()),
+                                                                vp(w.data_ptr()), vp(o.data_ptr()), st)),
+                B * (n * 3 * 8 + n * C * 2 + m * C * 2))
+            del u, k, d, i, w, f, fcl, o
+    return {"peak_GBps": peaks["hbm"], "peak_source": peaks["src"], "bar": "north_star: >= 0.60 of the HBM roofline on the "
+            "grouping / interpolation kernels", "rows": rows}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -385,10 +503,11 @@ def run_ours(args):
         model.backbone.overlap_geometry = False          # per-kernel view: one stream, nothing overlapped
         from sad_b200 import modules as _modules
         _modules.FPS_POLICY[0] = args.fps_policy         # the same FPS kernel the captured graphs run
-        roof, kernels = build_roofline(model, *sets[0]["dev"])
+        roof, kernels, fps_rows = build_roofline(model, *sets[0]["dev"])
         _modules.FPS_POLICY[0] = "latency"
         model.backbone.overlap_geometry = True
         roof = attach_traffic(roof)
+        hbm_block = hbm_kernel_block(dev) if world == 1 and not args.no_hbm else None
         cpu = None
         if world == 1 and not args.no_cpu:
             n_s = max(1, min(B_PER_GPU, host_threads()))
@@ -401,23 +520,28 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "scenes_per_gpu_per_step": B_PER_GPU, "points_per_scene": N_POINTS,
-                       "l2": f"{NSETS} rotating input sets x {set_bytes / 1e6:.1f} MB = {NSETS * set_bytes / 1e6:.0f} MB "
-                             "> 126 MB L2 (inputs larger than L2, no flush)",
-                       "pipeline": f"{eng.slots} batches in flight (one CUDA graph + stream per slot); every batch runs "
-                                   "the full path and results are delivered in order",
-                       "fps_policy": f"{args.fps_policy} (throughput = one SM per scene for the 40k-point FPS, latency = "
-                                     "4-SM cluster per scene; identical indices)",
-                       "batch_latency_loaded_ms": round(eng.slots * (total_ms / args.steps), 4),
-                       "batch_latency_ms": round(lat[len(lat) // 2], 4),
-                       "search_dtype": "f32 (bit-exact indices)", "mlp_dtype": "bf16 in / f32 accumulate",
-                       "parallelism": f"scene-data-parallel x{world}, no collective"},
+            "config": workload_config(world),
+            "run": {"l2": f"{NSETS} rotating input sets x {set_bytes / 1e6:.1f} MB = {NSETS * set_bytes / 1e6:.0f} MB "
+                          "> 126 MB L2 (inputs larger than L2, no flush)",
+                    "pipeline": f"{eng.slots} batches in flight (one CUDA graph + stream per slot); every batch runs "
+                                "the full path and results are delivered in order",
+                    "steady_state": bool(args.steps >= 2 * eng.slots),
+                    "steady_state_note": "with steps < 2 x slots the timed window is one pipeline fill and drain: every "
+                                         "batch is submitted at once and `value` is total work / total time, not the "
+                                         "sustained rate (python bench.py without flags runs 200 steps)",
+                    "fps_policy": f"{args.fps_policy} (throughput = one SM per scene for the 40k-point FPS, latency = "
+                                  "4-SM cluster per scene; identical indices)",
+                    "batch_latency_loaded_ms": round(eng.slots * (total_ms / args.steps), 4),
+                    "batch_latency_ms": round(lat[len(lat) // 2], 4),
+                    "search_dtype": "f32 (bit-exact indices)", "mlp_dtype": "bf16 in / f32 accumulate"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms / args.steps, 4), "checksum": round(checksum, 4)},
             "gpu_launches": int(eng.launches_per_batch * args.steps),
             "gpu_launches_per_step": eng.launches_per_batch,
-            "roofline": roof, "kernels": kernels, "clocks": clocks,
+            "roofline": roof, "fps": fps_rows, "kernels": kernels, "clocks": clocks,
         }
+        if hbm_block is not None:
+            line["hbm_kernels"] = hbm_block
         if cpu is not None:
             line["cpu_baseline"] = cpu
         emit(line)
@@ -432,10 +556,7 @@ def attach_traffic(roof):
     (profiles/ncu_full_summary.json, written by tools/ncu_full_summary.py), per launch."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "ncu_full_summary.json")))
-        key = roof["kernel"].split("[")[0]
-        rows = [r for r in d.get("kernels", []) if r.get("roofline_key") == key and "dram_bytes_per_launch" in r]
-        if key.startswith("furthest_point_sample"):      # several FPS launches per step: the one over the raw scene
-            rows = sorted(rows, key=lambda r: -r.get("duration_us", 0))[:1]
+        rows = [r for r in d.get("kernels", []) if r.get("roofline_key") in ("shared_mlp", "sa_mlp") and "dram_bytes_per_launch" in r]
         if rows:
             roof["traffic"] = int(sum(r["dram_bytes_per_launch"] for r in rows) / len(rows))
             roof["traffic_source"] = "profiles/ncu_full_summary.json (ncu --set full, mean over the step's launches of this kernel)"
@@ -462,6 +583,7 @@ def main():
                     help="scheduling of the 40k-point FPS (same indices either way)")
     ap.add_argument("--sets", type=int, default=32, help="rotating input sets (32 x 5.1 MB > L2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-hbm", action="store_true", help="skip the hbm_kernels micro-benchmark block")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything a library prints to fd 1 during the run (NCCL's version banner
     # under NCCL_DEBUG=VERSION, for one) is sent to stderr, and the line is written to the original stdout

@@ -55,6 +55,12 @@ SAD_API const char* sad_last_error_string(void);
  * N <= 204800 (register-resident cluster kernel); larger -> SAD_EUNSUPPORTED. */
 SAD_API int sad_furthest_point_sample_fwd(int B, int N, int npoint, const float* xyz, int32_t* idx,
                                   sad_stream_t stream);
+/* a1 over PREFIX-ORDERED input: row k of xyz is the k-th pick of a farthest-point sampling of a superset (e.g. the
+ * previous stage's new_xyz).  Returns exactly what sad_furthest_point_sample_fwd returns; scenes whose first npoint
+ * rows hold no exact duplicate (checked on the device, contract arithmetic) get the identity without sampling, the
+ * others run the sampler.  flags = B device int32 of scratch (1 = identity taken). */
+SAD_API int sad_furthest_point_sample_prefix_fwd(int B, int N, int npoint, const float* xyz, int32_t* idx, int* flags,
+                                                 sad_stream_t stream);
 
 /* ---- scene grid: spatial sort shared by the exact culled FPS and the grid ball query ----------
  * workspace (caller-owned, 16-byte aligned, sad_scene_grid_workspace_bytes(B,N) bytes) receives, per
@@ -181,6 +187,7 @@ SAD_API int sad_mlp_pack_weights(const float* W, int cout, int cin, const int32_
  *                           words must be stream-ordered); tiles_per_cta = scheduling hint (>= 1, never changes
  *                           results): minimum tiles per CTA, i.e. a narrower grid for small stages. */
 SAD_API int sad_sa_mlp_query(int C0, int h1, int h2, int c3, int S, int E, int has_xyz, int prefer);
+SAD_API int sad_sa_mlp_instance_info(int instance, int* out5); /* {CTAs per MMA group, gathered 64-wide chunks, hidden width, max outputs, nsample} */
 SAD_API long long sad_sa_mlp_image_bytes(int instance);
 SAD_API int sad_sa_mlp_pack(int instance, const float* W1, int cin1, const int32_t* perm_feat, const int32_t* perm_sp,
                             const float* b1, const float* W2, const float* b2, const float* W3, int c3, void* out_image);

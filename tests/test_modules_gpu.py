@@ -97,3 +97,24 @@ def test_forward_host_roundtrip(setup):
         end = model(cu(xyz), cu(feat), cu(size))
     assert torch.equal(cx, end["cluster_xyz"].cpu()) and torch.equal(cf, end["cluster_features"].cpu())
     assert not cx.is_cuda and tuple(cf.shape) == (1, 128, 256)
+
+
+def test_folded_weights_follow_parameter_updates():
+    """the BN-folded / packed weight cache must not survive load_state_dict or an in-place update."""
+    from sad_b200.modules import SharedMLP
+    from sad_b200 import mlp as M
+    torch.manual_seed(0)
+    sm = SharedMLP([64, 64, 64]).to(DEV).eval()
+    x = torch.randn(2, 64, 128, device=DEV)
+    with torch.no_grad():
+        y0 = M.pointwise_mlp(x, sm.folded()).clone()
+        sd = {k: (v * 0.5 if k.startswith("convs") else v) for k, v in sm.state_dict().items()}
+        sm.load_state_dict(sd)
+        y1 = M.pointwise_mlp(x, sm.folded()).clone()
+        ref = sm(x.unsqueeze(-1)).squeeze(-1)
+        assert not torch.allclose(y0, y1), "eval forward after load_state_dict still ran the old weights"
+        assert float((y1 - ref).abs().max()) <= 2e-2 * max(1e-6, float(ref.abs().max()))
+        sm.convs[0].weight.mul_(2.0)                   # in-place update (an optimizer step)
+        y2 = M.pointwise_mlp(x, sm.folded())
+        ref2 = sm(x.unsqueeze(-1)).squeeze(-1)
+        assert float((y2 - ref2).abs().max()) <= 2e-2 * max(1e-6, float(ref2.abs().max()))
