@@ -18,7 +18,7 @@ _vp = ctypes.c_void_p
 SIGNATURES = {
     "sad_version": [],
     "sad_last_error_string": [],
-    "sad_fps_force_cluster_size": [_c_int],
+    "sad_furthest_point_sample_cs_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _c_int, _vp],
     "sad_launch_count": [],
     "sad_furthest_point_sample_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
     "sad_furthest_point_sample_prefix_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
@@ -29,20 +29,21 @@ SIGNATURES = {
     "sad_grouping_operation_fwd": [_c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_grouping_operation_bwd": [_c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_three_nn_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
+    "sad_three_nn_weights_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp],
+    "sad_size_to_radius": [ctypes.c_longlong, _vp, _c_float, _c_float, _c_float, _vp, _vp],
+    "sad_gather_points_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_three_interpolate_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_three_interpolate_bwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_scene_grid_workspace_bytes": [_c_int, _c_int],
     "sad_scene_grid_build": [_c_int, _c_int, _vp, _vp, _vp],
     "sad_ball_query_grid_fwd": [_c_int, _c_int, _c_int, _c_float, _vp, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_fps_grid_max_points": [],
-    "sad_fps_grid_force_cluster": [_c_int],
-    "sad_mlp_set_tiles_per_cta": [_c_int],
     "sad_furthest_point_sample_grid_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
-    "sad_furthest_point_sample_grid_policy_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp],
+    "sad_furthest_point_sample_grid_policy_fwd": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _c_int, _vp],
     "sad_mlp_weight_image_bytes": [_c_int, _c_int, _c_int],
     "sad_mlp_pack_weights": [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp],
     "sad_shared_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _c_int, _vp, _c_int, _vp, _vp, _vp, _c_float, _vp,
-                           _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp],
+                           _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_sa_mlp_query": [_c_int] * 8,
     "sad_sa_mlp_instance_info": [_c_int, _vp],
     "sad_sa_mlp_image_bytes": [_c_int],
@@ -53,9 +54,14 @@ SIGNATURES = {
     "sad_three_interpolate_cl_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_cf_to_cl_bf16": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
 }
-_RESTYPES = {"sad_last_error_string": ctypes.c_char_p, "sad_fps_force_cluster_size": None, "sad_fps_grid_force_cluster": None, "sad_mlp_set_tiles_per_cta": None,
+_RESTYPES = {"sad_last_error_string": ctypes.c_char_p,
              "sad_launch_count": ctypes.c_ulonglong, "sad_scene_grid_workspace_bytes": ctypes.c_longlong, "sad_mlp_weight_image_bytes": ctypes.c_longlong,
              "sad_sa_mlp_image_bytes": ctypes.c_longlong}
+
+class MlpOpts(ctypes.Structure):
+    """include/sad_ops.h sad_mlp_opts"""
+    _fields_ = [("tiles_per_cta", ctypes.c_int), ("super_tiles", ctypes.c_int)]
+
 
 _lib = None
 _lock = threading.Lock()

@@ -235,11 +235,7 @@ __global__ void ablate_strided_idx_plain(int N, int npoint, int32_t* idx) {
   for (int j = threadIdx.x; j < npoint; j += blockDim.x) idx[(size_t)blockIdx.x * npoint + j] = (int32_t)((long long)j * N / npoint);
 }
 #endif
-// Exposed for tests/benchmarks: force a cluster size (0 = heuristic).
-static thread_local int g_force_cs = 0;
-extern "C" void sad_fps_force_cluster_size(int cs) { g_force_cs = cs; }
-
-static int fps_plain(int B, int N, int npoint, const float* xyz, int32_t* idx, const int* skip, cudaStream_t stream) {
+static int fps_plain(int B, int N, int npoint, const float* xyz, int32_t* idx, const int* skip, int force_cs, cudaStream_t stream) {
   SAD_REQUIRE(B >= 0 && N >= 1 && npoint >= 1, "furthest_point_sample: bad sizes B=%d N=%d npoint=%d", B, N,
               npoint);
   if (B == 0) return SAD_OK;
@@ -262,7 +258,7 @@ static int fps_plain(int B, int N, int npoint, const float* xyz, int32_t* idx, c
     }
     return dispatch_big(512, 25, B, N, npoint, xyz, idx, skip, stream);
   }
-  int cs = g_force_cs;
+  int cs = force_cs;
   if (cs == 0) {
     if (N <= 3072) {
       cs = 1;
@@ -286,7 +282,14 @@ static int fps_plain(int B, int N, int npoint, const float* xyz, int32_t* idx, c
 
 extern "C" int sad_furthest_point_sample_fwd(int B, int N, int npoint, const float* xyz, int32_t* idx,
                                              sad_stream_t stream) {
-  return fps_plain(B, N, npoint, xyz, idx, nullptr, (cudaStream_t)stream);
+  return fps_plain(B, N, npoint, xyz, idx, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int sad_furthest_point_sample_cs_fwd(int B, int N, int npoint, const float* xyz, int32_t* idx, int cluster_size,
+                                                sad_stream_t stream) {
+  SAD_REQUIRE(cluster_size == 0 || cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8 ||
+              cluster_size == 16, "furthest_point_sample: cluster_size must be 0 (heuristic), 1, 2, 4, 8 or 16");
+  return fps_plain(B, N, npoint, xyz, idx, nullptr, cluster_size, (cudaStream_t)stream);
 }
 
 // ---- a1 over PREFIX-ORDERED input (SURVEY.md H3 side note) ---------------------------------------
@@ -335,7 +338,7 @@ extern "C" int sad_furthest_point_sample_prefix_fwd(int B, int N, int npoint, co
   SAD_REQUIRE(B >= 0 && N >= 1 && npoint >= 1 && npoint <= N, "furthest_point_sample_prefix: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
   if (B == 0) return SAD_OK;
   SAD_REQUIRE(xyz && idx && flags, "furthest_point_sample_prefix: null pointer");
-  if (npoint > 8192) return fps_plain(B, N, npoint, xyz, idx, nullptr, stream);      // guard table would not fit: plain sampler
+  if (npoint > 8192) return fps_plain(B, N, npoint, xyz, idx, nullptr, 0, stream);      // guard table would not fit: plain sampler
   const size_t smem = (size_t)npoint * sizeof(float4);
   static thread_local int configured_dev = -1;
   int dev = 0;
@@ -346,5 +349,5 @@ extern "C" int sad_furthest_point_sample_prefix_fwd(int B, int N, int npoint, co
   }
   fps_prefix_guard_kernel<<<B, 1024, smem, stream>>>(xyz, N, npoint, idx, flags);
   SAD_LAUNCH_CHECK("fps_prefix_guard_kernel");
-  return fps_plain(B, N, npoint, xyz, idx, flags, stream);
+  return fps_plain(B, N, npoint, xyz, idx, flags, 0, stream);
 }

@@ -553,26 +553,23 @@ __global__ void ablate_strided_idx(int N, int npoint, int32_t* idx) {
   for (int j = threadIdx.x; j < npoint; j += blockDim.x) idx[(size_t)blockIdx.x * npoint + j] = (int32_t)((long long)j * N / npoint);
 }
 #endif
-static int env_cull_cluster() {                       // SAD_FPS_CLUSTER: tools only (A/B runs of the kernel choice)
-  const char* e = getenv("SAD_FPS_CLUSTER");
-  return e ? atoi(e) : 0;
-}
-static thread_local int g_cull_cluster = env_cull_cluster();
-extern "C" void sad_fps_grid_force_cluster(int cs) { g_cull_cluster = cs; }
 
 // Largest scene the culled kernels accept.
 extern "C" int sad_fps_grid_max_points(void) { return 16 * 32 * FC1_NW * 32; }
 
 extern "C" int sad_furthest_point_sample_grid_fwd(int B, int N, int npoint, const float* xyz, void* grid_ws,
                                                   int32_t* idx, sad_stream_t stream_) {
-  return sad_furthest_point_sample_grid_policy_fwd(B, N, npoint, xyz, grid_ws, idx, SAD_FPS_LATENCY, stream_);
+  return sad_furthest_point_sample_grid_policy_fwd(B, N, npoint, xyz, grid_ws, idx, SAD_FPS_LATENCY, 0, stream_);
 }
 
 extern "C" int sad_furthest_point_sample_grid_policy_fwd(int B, int N, int npoint, const float* xyz, void* grid_ws,
-                                                         int32_t* idx, int policy, sad_stream_t stream_) {
+                                                         int32_t* idx, int policy, int variant, sad_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  SAD_REQUIRE(policy == SAD_FPS_LATENCY || policy == SAD_FPS_THROUGHPUT, "furthest_point_sample_grid: bad policy %d", policy);
-  const int force = g_cull_cluster != 0 ? g_cull_cluster : (policy == SAD_FPS_THROUGHPUT ? -1 : 0);
+  SAD_REQUIRE(policy == SAD_FPS_LATENCY || policy == SAD_FPS_THROUGHPUT || policy == SAD_FPS_THROUGHPUT_PAIRED,
+              "furthest_point_sample_grid: bad policy %d", policy);
+  SAD_REQUIRE(variant == 0 || variant == -1 || variant == 1 || variant == 2 || variant == 4 || variant == 8 || variant == 16,
+              "furthest_point_sample_grid: bad variant %d", variant);
+  const int force = variant != 0 ? variant : (policy == SAD_FPS_LATENCY ? 0 : -1);
   SAD_REQUIRE(B >= 0 && N >= 1 && npoint >= 1, "furthest_point_sample_grid: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
   if (B == 0) return SAD_OK;
   SAD_REQUIRE(xyz && grid_ws && idx, "furthest_point_sample_grid: null pointer");
@@ -608,15 +605,14 @@ extern "C" int sad_furthest_point_sample_grid_policy_fwd(int B, int N, int npoin
   if (N <= FC1_MDS_MAX) {                 // min-distances in shared memory
     // 16 warps per scene: a pick's fixed cost is issue-bound (every warp runs ~180 bookkeeping + box-test
     // instructions per pick), so 16 warps x 3 register sets beat 32 x 2 (2.83 vs 2.99 ms at 40k points)
-    static const int sc_env = getenv("SAD_FPS1_SC") ? atoi(getenv("SAD_FPS1_SC")) : 1;    // tools: scenes per CTA
-    if (sc_env == 2 && B >= 2) {
+    if (policy == SAD_FPS_THROUGHPUT_PAIRED && B >= 2) {      // two scenes per SM (16 warps each)
       const int pl = sad_ceil_div(sad_ceil_div(nbk, 16), 32);
       if (pl <= 1) return launch_cull1<1, 16, false, 2>(B, N, npoint, xyz, grid_ws, idx, stream);
       if (pl <= 2) return launch_cull1<2, 16, false, 2>(B, N, npoint, xyz, grid_ws, idx, stream);
       return launch_cull1<3, 16, false, 2>(B, N, npoint, xyz, grid_ws, idx, stream);
     }
-    static const int nw_env = getenv("SAD_FPS1_NW") ? atoi(getenv("SAD_FPS1_NW")) : 16;   // tools: warps per scene
-    if (nw_env != 32) {
+    const char* e_nw = sad_tool_env("SAD_FPS1_NW");                                      // tools: warps per scene
+    if (!e_nw || atoi(e_nw) != 32) {
       const int pl = sad_ceil_div(sad_ceil_div(nbk, 16), 32);
       if (pl <= 1) return launch_cull1<1, 16, true>(B, N, npoint, xyz, grid_ws, idx, stream);
       if (pl <= 2) return launch_cull1<2, 16, true>(B, N, npoint, xyz, grid_ws, idx, stream);

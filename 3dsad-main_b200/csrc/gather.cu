@@ -204,6 +204,36 @@ extern "C" int sad_grouping_operation_bwd(int B, int C, int N, int npoint, int n
                    (cudaStream_t)stream);
 }
 
+// new_xyz (B,P,3) = xyz[b, inds[b,j]] straight from the (B,N,3) layout (the lineage idiom transposes twice around
+// gather_operation: three launches); optionally also the padded float4 rows the fused SA kernel gathers from.
+__global__ void __launch_bounds__(256)
+gather_points_kernel(long long rows, int N, int P, const float* __restrict__ xyz, const int32_t* __restrict__ inds,
+                     float* __restrict__ out, float4* __restrict__ out_xyzw) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= rows) return;
+  const long long b = i / P;
+  int k = __ldg(inds + i);
+  k = (unsigned)k < (unsigned)N ? k : 0;
+  const float* p = xyz + ((size_t)b * N + k) * 3;
+  const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+  out[3 * i] = x;
+  out[3 * i + 1] = y;
+  out[3 * i + 2] = z;
+  if (out_xyzw) out_xyzw[i] = make_float4(x, y, z, 0.f);
+}
+
+extern "C" int sad_gather_points_fwd(int B, int N, int npoint, const float* xyz, const int32_t* inds, float* new_xyz,
+                                     void* new_xyzw, sad_stream_t stream) {
+  SAD_REQUIRE(B >= 0 && N >= 1 && npoint >= 0, "gather_points: bad sizes");
+  if (B == 0 || npoint == 0) return SAD_OK;
+  SAD_REQUIRE(xyz && inds && new_xyz, "gather_points: null pointer");
+  const long long rows = (long long)B * npoint;
+  gather_points_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, N, npoint, xyz, inds, new_xyz,
+                                                                                        static_cast<float4*>(new_xyzw));
+  SAD_LAUNCH_CHECK("gather_points_kernel");
+  return SAD_OK;
+}
+
 extern "C" int sad_gather_operation_fwd(int B, int C, int N, int npoint, const float* features,
                                         const int32_t* idx, float* out, sad_stream_t stream) {
   SAD_REQUIRE(npoint >= 0, "gather_operation: bad npoint");

@@ -267,7 +267,7 @@ extern "C" int sad_three_interpolate_fwd(int B, int C, int m, int n, const float
   // both kernels sit at ~70 % of the SM's LSU wavefront rate; the point-major kernel takes
   // the larger-m shapes, where its lower wavefront count per output wins)
   if (n % 4 == 0 && aligned16(out) && aligned16(idx) && aligned16(weight) && m >= 384 && m <= 1408 && 2LL * n >= m &&
-      !getenv("SAD_INTERP_LEGACY")) {
+      !sad_tool_env("SAD_INTERP_LEGACY")) {
     const int cn = (m <= 128 && C > 32) ? 64 : 32;
     const int ychunks = sad_ceil_div(C, cn);
     SAD_REQUIRE(ychunks <= 65535, "three_interpolate: C exceeds grid limits");

@@ -1150,7 +1150,7 @@ extern "C" int sad_mlp_pack_weights(const float* W, int cout, int cin, const int
 }
 
 // Shared-memory / TMEM plan of one launch.  Returns false when nothing fits.
-static bool plan_launch(MlpParams& p, int hidden_max, size_t& smem_out) {
+static bool plan_launch(MlpParams& p, int hidden_max, int super_tiles, size_t& smem_out) {
   const int nl = p.n_layers;
   const int c_last = p.c[nl - 1];
   p.transposed = p.S > 1 ? 1 : 0;
@@ -1176,12 +1176,12 @@ static bool plan_launch(MlpParams& p, int hidden_max, size_t& smem_out) {
   // shared-memory budget per CTA: everything the SM has by default; SAD_MLP_SMEM_KB (tuning hook) leaves room for
   // another stream's CTAs (e.g. a latency-bound FPS cluster) to share the SM
   long long budget_kb = 227;
-  if (const char* e_kb = getenv("SAD_MLP_SMEM_KB")) budget_kb = atoi(e_kb) < 64 ? 64 : (atoi(e_kb) > 227 ? 227 : atoi(e_kb));
+  if (const char* e_kb = sad_tool_env("SAD_MLP_SMEM_KB")) budget_kb = atoi(e_kb) < 64 ? 64 : (atoi(e_kb) > 227 ? 227 : atoi(e_kb));
   const long long avail = budget_kb * 1024 - 1024 - kMiscBytes;
   // tuning hooks (benchmarks only): cap the tile contexts / A-ring stages, force a minimum weight ring
-  const char* e_slot = getenv("SAD_MLP_NSLOT");
-  const char* e_na = getenv("SAD_MLP_NA");
-  const char* e_nr = getenv("SAD_MLP_NR");
+  const char* e_slot = sad_tool_env("SAD_MLP_NSLOT");
+  const char* e_na = sad_tool_env("SAD_MLP_NA");
+  const char* e_nr = sad_tool_env("SAD_MLP_NR");
   const int max_slot = e_slot ? atoi(e_slot) : 2, max_na = e_na ? atoi(e_na) : 4, want_nr = e_nr ? atoi(e_nr) : 2;
   int max_pieces = 0;
   for (int li = 0; li < nl; ++li) max_pieces = p.pieces[li] > max_pieces ? p.pieces[li] : max_pieces;
@@ -1190,9 +1190,8 @@ static bool plan_launch(MlpParams& p, int hidden_max, size_t& smem_out) {
   const bool two_ok = p.kpad[0] / 64 + 1 + kMaxA <= kFullBars && max_pieces + 1 + kMaxRing <= kFullBars;
   // super-tiles (T = 2 tiles per context and phase): pooled stages with enough tiles per CTA, two contexts of two
   // tiles in TMEM, two tiles of layer-1 chunks in the A ring, and EVERY weight piece pinned (SAD_MLP_T: tuning / tests)
-  const char* e_T = getenv("SAD_MLP_T");
   const bool try_T2 = p.transposed && 4 * p.region1 <= 512 && max_slot >= 2 && two_ok &&
-                      (e_T ? atoi(e_T) == 2 : p.num_tiles >= 1024);
+                      (super_tiles == 0 ? p.num_tiles >= 1024 : super_tiles == 2);
   for (int T = try_T2 ? 2 : 1; T >= 1; --T)
   for (int nslot = (2 * T * p.region1 <= 512 && p.num_tiles > 1 && max_slot >= 2 && two_ok) ? 2 : 1; nslot >= 1; --nslot) {
     if (T == 2 && nslot != 2) continue;
@@ -1227,7 +1226,7 @@ static bool plan_launch(MlpParams& p, int hidden_max, size_t& smem_out) {
       // Exception: the wide point-wise stages (S == 1, K0 >= 384: FP layers) run one tile per CTA, nothing overlaps the
       // gather, and three groups in flight cut its eight serial L2 round trips (CTA span 20.6 -> 15.9 us).
       p.depth = (p.S == 1 && p.kpad[0] >= 384) ? 3 : 1;
-      if (const char* e_d = getenv("SAD_MLP_DEPTH")) p.depth = atoi(e_d) < 1 ? 1 : (atoi(e_d) > 3 ? 3 : atoi(e_d));
+      if (const char* e_d = sad_tool_env("SAD_MLP_DEPTH")) p.depth = atoi(e_d) < 1 ? 1 : (atoi(e_d) > 3 ? 3 : atoi(e_d));
       if (p.depth > na - 1) p.depth = na - 1;
       p.n_pinned = n_pinned;
       p.pinned_bytes = (int)pinned;
@@ -1248,15 +1247,12 @@ static bool plan_launch(MlpParams& p, int hidden_max, size_t& smem_out) {
   return false;
 }
 
-// Scheduling hint (never changes results): minimum tiles per CTA of the fused-MLP launches issued by this thread.
-static thread_local int g_tiles_per_cta = 1;
-extern "C" void sad_mlp_set_tiles_per_cta(int tiles) { g_tiles_per_cta = tiles < 1 ? 1 : tiles; }
-
 extern "C" int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_cl, int C0, const void* feat2_cl,
                                   int C1in, const float* xyz, const float* new_xyz, const int32_t* idx, float radius,
                                   const float* radius_t, int normalize_xyz, const float* extra, int E, int n_layers,
                                   const void* const* w_img, const float* const* bias, const int* c_out, int last_relu,
-                                  void* out_cl_bf16, float* out_cf_f32, int* tile_counter, sad_stream_t stream_) {
+                                  void* out_cl_bf16, float* out_cf_f32, int* tile_counter, const sad_mlp_opts* opts,
+                                  sad_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
 #ifdef SAD_TOOLS_ABLATE
   if (sad_ablate_mask() & 2) return SAD_OK;
@@ -1311,7 +1307,9 @@ extern "C" int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_c
   }
   SAD_REQUIRE(c_out[n_layers - 1] <= 512, "shared_mlp: at most 512 output channels");
   size_t smem = 0;
-  SAD_REQUIRE(plan_launch(p, hidden_max, smem), "shared_mlp: shared-memory / TMEM budget exceeded");
+  const int super_tiles = opts ? opts->super_tiles : 0;
+  SAD_REQUIRE(super_tiles >= 0 && super_tiles <= 2, "shared_mlp: opts.super_tiles must be 0 (auto), 1 (off) or 2 (on)");
+  SAD_REQUIRE(plan_launch(p, hidden_max, super_tiles, smem), "shared_mlp: shared-memory / TMEM budget exceeded");
 
   int dev = 0, sms = 0;
   SAD_CUDA_OK(cudaGetDevice(&dev));
@@ -1321,16 +1319,14 @@ extern "C" int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_c
     SAD_CUDA_OK(cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured_dev = dev;
   }
-  if (getenv("SAD_DEBUG_MLP"))
+  if (sad_tool_env("SAD_DEBUG_MLP"))
     fprintf(stderr, "[sad] fused_mlp: rows=%lld tiles=%d S=%d K0=%d c=[%d,%d,%d] T=%d nslot=%d na=%d depth=%d pinned=%d/%d "
             "(%d B) ring=%dx%d tmem=%d smem=%zu\n", p.total_rows, p.num_tiles, S, p.kpad[0], p.c[0], p.c[1], p.c[2], p.T, p.nslot,
             p.na, p.depth, p.n_pinned, p.n_pieces, p.pinned_bytes, p.nr, p.ring_slot_bytes, p.tmem_cols, smem);
-  // CTAs: one per SM, but never fewer than `tpc` tiles per CTA (sad_mlp_set_tiles_per_cta; SAD_MLP_TILES_PER_CTA
-  // overrides it for tuning).  The per-CTA prologue -- TMEM allocation, barrier init, pinned weight loads -- is paid per
+  // CTAs: one per SM, but never fewer than opts.tiles_per_cta tiles per CTA.  The per-CTA prologue -- TMEM allocation, barrier init, pinned weight loads -- is paid per
   // CTA, and under a pipelined caller a narrower grid leaves SMs to the other streams' kernels: the small stages take
   // longer alone but cost less SM-time (bench: 15.7k -> 16.5k scenes/s at 6 tiles per CTA).
-  static const int tpc_env = getenv("SAD_MLP_TILES_PER_CTA") ? atoi(getenv("SAD_MLP_TILES_PER_CTA")) : 0;
-  const int tpc = tpc_env > 0 ? tpc_env : g_tiles_per_cta;
+  const int tpc = (opts && opts->tiles_per_cta > 0) ? opts->tiles_per_cta : 1;
   int grid = sad_ceil_div(p.num_tiles, tpc < 1 ? 1 : tpc);
   if (grid > sms) grid = sms;
   fused_mlp_kernel<<<grid, kThreads, smem, stream>>>(p);

@@ -44,6 +44,15 @@ void sad_count_launch(int n);
 
 static inline int sad_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Tuning / A-B hooks read the environment only in tools builds (tools/build_variant.py <name> -DSAD_TOOLS); the product
+// library never looks at the environment.
+#ifdef SAD_TOOLS
+#include <stdlib.h>
+static inline const char* sad_tool_env(const char* name) { return getenv(name); }
+#else
+static inline const char* sad_tool_env(const char*) { return nullptr; }
+#endif
+
 #ifdef SAD_TOOLS_ABLATE
 // tools/build_variant.py builds only: SAD_ABLATE bit 0 = skip the scene-grid FPS, bit 1 = skip the fused MLP launches,
 // bit 2 = skip the register-resident FPS (pipeline cost attribution; results are garbage by design).

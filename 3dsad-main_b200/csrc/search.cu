@@ -219,7 +219,7 @@ __device__ __forceinline__ void nn_insert(float d, int k, float& b0, float& b1, 
 // '<' insertion), then three rounds of warp arg-min with ties to the lowest index.
 __global__ void __launch_bounds__(NN_T)
 three_nn_kernel(int n, int m, const float* __restrict__ unknown, const float* __restrict__ known,
-                float* __restrict__ dist, int32_t* __restrict__ idx) {
+                float* __restrict__ dist, int32_t* __restrict__ idx, float* __restrict__ weight) {
   __shared__ float s_known[NN_TILE * 3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
@@ -261,13 +261,31 @@ three_nn_kernel(int n, int m, const float* __restrict__ unknown, const float* __
     }
     if (lane == r) {
       od = __fsqrt_rn(__uint_as_float(mn));
-      oi = (int)ck;
+      oi = ck < (uint32_t)m ? (int)ck : 0;                  // (non-finite coordinates find no candidate: stay in range)
     }
   }
   if (lane < 3) {
     dist[((size_t)b * n + i) * 3 + lane] = od;
     idx[((size_t)b * n + i) * 3 + lane] = oi;
   }
+  if (weight != nullptr) {
+    // FP-module weights, the oracle's evaluation order: r_t = 1 / (dist_t + 1e-8), w_t = r_t / ((r_0 + r_1) + r_2)
+    const float rc = __fdiv_rn(1.0f, __fadd_rn(od, 1e-8f));
+    const float r0 = __shfl_sync(FULL, rc, 0), r1 = __shfl_sync(FULL, rc, 1), r2 = __shfl_sync(FULL, rc, 2);
+    const float norm = __fadd_rn(__fadd_rn(r0, r1), r2);
+    if (lane < 3) weight[((size_t)b * n + i) * 3 + lane] = __fdiv_rn(rc, norm);
+  }
+}
+
+// a4 helper: predicted box size (rows,3) -> radius r = clamp(c * sqrt(((sx*sx)+(sy*sy))+(sz*sz)), r_min, r_max), c = alpha/2
+__global__ void __launch_bounds__(256)
+size_to_radius_kernel(long long rows, const float* __restrict__ size, float c, float r_min, float r_max, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= rows) return;
+  const float sx = __ldg(size + 3 * i), sy = __ldg(size + 3 * i + 1), sz = __ldg(size + 3 * i + 2);
+  const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy)), __fmul_rn(sz, sz));
+  const float r = __fmul_rn(c, __fsqrt_rn(n2));
+  out[i] = fminf(fmaxf(r, r_min), r_max);
 }
 
 }  // namespace
@@ -292,7 +310,30 @@ extern "C" int sad_three_nn_fwd(int B, int n, int m, const float* unknown, const
   SAD_REQUIRE(unknown && known && dist && idx, "three_nn: null pointer");
   SAD_REQUIRE(B <= 65535, "three_nn: B=%d exceeds grid.y", B);
   dim3 grid((unsigned)sad_ceil_div(n, NN_T / 32), (unsigned)B);
-  three_nn_kernel<<<grid, NN_T, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist, idx);
+  three_nn_kernel<<<grid, NN_T, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist, idx, nullptr);
   SAD_LAUNCH_CHECK("three_nn_kernel");
+  return SAD_OK;
+}
+
+extern "C" int sad_three_nn_weights_fwd(int B, int n, int m, const float* unknown, const float* known, float* dist,
+                                        int32_t* idx, float* weight, sad_stream_t stream) {
+  SAD_REQUIRE(B >= 0 && n >= 0, "three_nn: bad sizes B=%d n=%d", B, n);
+  SAD_REQUIRE(m >= 3, "three_nn: needs m >= 3 known points (m=%d)", m);
+  if (B == 0 || n == 0) return SAD_OK;
+  SAD_REQUIRE(unknown && known && dist && idx && weight, "three_nn: null pointer");
+  SAD_REQUIRE(B <= 65535, "three_nn: B=%d exceeds grid.y", B);
+  dim3 grid((unsigned)sad_ceil_div(n, NN_T / 32), (unsigned)B);
+  three_nn_kernel<<<grid, NN_T, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist, idx, weight);
+  SAD_LAUNCH_CHECK("three_nn_kernel");
+  return SAD_OK;
+}
+
+extern "C" int sad_size_to_radius(long long rows, const float* size, float alpha, float r_min, float r_max, float* radius,
+                                  sad_stream_t stream) {
+  SAD_REQUIRE(rows >= 0, "size_to_radius: bad row count");
+  if (rows == 0) return SAD_OK;
+  SAD_REQUIRE(size && radius, "size_to_radius: null pointer");
+  size_to_radius_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, size, alpha * 0.5f, r_min, r_max, radius);
+  SAD_LAUNCH_CHECK("size_to_radius_kernel");
   return SAD_OK;
 }

@@ -57,13 +57,11 @@ class PipelinedHotPath:
         from . import modules as _modules, mlp as _mlp
         saved_policy = _modules.FPS_POLICY[0]
         _modules.FPS_POLICY[0] = fps_policy
-        lib.sad_mlp_set_tiles_per_cta(int(mlp_tiles_per_cta))
         _mlp.TILES_PER_CTA[0] = int(mlp_tiles_per_cta)
         try:
             self._capture(model, batch, n_points, feat_dim, slots, dev, warmup, lib)
         finally:
             _modules.FPS_POLICY[0] = saved_policy
-            lib.sad_mlp_set_tiles_per_cta(1)
             _mlp.TILES_PER_CTA[0] = 1
         self.launches_per_batch = self._slots[0].launches
 
@@ -176,3 +174,64 @@ class PipelinedHotPath:
             if s.busy:
                 s.done.synchronize()
                 s.busy = False
+
+
+class ShardedHotPath:
+    """Scene-data-parallel front end: ONE PROCESS PER GPU, every rank owns a contiguous block
+    of the scenes and runs its own PipelinedHotPath over it; there is no data-path collective.  Launch with torchrun:
+
+        torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 my_script.py
+        ...
+        dist.init_process_group("nccl")                      # or not at all: a single process owns every scene
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        shp = ShardedHotPath(model, batch=8, n_points=40000)
+        cxyz, cfeat = shp.run(xyz_all, feat_all, size_all)   # host arrays of ALL scenes, the same on every rank
+        # rank 0: (S,256,3) / (S,128,256) for all S scenes in scene order; other ranks: their own block
+
+    `engine` may be any object with submit_host / result / slots (tests drive the sharding logic on CPU with a stub).
+    Results are bit-identical to a single process running all scenes: every scene's result depends on that scene only.
+    """
+
+    def __init__(self, model=None, batch: int = 8, n_points: int = 40000, engine=None, **engine_kw):
+        from . import dist as _dist
+        self._dist = _dist
+        self.world, self.rank = _dist.world_info()
+        self.batch = batch
+        self.engine = engine if engine is not None else PipelinedHotPath(model, batch, n_points, **engine_kw)
+
+    def my_range(self, num_scenes: int):
+        return self._dist.shard_range(num_scenes, self.world, self.rank)
+
+    def run(self, xyz, feat, size, gather: bool = True):
+        """xyz (S,N,3), feat (S,C,N), size (S,K,3): host tensors / arrays holding ALL scenes -> (cluster_xyz, cluster_features)
+        host tensors: every scene on rank 0 (gather=True), this rank's block elsewhere / otherwise."""
+        xyz, feat, size = (torch.as_tensor(a) for a in (xyz, feat, size))
+        lo, hi = self.my_range(xyz.shape[0])
+        outs_x, outs_f, tickets = [], [], []
+
+        def drain_one():
+            (k0, n_valid), t = tickets.pop(0)
+            cx, cf = self.engine.result(t)
+            outs_x.append(cx[:n_valid].clone())
+            outs_f.append(cf[:n_valid].clone())
+
+        for k0 in range(lo, hi, self.batch):
+            k1 = min(hi, k0 + self.batch)
+            sel = list(range(k0, k1)) + [k1 - 1] * (self.batch - (k1 - k0))      # pad the last batch with its last scene
+            staged = tuple(a[sel].contiguous().pin_memory() if torch.cuda.is_available() else a[sel].contiguous()
+                           for a in (xyz, feat, size))
+            tickets.append(((k0, k1 - k0), self.engine.submit_host(*staged)))
+            if len(tickets) >= self.engine.slots:
+                drain_one()
+        while tickets:
+            drain_one()
+        mine_x = torch.cat(outs_x) if outs_x else torch.empty((0,))
+        mine_f = torch.cat(outs_f) if outs_f else torch.empty((0,))
+        if not gather or self.world == 1:
+            return mine_x, mine_f
+        import torch.distributed as dist
+        parts = [None] * self.world if self.rank == 0 else None
+        dist.gather_object((mine_x, mine_f), parts, dst=0)       # control plane only: results leave the GPUs as host tensors
+        if self.rank != 0:
+            return mine_x, mine_f
+        return (torch.cat([p[0] for p in parts if p[0].numel()]), torch.cat([p[1] for p in parts if p[1].numel()]))

@@ -34,6 +34,8 @@ FAST_SA = [True]
 # Scheduling hint for the fused-MLP launches issued from Python (never changes results): minimum 128-row tiles per
 # CTA.  engine.PipelinedHotPath raises it while it captures its graphs (narrower grids for the small stages).
 TILES_PER_CTA = [1]
+# general kernel only: 0 = automatic, 1 = never, 2 = always (where the shape allows) two tiles per context and phase
+SUPER_TILES = [0]
 # tools: skip the (B,C,P) f32 output of the specialised SA stages (only the channel-last bf16 twin is written)
 _WANT_CF = [True]
 
@@ -228,7 +230,11 @@ def fused_sa_fast(mlp: "PreparedMLP", inst: int, layout: Layout, B, N, P, feat_c
     E = len(layout.extra_cols)
     xyzw = None
     with torch.cuda.device(dev):
-        if E <= 1:      # gathered source of the special K step as one 16-byte row per point
+        if E == 0:
+            xyzw = getattr(xyz, "_sad_xyzw", None)      # written next to new_xyz by ops.gather_points
+            if xyzw is not None and tuple(xyzw.shape) != (B, N, 4):
+                xyzw = None
+        if xyzw is None and E <= 1:      # gathered source of the special K step as one 16-byte row per point
             xyzw = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
             _lib.check(_lib.load().sad_pack_xyzw(B, N, _ptr(xyz), _ptr(extra if E else None), _ptr(xyzw), _stream(xyzw)),
                        "pack_xyzw")
@@ -282,11 +288,12 @@ def fused_mlp(mlp: PreparedMLP, layout: Layout, B, N, P, S, feat_cl=None, feat2_
     out_cl = torch.empty((B, P, c_last), dtype=torch.bfloat16, device=dev) if want_cl else None
     E = len(layout.extra_cols)
     counter = torch.zeros(1, dtype=torch.int32, device=dev) if DYNAMIC_TILES else None
+    opts = _lib.MlpOpts(int(TILES_PER_CTA[0]), int(SUPER_TILES[0]))
     with torch.cuda.device(dev):
         rc = _lib.load().sad_shared_mlp_fwd(
             B, N, P, S, _ptr(feat_cl), layout.c0, _ptr(feat2_cl), layout.c1, _ptr(xyz), _ptr(new_xyz), _ptr(idx),
             float(radius), _ptr(radius_t), int(bool(normalize_xyz)), _ptr(extra), E, len(mlp), w_ptrs, b_ptrs, c_arr,
-            int(bool(last_relu)), _ptr(out_cl), _ptr(out_cf), _ptr(counter),
+            int(bool(last_relu)), _ptr(out_cl), _ptr(out_cf), _ptr(counter), ctypes.byref(opts),
             _VP(torch.cuda.current_stream(dev).cuda_stream))
     _lib.check(rc, "shared_mlp")
     return out_cf, out_cl

@@ -113,7 +113,12 @@ class SharedMLP(nn.Module):
 
 
 def _gather_xyz(xyz: torch.Tensor, inds: torch.Tensor) -> torch.Tensor:
-    """new_xyz (B,npoint,3) = xyz[b, inds[b]] through gather_operation (lineage idiom)."""
+    """new_xyz (B,npoint,3) = xyz[b, inds[b]]: one launch when no gradient is wanted, else through gather_operation
+    (lineage idiom: transpose, gather, transpose)."""
+    if not (torch.is_grad_enabled() and xyz.requires_grad):
+        out, xyzw = ops.gather_points(xyz, inds, with_xyzw=True)
+        out._sad_xyzw = xyzw          # padded twin: what the next stage's fused kernel gathers its special K step from
+        return out
     flipped = xyz.transpose(1, 2).contiguous()
     return ops.gather_operation(flipped, inds).transpose(1, 2).contiguous()
 
@@ -183,6 +188,9 @@ class PointnetFPModule(nn.Module):
     @staticmethod
     def interpolation_plan(unknown, known):
         """three_nn + inverse-distance weights (depends on coordinates only) -> (idx, weight)."""
+        if not (torch.is_grad_enabled() and (unknown.requires_grad or known.requires_grad)):
+            _, idx, weight = ops.three_nn_weights(unknown, known)      # one launch, weights bit-equal to the lines below
+            return idx, weight
         dist, idx = ops.three_nn(unknown, known)
         dist_recip = 1.0 / (dist + 1e-8)
         norm = (dist_recip[..., 0] + dist_recip[..., 1]) + dist_recip[..., 2]

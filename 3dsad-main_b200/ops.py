@@ -92,7 +92,7 @@ def build_scene_grid(xyz: torch.Tensor) -> SceneGrid:
 # Scenes at least this large get a scene grid built on the fly by furthest_point_sample / ball_query
 # when the caller passes none (the build costs one short kernel; below it the plain kernels win).
 GRID_MIN_POINTS = 8192
-FPS_POLICIES = {"latency": 0, "throughput": 1}        # include/sad_ops.h SAD_FPS_LATENCY / SAD_FPS_THROUGHPUT
+FPS_POLICIES = {"latency": 0, "throughput": 1, "throughput_paired": 2}   # include/sad_ops.h SAD_FPS_*
 
 
 # Under torch.autocast the differentiable ops run in fp32 (bf16 features are cast on entry, gradients come back in the
@@ -104,10 +104,11 @@ _amp_bwd = torch.amp.custom_bwd(device_type="cuda")
 class FurthestPointSampling(Function):
     """a1.  xyz (B,N,3) f32 -> (B,npoint) i32; sel[0]=0, ties to the lowest index.
     Optional `grid` (SceneGrid of the same xyz) selects the exact culled kernel; `policy` picks how it is scheduled
-    ("latency": a cluster of SMs per scene, "throughput": one SM per scene) -- never the result."""
+    ("latency": a cluster of SMs per scene, "throughput": one SM per scene, "throughput_paired": two scenes per
+    SM) -- never the result.  `variant` (tests / tools): forced cluster size of the kernel, 0 = the default."""
 
     @staticmethod
-    def forward(ctx, xyz, npoint, grid=None, policy="latency", prefix_ordered=False):
+    def forward(ctx, xyz, npoint, grid=None, policy="latency", prefix_ordered=False, variant=0):
         _req(xyz, "xyz", torch.float32, 3, 3)
         B, N, _ = xyz.shape
         npoint = int(npoint)
@@ -130,17 +131,17 @@ class FurthestPointSampling(Function):
             if grid is not None and N <= lib.sad_fps_grid_max_points():
                 grid.check(xyz)
                 _lib.check(lib.sad_furthest_point_sample_grid_policy_fwd(
-                    B, N, npoint, _p(xyz), _p(grid.workspace), _p(out), FPS_POLICIES[policy], _stream(xyz)),
+                    B, N, npoint, _p(xyz), _p(grid.workspace), _p(out), FPS_POLICIES[policy], int(variant), _stream(xyz)),
                     "furthest_point_sample_grid")
             else:
-                _lib.check(lib.sad_furthest_point_sample_fwd(B, N, npoint, _p(xyz), _p(out), _stream(xyz)),
+                _lib.check(lib.sad_furthest_point_sample_cs_fwd(B, N, npoint, _p(xyz), _p(out), int(variant), _stream(xyz)),
                            "furthest_point_sample")
         ctx.mark_non_differentiable(out)
         return out
 
     @staticmethod
     def backward(ctx, grad=None):
-        return None, None, None, None, None
+        return None, None, None, None, None, None
 
 
 class GatherOperation(Function):
@@ -356,8 +357,54 @@ three_interpolate = ThreeInterpolate.apply
 
 def size_to_radius(size: torch.Tensor, alpha: float = 1.0, r_min: float = 0.1, r_max: float = 1.2):
     """Predicted box size (B,K,3) -> per-cluster radius (B,K):
-    r = clamp(alpha * 0.5 * ||size||_2, r_min, r_max)   [SURVEY a4, DECISION: formula unpinned]."""
+    r = clamp(alpha * 0.5 * ||size||_2, r_min, r_max)   [SURVEY a4, DECISION: formula unpinned].
+    One kernel on CUDA inputs without autograd (bit-equal to the torch expression below and to the oracle)."""
+    if size.is_cuda and not (torch.is_grad_enabled() and size.requires_grad) and size.dtype == torch.float32 \
+            and size.dim() >= 1 and size.shape[-1] == 3:
+        s = size.contiguous()
+        out = torch.empty(s.shape[:-1], dtype=torch.float32, device=s.device)
+        with torch.cuda.device(s.device):
+            _lib.check(_lib.load().sad_size_to_radius(out.numel(), _p(s), float(alpha), float(r_min), float(r_max), _p(out),
+                                                      _stream(s)), "size_to_radius")
+        return out
     s = size.float()
     n2 = (s[..., 0] * s[..., 0] + s[..., 1] * s[..., 1]) + s[..., 2] * s[..., 2]
     r = (alpha * 0.5) * torch.sqrt(n2)
     return r.clamp(min=r_min, max=r_max).contiguous()
+
+
+def gather_points(xyz: torch.Tensor, inds: torch.Tensor, with_xyzw: bool = False):
+    """new_xyz (B,npoint,3) = xyz[b, inds[b, j], :] in one launch, no autograd (coordinates are inputs).  With
+    `with_xyzw` also returns the padded (B,npoint,4) copy the fused SA kernel gathers its special K step from."""
+    _req(xyz, "xyz", torch.float32, 3, 3)
+    _req(inds, "inds", torch.int32, 2)
+    _same_dev(xyz, inds)
+    B, N, _ = xyz.shape
+    P = inds.shape[1]
+    out = torch.empty((B, P, 3), dtype=torch.float32, device=xyz.device)
+    xyzw = torch.empty((B, P, 4), dtype=torch.float32, device=xyz.device) if with_xyzw else None
+    with torch.cuda.device(xyz.device):
+        _lib.check(_lib.load().sad_gather_points_fwd(B, N, P, _p(xyz), _p(inds), _p(out),
+                                                     _p(xyzw) if xyzw is not None else _VP0, _stream(xyz)), "gather_points")
+    return (out, xyzw) if with_xyzw else out
+
+
+def three_nn_weights(unknown: torch.Tensor, known: torch.Tensor):
+    """three_nn plus the FP module's normalised inverse-distance weights in the same launch
+    -> dist (B,n,3), idx (B,n,3) i32, weight (B,n,3); no autograd (coordinates only)."""
+    _req(unknown, "unknown", torch.float32, 3, 3)
+    _req(known, "known", torch.float32, 3, 3)
+    _same_dev(unknown, known)
+    B, n, _ = unknown.shape
+    m = known.shape[1]
+    if known.shape[0] != B:
+        raise ValueError("three_nn: batch mismatch")
+    if m < 3:
+        raise ValueError("three_nn requires m >= 3 known points")
+    dist = torch.empty((B, n, 3), dtype=torch.float32, device=unknown.device)
+    idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknown.device)
+    weight = torch.empty((B, n, 3), dtype=torch.float32, device=unknown.device)
+    with torch.cuda.device(unknown.device):
+        _lib.check(_lib.load().sad_three_nn_weights_fwd(B, n, m, _p(unknown), _p(known), _p(dist), _p(idx), _p(weight),
+                                                        _stream(unknown)), "three_nn_weights")
+    return dist, idx, weight

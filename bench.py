@@ -417,10 +417,11 @@ def run_ours(args):
 
     # distinct scenes per rank and per rotating input set; the sets together exceed L2 (126 MB),
     # so no step finds its inputs cached from an earlier one
+    from sad_b200 import dist as D          # the package's scene-sharding / max-over-ranks bookkeeping
     NSETS = args.sets
     sets = []
     for s in range(NSETS):
-        first = (rank * NSETS + s) * B_PER_GPU
+        first = D.weak_scaling_first_scene(rank, B_PER_GPU, input_sets=NSETS, set_index=s)
         xyz, feat = make_scenes(B_PER_GPU, N_POINTS, "surface", first_scene=first)
         size = make_sizes(B_PER_GPU, LAYER_CFG["agg"][0], first_scene=first)
         host = tuple(torch.from_numpy(a).pin_memory() for a in (xyz, feat, size))
@@ -432,8 +433,7 @@ def run_ours(args):
     main = torch.cuda.current_stream(dev)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        D.barrier()
         torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM, K batches through the pipelined executor, device-timed
@@ -491,10 +491,7 @@ def run_ours(args):
     d2h = sum(int(o.numel() * o.element_size()) for o in out_host)
 
     # ---- max over ranks
-    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    total_ms, e2e_ms = D.reduce_scalars([total_ms, e2e_s * 1e3], "max", device=dev)
     scenes = B_PER_GPU * world * args.steps
     value = scenes / (total_ms / 1e3)
     e2e_value = scenes / (e2e_ms / 1e3)
@@ -579,7 +576,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slots", type=int, default=32, help="batches in flight in the pipelined executor")
-    ap.add_argument("--fps-policy", default="throughput", choices=["throughput", "latency"],
+    ap.add_argument("--fps-policy", default="throughput", choices=["throughput", "throughput_paired", "latency"],
                     help="scheduling of the 40k-point FPS (same indices either way)")
     ap.add_argument("--sets", type=int, default=32, help="rotating input sets (32 x 5.1 MB > L2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -15,7 +15,8 @@
  *    fp32, idx = int32; bf16 tensors are passed as const void* / void*;
  *  - every call is asynchronous on `stream` (a cudaStream_t / CUstream handle; NULL =
  *    legacy default stream), performs no host<->device synchronisation and keeps no
- *    global mutable state besides a thread-local error string;
+ *    global mutable state besides a thread-local error string: scheduling choices (FPS policy / variant, fused-MLP
+ *    grid width) are explicit arguments, and the library never reads the environment;
  *  - return value: SAD_OK (0) or a negative SAD_E* code; never throws, never aborts;
  *  - arithmetic contract: fp32, no FMA contraction,
  *    d2 = ((dx*dx)+(dy*dy))+(dz*dz), strict d2 < r*r, ties to the lowest index.
@@ -80,15 +81,16 @@ SAD_API int sad_furthest_point_sample_grid_fwd(int B, int N, int npoint, const f
  * fewest-CTA cluster whose shared memory holds the scene -- shortest time per scene (40k points: 4 SMs, 0.70 us per
  * pick).  SAD_FPS_THROUGHPUT: ONE SM per scene over the L2-resident sorted array (1.5 us per pick, i.e. about half
  * the SM-time per scene): what a pipelined caller with other kernels to overlap wants (writes the workspace's
- * min-distance scratch, so two calls must not share a workspace). */
+ * min-distance scratch, so two calls must not share a workspace).
+ * SAD_FPS_THROUGHPUT_PAIRED: two scenes share one SM (16 warps each): ~30 % less SM-time again, longer per scene.
+ * `variant` (tests / tools; results never depend on it): 0 = the policy's kernel; 1,2,4,8,16 = the cluster kernel with
+ * at least that many CTAs per scene; -1 = the single-SM kernel. */
 #define SAD_FPS_LATENCY 0
 #define SAD_FPS_THROUGHPUT 1
+#define SAD_FPS_THROUGHPUT_PAIRED 2
 SAD_API int sad_furthest_point_sample_grid_policy_fwd(int B, int N, int npoint, const float* xyz,
-                                                      void* grid_workspace, int32_t* idx, int policy,
+                                                      void* grid_workspace, int32_t* idx, int policy, int variant,
                                                       sad_stream_t stream);
-/* Test / benchmark hook: 0 = default; 1,2,4,8,16 = cluster kernel with at least that many CTAs per
- * scene; -1 = single-CTA kernel.  Results never depend on it. */
-SAD_API void sad_fps_grid_force_cluster(int cluster_size);
 /* a3 / a4 over the grid: radius_t (B,npoint) per-query radius or NULL (then `radius`). */
 SAD_API int sad_ball_query_grid_fwd(int B, int N, int npoint, float radius, const float* radius_t,
                                     int nsample, const float* xyz, const void* grid_workspace,
@@ -126,6 +128,18 @@ SAD_API int sad_grouping_operation_bwd(int B, int C, int N, int npoint, int nsam
  * -> dist (B,n,3) f32 (sqrt of d2, ascending), idx (B,n,3) i32. */
 SAD_API int sad_three_nn_fwd(int B, int n, int m, const float* unknown, const float* known, float* dist,
                      int32_t* idx, sad_stream_t stream);
+/* a8 + the FP module's inverse-distance weights in the same launch: weight (B,n,3) = r / ((r0 + r1) + r2),
+ * r = 1 / (dist + 1e-8), evaluated in that order (bit-equal to the oracle's interpolation_weights). */
+SAD_API int sad_three_nn_weights_fwd(int B, int n, int m, const float* unknown, const float* known, float* dist,
+                                     int32_t* idx, float* weight, sad_stream_t stream);
+/* a4 helper: predicted box size (rows,3) -> per-cluster radius = clamp(alpha/2 * ||size||_2, r_min, r_max), norm
+ * evaluated as sqrt(((sx*sx)+(sy*sy))+(sz*sz)) (formula unpinned by the reference: SURVEY a4 DECISION). */
+SAD_API int sad_size_to_radius(long long rows, const float* size, float alpha, float r_min, float r_max, float* radius,
+                               sad_stream_t stream);
+/* new_xyz (B,npoint,3) = xyz[b, inds[b,j], :] from the (B,N,3) layout in one launch; new_xyzw (optional, (B,npoint) float4
+ * {x,y,z,0}) is the padded copy sad_sa_mlp_fwd gathers from. */
+SAD_API int sad_gather_points_fwd(int B, int N, int npoint, const float* xyz, const int32_t* inds, float* new_xyz,
+                                  void* new_xyzw, sad_stream_t stream);
 
 /* a9  three_interpolate: out[b,c,i] = ((w0*f[i0]) + (w1*f[i1])) + (w2*f[i2]).
  * features (B,C,m) f32, idx (B,n,3) i32, weight (B,n,3) f32 -> out (B,C,n) f32. */
@@ -197,17 +211,21 @@ SAD_API int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* feat_c
                            int normalize_xyz, const float* extra, int E, const void* w_image, const float* bias3_padded, int c3, void* out_cl_bf16,
                            float* out_cf_f32, int* sched, int tiles_per_cta, sad_stream_t stream);
 
-/* Scheduling hint for the calling thread's sad_shared_mlp_fwd launches (never changes results): at least `tiles`
- * 128-row tiles per CTA, i.e. a narrower grid for the small stages.  1 (default) = one CTA per SM whenever there are
- * that many tiles: shortest time for one launch.  A pipelined caller with other streams to fill the SMs wants ~6
- * (fewer per-CTA prologues, less SM-time; engine.PipelinedHotPath sets it while it captures its graphs). */
-SAD_API void sad_mlp_set_tiles_per_cta(int tiles);
+/* Scheduling options of one sad_shared_mlp_fwd launch (never change results); NULL = defaults.
+ *   tiles_per_cta  at least this many 128-row tiles per CTA, i.e. a narrower grid for the small stages.  1 (default) =
+ *                  one CTA per SM whenever there are that many tiles: shortest time for one launch.  A pipelined
+ *                  caller with other streams to fill the SMs wants ~6 (fewer per-CTA prologues, less SM-time).
+ *   super_tiles    0 = automatic, 1 = never, 2 = always (when the shape allows) two tiles per context and phase. */
+typedef struct sad_mlp_opts {
+  int tiles_per_cta;
+  int super_tiles;
+} sad_mlp_opts;
 SAD_API int sad_shared_mlp_fwd(int B, int N, int P, int S, const void* feat_cl, int C0,
                                const void* feat2_cl, int C1in, const float* xyz, const float* new_xyz,
                                const int32_t* idx, float radius, const float* radius_t,
                                int normalize_xyz, const float* extra, int E, int n_layers,
                                const void* const* w_img, const float* const* bias, const int* c_out,
-                               int last_relu, void* out_cl_bf16, float* out_cf_f32, int* tile_counter,
+                               int last_relu, void* out_cl_bf16, float* out_cf_f32, int* tile_counter, const sad_mlp_opts* opts,
                                sad_stream_t stream);
 
 /* a9 on the internal layout: features (B,m,C) bf16 channel-last -> out (B,n,C) bf16 (C % 8 == 0). */
@@ -222,9 +240,10 @@ SAD_API int sad_cf_to_cl_bf16(int B, int C, int N, const float* in_cf, void* out
 /* Number of kernels this library has launched in this process (all threads, monotonic). */
 SAD_API unsigned long long sad_launch_count(void);
 
-/* Test / benchmark hook: force the FPS thread-block-cluster size for subsequent calls on
- * this thread (1,2,4,8,16; 0 = built-in heuristic).  Results never depend on it. */
-SAD_API void sad_fps_force_cluster_size(int cluster_size);
+/* a1 with an explicit thread-block-cluster size (tests / tools: 1,2,4,8,16; 0 = the built-in heuristic, i.e.
+ * sad_furthest_point_sample_fwd).  Results never depend on it. */
+SAD_API int sad_furthest_point_sample_cs_fwd(int B, int N, int npoint, const float* xyz, int32_t* idx, int cluster_size,
+                                             sad_stream_t stream);
 
 #ifdef __cplusplus
 }

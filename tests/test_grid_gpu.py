@@ -96,11 +96,7 @@ def test_culled_fps_every_kernel_variant_is_bitexact(ops, cs):
     xyz = scene(rng, 2, 9000, 0.125)          # lattice => many exact ties
     want = C.furthest_point_sample(xyz, 300)
     x = cu(xyz)
-    _lib.load().sad_fps_grid_force_cluster(cs)
-    try:
-        got = ops.furthest_point_sample(x, 300, ops.build_scene_grid(x))
-    finally:
-        _lib.load().sad_fps_grid_force_cluster(0)
+    got = ops.furthest_point_sample(x, 300, ops.build_scene_grid(x), "latency", False, cs)
     assert np.array_equal(got.cpu().numpy(), want)
 
 

@@ -80,10 +80,11 @@ def test_fused_sa_stage(B, N, P, S, Cf, hidden, radius, adaptive):
 
 @pytest.mark.parametrize("B,N,P,S", [(2, 3000, 64, 64), (1, 3000, 37, 64), (3, 4000, 333, 64), (2, 3000, 500, 16)])
 def test_fused_sa_stage_super_tiles(B, N, P, S, monkeypatch):
-    """SAD_MLP_T=2 forces two tiles per context and phase (what SA1 runs at full size) on small shapes: CTAs with one
-    tile, odd tile counts, a partial last tile."""
+    """sad_mlp_opts.super_tiles = 2 forces two tiles per context and phase in the general kernel (what it runs for SA1
+    at full size) on small shapes: CTAs with one tile, odd tile counts, a partial last tile."""
     from sad_b200 import mlp as M
-    monkeypatch.setenv("SAD_MLP_T", "2")
+    monkeypatch.setattr(M, "SUPER_TILES", [2])
+    monkeypatch.setattr(M, "FAST_SA", [False])
     rng = np.random.default_rng(N + P + S)
     xyz = (rng.random((B, N, 3), dtype=np.float32) * 3).astype(np.float32)
     feat = rng.standard_normal((B, 1, N)).astype(np.float32)

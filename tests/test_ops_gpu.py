@@ -58,11 +58,7 @@ def test_fps_every_cluster_size_is_bitexact(ops, cs):
     rng = np.random.default_rng(cs)
     xyz = scene(rng, 3, 6000, 0.125)          # lattice => many exact ties
     want = C.furthest_point_sample(xyz, 300)
-    _lib.load().sad_fps_force_cluster_size(cs)
-    try:
-        got = ops.furthest_point_sample(cu(xyz), 300)
-    finally:
-        _lib.load().sad_fps_force_cluster_size(0)
+    got = ops.furthest_point_sample(cu(xyz), 300, None, "latency", False, cs)
     assert np.array_equal(got.cpu().numpy(), want)
 
 
@@ -269,3 +265,27 @@ def test_fps_prefix_ordered_matches_sampler(case):
         Y = np.stack([Y[b][want[b]] for b in range(Y.shape[0])]) if K > 1 else Y
     if case == "random":
         assert (want >= 0).all()
+
+
+def test_glue_kernels_match_their_torch_expressions():
+    """the one-launch replacements of the torch glue are bit-equal to what they replace and to the
+    oracle: new_xyz gather, three_nn + normalised weights, size -> radius."""
+    from sad_b200 import ops
+    rng = np.random.default_rng(11)
+    xyz = (rng.random((3, 5000, 3), dtype=np.float32) * 5).astype(np.float32)
+    inds = C.furthest_point_sample(xyz, 257)
+    want_xyz = np.stack([xyz[b][inds[b]] for b in range(3)])
+    got, got4 = ops.gather_points(cu(xyz), cu(inds), with_xyzw=True)
+    assert np.array_equal(got.cpu().numpy(), want_xyz)
+    assert np.array_equal(got4.cpu().numpy()[..., :3], want_xyz) and not got4.cpu().numpy()[..., 3].any()
+    unknown = (rng.random((2, 700, 3), dtype=np.float32) * 4).astype(np.float32)
+    known = (rng.random((2, 130, 3), dtype=np.float32) * 4).astype(np.float32)
+    known[0, 5] = unknown[0, 9]                        # a zero distance: weight = 1 / 1e-8 normalised
+    d, i, w = ops.three_nn_weights(cu(unknown), cu(known))
+    wd, wi = O.three_nn(unknown, known)
+    assert np.array_equal(i.cpu().numpy(), wi) and np.array_equal(d.cpu().numpy(), wd)
+    assert np.array_equal(w.cpu().numpy(), O.interpolation_weights(wd))
+    size = (rng.random((4, 256, 3), dtype=np.float32) * 3).astype(np.float32)
+    for (alpha, lo, hi) in ((1.0, 0.1, 1.2), (0.7, 0.05, 0.9)):
+        r = ops.size_to_radius(cu(size), alpha, lo, hi)
+        assert np.array_equal(r.cpu().numpy(), O.size_to_radius(size, alpha, lo, hi))

@@ -30,16 +30,14 @@ def t(fn, it=10):
 
 ref = None
 for cs in (0, -1, 4, 8):
-    lib.sad_fps_grid_force_cluster(cs)
     try:
-        ms = t(lambda: ops.furthest_point_sample(x, npnt, g))
+        ms = t(lambda: ops.furthest_point_sample(x, npnt, g, "latency", False, cs))
     except RuntimeError as e:
         print(f"cs={cs}: {e}")
         continue
-    out = ops.furthest_point_sample(x, npnt, g)
+    out = ops.furthest_point_sample(x, npnt, g, "latency", False, cs)
     if ref is None:
         ref = out
     same = bool((out == ref).all())
     eff = cs if cs else "auto"
     print(f"N={N} npoint={npnt} cs={eff}: {1e3 * ms:8.1f} us  ({1e3 * ms / (npnt - 1) * 1.0:6.3f} us/pick)  same={same}", flush=True)
-lib.sad_fps_grid_force_cluster(0)

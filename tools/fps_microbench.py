@@ -31,10 +31,7 @@ for (N, npnt) in [(40000, 2048), (2048, 1024), (1024, 512), (512, 256)]:
     g = ops.build_scene_grid(x)
     build = t(lambda: ops.build_scene_grid(x))
     cull = t(lambda: ops.furthest_point_sample(x, npnt, g), it=3 if os.environ.get("SAD_B200_LIB") else 10)
-    from sad_b200 import _lib
-    _lib.load().sad_fps_grid_force_cluster(-1)
-    one = t(lambda: ops.furthest_point_sample(x, npnt, g), it=3)
-    _lib.load().sad_fps_grid_force_cluster(0)
+    one = t(lambda: ops.furthest_point_sample(x, npnt, g, "throughput"), it=3)
     print(f"N={N:6d} -> {npnt:5d}: plain {1e3 * plain:8.1f} us   grid build {1e3 * build:6.1f} us   culled {1e3 * cull:8.1f} us   "
           f"single-CTA culled {1e3 * one:8.1f} us", flush=True)
     inds = ops.furthest_point_sample(x, npnt, g).long()

@@ -90,13 +90,11 @@ def main():
     # ---- FPS at every cluster size
     lib = _lib.load()
     for cs in (0, 4, 8, 16):
-        lib.sad_fps_force_cluster_size(cs)
         try:
-            ms, best = timeit(lambda: S.furthest_point_sample(xyz, 2048), iters=10, warm=2)
+            ms, best = timeit(lambda: S.furthest_point_sample(xyz, 2048, None, "latency", False, cs), iters=10, warm=2)
             row(f"fps N={N}->2048 cs={cs or 'auto'}", ms, best, note=f"{2047 / best:.0f} iters/ms")
         except Exception as e:  # noqa: BLE001
             print("fps", cs, "failed:", e)
-    lib.sad_fps_force_cluster_size(0)
     inds = S.furthest_point_sample(xyz, 2048)
     new_xyz = S.gather_operation(xyz.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
     for (n_in, n_out) in ((2048, 1024), (1024, 512), (512, 256)):

@@ -52,8 +52,6 @@ def main():
     dev, B = "cuda", args.batch
     M.TILES_PER_CTA[0] = args.tpc
     M._WANT_CF[0] = not args.no_cf
-    from sad_b200 import _lib
-    _lib.load().sad_mlp_set_tiles_per_cta(args.tpc)
     rows = []
     stages = [("sa1", 40000, 2048, 64, 1, [64, 64, 128]), ("sa2", 2048, 1024, 32, 128, [128, 128, 256]),
               ("sa3", 1024, 512, 16, 256, [128, 128, 256]), ("sa4", 512, 256, 16, 256, [128, 128, 256]),
