@@ -51,12 +51,16 @@ SIGNATURES = {
     "sad_pack_xyzw": [_c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_sa_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_float, _vp, _c_int, _vp, _c_int, _vp, _vp,
                        _c_int, _vp, _vp, _vp, _c_int, _vp],
+    "sad_pw_mlp_image_bytes": [_c_int],
+    "sad_pw_mlp_pack": [_c_int, _vp, _vp, _vp, _c_int, _vp],
+    "sad_pw_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp,
+                       _c_int, _vp],
     "sad_three_interpolate_cl_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_cf_to_cl_bf16": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
 }
 _RESTYPES = {"sad_last_error_string": ctypes.c_char_p,
              "sad_launch_count": ctypes.c_ulonglong, "sad_scene_grid_workspace_bytes": ctypes.c_longlong, "sad_mlp_weight_image_bytes": ctypes.c_longlong,
-             "sad_sa_mlp_image_bytes": ctypes.c_longlong}
+             "sad_sa_mlp_image_bytes": ctypes.c_longlong, "sad_pw_mlp_image_bytes": ctypes.c_longlong}
 
 class MlpOpts(ctypes.Structure):
     """include/sad_ops.h sad_mlp_opts"""

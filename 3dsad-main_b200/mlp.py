@@ -299,6 +299,73 @@ def fused_mlp(mlp: PreparedMLP, layout: Layout, B, N, P, S, feat_cl=None, feat2_
     return out_cf, out_cl
 
 
+# ----------------------------------------------------------------------------- point-wise fast path (csrc/mlp_pw.cu)
+FAST_PW = [True]      # False: FP / voting stages through the general kernel (tests compare the two)
+
+
+def _packed_pw(mlp: PreparedMLP, kind: int):
+    key = ("pw", kind)
+    if key not in mlp._packed:
+        lib = _lib.load()
+        dev = mlp.layers[0][0].device
+        Ws = [np.ascontiguousarray(W.detach().cpu().numpy(), dtype=np.float32) for (W, _) in mlp.layers]
+        bs = [np.ascontiguousarray(b.detach().cpu().numpy(), dtype=np.float32) for (_, b) in mlp.layers]
+        c_last = Ws[-1].shape[0]
+        img = np.zeros(int(lib.sad_pw_mlp_image_bytes(kind)), dtype=np.uint8)
+        W2 = Ws[1] if len(Ws) == 3 else None
+        _lib.check(lib.sad_pw_mlp_pack(kind, _VP(Ws[0].ctypes.data), _VP(W2.ctypes.data) if W2 is not None else _VP(0),
+                                       _VP(Ws[-1].ctypes.data), int(c_last), _VP(img.ctypes.data)), "pw_mlp_pack")
+        bl = np.zeros(384, dtype=np.float32)
+        bl[:c_last] = bs[-1]
+        mlp._packed[key] = (torch.from_numpy(img).to(dev), torch.from_numpy(bs[0]).to(dev),
+                            torch.from_numpy(bs[1]).to(dev) if len(bs) == 3 else None, torch.from_numpy(bl).to(dev))
+    return mlp._packed[key]
+
+
+def _pw_tiles_per_cta():
+    return min(2, int(TILES_PER_CTA[0]))      # these stages have 32-64 tiles: keep them spread over the SMs
+
+
+def fp_interp_mlp_fast(known_cl, skip_cl, idx, weight, mlp: PreparedMLP, B, m, n):
+    """FP module in ONE launch: interpolation + concat + MLP -> (out_cf (B,C,n) f32, out_cl (B,n,C) bf16)."""
+    img, b1, _, bl = _packed_pw(mlp, 0)
+    dev = img.device
+    c_last = mlp.c_out[-1]
+    out_cf = torch.empty((B, c_last, n), dtype=torch.float32, device=dev)
+    out_cl = torch.empty((B, n, c_last), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().sad_pw_mlp_fwd(0, B, n, m, _ptr(skip_cl), _ptr(known_cl), _ptr(idx), _ptr(weight), _ptr(img),
+                                        _ptr(b1), _VP(0), _ptr(bl), c_last, _ptr(out_cf), _ptr(out_cl), _VP(0), _VP(0), _VP(0),
+                                        _pw_tiles_per_cta(), _VP(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "pw_mlp (FP)")
+    return out_cf, out_cl
+
+
+def vote_mlp_fast(seed_xyz, seed_features, mlp: PreparedMLP):
+    """Voting module in ONE launch: 3-layer MLP + (vote = seed + y) -> vote_xyz (B,n,3), vote_features (B,256,n) f32
+    carrying its bf16 channel-last twin."""
+    B, C, n = seed_features.shape
+    img, b1, b2, bl = _packed_pw(mlp, 1)
+    dev = img.device
+    seed_cl = to_cl_bf16(seed_features)
+    sf = seed_features.contiguous()
+    vote_xyz = torch.empty((B, n, 3), dtype=torch.float32, device=dev)
+    out_cf = torch.empty((B, 256, n), dtype=torch.float32, device=dev)
+    out_cl = torch.empty((B, n, 256), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().sad_pw_mlp_fwd(1, B, n, 0, _ptr(seed_cl), _VP(0), _VP(0), _VP(0), _ptr(img), _ptr(b1), _ptr(b2),
+                                        _ptr(bl), 259, _ptr(out_cf), _ptr(out_cl), _ptr(seed_xyz.contiguous()), _ptr(sf),
+                                        _ptr(vote_xyz), _pw_tiles_per_cta(),
+                                        _VP(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "pw_mlp (voting)")
+    return vote_xyz, _attach(out_cf, out_cl)
+
+
+def vote_fast_ok(seed_features, mlp: PreparedMLP) -> bool:
+    B, C, n = seed_features.shape
+    return bool(FAST_PW[0]) and C == 256 and n % 128 == 0 and mlp.c_out == [256, 256, 259] and seed_features.dtype == torch.float32
+
+
 # ----------------------------------------------------------------------------- stage entry points
 def sa_group_mlp(xyz, new_xyz, features, idx, radius, mlp: PreparedMLP, use_xyz=True, normalize_xyz=True):
     """Group (relative, optionally radius-normalised xyz ++ features) -> MLP -> max over nsample.
@@ -337,6 +404,10 @@ def fp_interp_mlp(known_feats, unknow_feats, idx, weight, mlp: PreparedMLP):
         interp = ops.three_interpolate(known_feats.contiguous(), idx, weight)
         x = interp if unknow_feats is None else torch.cat([interp, unknow_feats], dim=1)
         return composed_pointwise(x, mlp, last_relu=True)
+    if FAST_PW[0] and C2 == 256 and c_skip == 256 and n % 128 == 0 and mlp.c_out[0] == 256 and len(mlp) == 2 \
+            and 8 <= mlp.c_out[1] <= 256:
+        out_cf, out_cl = fp_interp_mlp_fast(to_cl_bf16(known_feats), to_cl_bf16(unknow_feats), idx, weight, mlp, B, m, n)
+        return _attach(out_cf, out_cl)
     layout = fp_layout(C2, c_skip)
     known_cl = to_cl_bf16(known_feats, pad_to=layout.c0)
     interp_cl = torch.empty((B, n, layout.c0), dtype=torch.bfloat16, device=known_cl.device)

@@ -326,7 +326,10 @@ class VotingModule(nn.Module):
 
     def forward(self, seed_xyz, seed_features):
         if not self.training and not torch.is_grad_enabled():
-            y = _mlp.pointwise_mlp(seed_features, self.mlp.folded(), last_relu=False, want_cl=False)
+            folded = self.mlp.folded()
+            if _mlp.vote_fast_ok(seed_features, folded):      # MLP + (vote = seed + y) in one launch
+                return _mlp.vote_mlp_fast(seed_xyz, seed_features, folded)
+            y = _mlp.pointwise_mlp(seed_features, folded, last_relu=False, want_cl=False)
         else:
             y = self.mlp(seed_features.unsqueeze(-1)).squeeze(-1)
         vote_xyz = (seed_xyz + y[:, :3, :].transpose(1, 2)).contiguous()

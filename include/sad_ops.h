@@ -211,6 +211,23 @@ SAD_API int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* feat_c
                            int normalize_xyz, const float* extra, int E, const void* w_image, const float* bias3_padded, int c3, void* out_cl_bf16,
                            float* out_cf_f32, int* sched, int tiles_per_cta, sad_stream_t stream);
 
+/* ---- a6 / a9, shape-specialised POINT-WISE fast path (csrc/mlp_pw.cu): nsample == 1 stages with 256-wide layers.
+ *   kind 0  FP module: [three_interpolate(known) (256) | skip (256)] -> 256 -> c_last (<= 256), ReLU everywhere.  The
+ *           interpolation is computed inside the kernel from known_cl (B*m,256) bf16, nn_idx (B*n,3) (indices into
+ *           the m known points of the same batch element) and nn_w (B*n,3): no three_interpolate launch, no
+ *           interpolated tensor.  src_cl (B*n,256) bf16 = the skip features.
+ *   kind 1  voting module: seed features (256) -> 256 -> 256 -> 3 + 256 (linear), fused with vote = seed + y:
+ *           vote_xyz (B*n,3) = seed_xyz + y[0:3]; out_cf (B,256,n) = seed_cf + y[3:]; out_cl its bf16 twin.
+ * Weights stream through shared memory (sad_pw_mlp_pack: fp32 row-major W1 (256 x K0), W2 (256 x 256, kind 1), Wlast
+ * (c_last x 256) -> image of sad_pw_mlp_image_bytes(kind) bytes).  n must be a multiple of 128.  bias_last_padded has
+ * 256 (kind 0) / 384 (kind 1) entries.  Same math and tolerance as sad_shared_mlp_fwd. */
+SAD_API long long sad_pw_mlp_image_bytes(int kind);
+SAD_API int sad_pw_mlp_pack(int kind, const float* W1, const float* W2, const float* Wlast, int c_last, void* out_image);
+SAD_API int sad_pw_mlp_fwd(int kind, int B, int n, int m, const void* src_cl, const void* known_cl, const int32_t* nn_idx,
+                           const float* nn_w, const void* w_image, const float* bias1, const float* bias2,
+                           const float* bias_last_padded, int c_last, float* out_cf, void* out_cl, const float* seed_xyz,
+                           const float* seed_cf, float* vote_xyz, int tiles_per_cta, sad_stream_t stream);
+
 /* Scheduling options of one sad_shared_mlp_fwd launch (never change results); NULL = defaults.
  *   tiles_per_cta  at least this many 128-row tiles per CTA, i.e. a narrower grid for the small stages.  1 (default) =
  *                  one CTA per SM whenever there are that many tiles: shortest time for one launch.  A pipelined

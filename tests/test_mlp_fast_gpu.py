@@ -95,3 +95,58 @@ def test_fast_sa_stage(name, mode, B, N, P, S, Cf, hidden, radius, adaptive):
     twin = got._sad_cl
     assert tuple(twin.shape) == (B, P, hidden[-1]) and twin.dtype == torch.bfloat16
     close(twin.float().transpose(1, 2), want_bf, 1.2e-2)
+
+
+@pytest.mark.parametrize("tpc", [1, 6])
+@pytest.mark.parametrize("B,n,m", [(1, 128, 64), (2, 512, 256), (8, 1024, 512), (3, 384, 130)])
+def test_fast_fp_stage(B, n, m, tpc, monkeypatch):
+    """csrc/mlp_pw.cu kind 0: three_interpolate + concat + 2-layer MLP in one launch vs the oracle's FP module and vs
+    the general kernel (three_interpolate_cl + fused_mlp_kernel)."""
+    from sad_b200 import mlp as M
+    monkeypatch.setattr(M, "TILES_PER_CTA", [tpc])          # 6 -> two tiles per CTA: the ring wraps across tiles
+    rng = np.random.default_rng(n + m)
+    unknown = (rng.random((B, n, 3), dtype=np.float32) * 4).astype(np.float32)
+    known = (rng.random((B, m, 3), dtype=np.float32) * 4).astype(np.float32)
+    kf = rng.standard_normal((B, 256, m)).astype(np.float32)
+    uf = rng.standard_normal((B, 256, n)).astype(np.float32)
+    layers = make_layers(rng, [512, 256, 256])
+    dist, idx = O.three_nn(unknown, known)
+    w = O.interpolation_weights(dist)
+    x = np.concatenate([O.three_interpolate(kf, idx, w), uf], axis=1)[:, :, :, None]
+    want = O.shared_mlp(x, layers, pool=False)[..., 0]
+    mlp = M.prepare_layers([(cu(W), cu(b)) for W, b in layers])
+    args = (cu(kf), cu(uf), cu(idx), cu(w), mlp)
+    saved = M.FAST_PW[0]
+    try:
+        M.FAST_PW[0] = True
+        got = M.fp_interp_mlp(*args)
+        M.FAST_PW[0] = False
+        ref = M.fp_interp_mlp(*args)
+    finally:
+        M.FAST_PW[0] = saved
+    assert tuple(got.shape) == (B, 256, n)
+    close(got, want, 2e-2)
+    close(got, ref.detach().float().cpu().numpy(), 8e-3)
+    close(got._sad_cl.float().transpose(1, 2), want, 2e-2)
+
+
+@pytest.mark.parametrize("tpc", [1, 6])
+@pytest.mark.parametrize("B,n", [(1, 128), (8, 1024), (2, 384)])
+def test_fast_voting_stage(B, n, tpc, monkeypatch):
+    """csrc/mlp_pw.cu kind 1: 3-layer voting MLP fused with vote = seed + y vs the oracle's voting module."""
+    from sad_b200 import mlp as M
+    monkeypatch.setattr(M, "TILES_PER_CTA", [tpc])
+    rng = np.random.default_rng(n)
+    seed_xyz = (rng.random((B, n, 3), dtype=np.float32) * 4).astype(np.float32)
+    sf = rng.standard_normal((B, 256, n)).astype(np.float32)
+    layers = make_layers(rng, [256, 256, 256, 259])
+    want_xyz, want_feat = O.voting_module(seed_xyz, sf, layers)
+    mlp = M.prepare_layers([(cu(W), cu(b)) for W, b in layers])
+    assert M.vote_fast_ok(cu(sf), mlp)
+    vx, vf = M.vote_mlp_fast(cu(seed_xyz), cu(sf), mlp)
+    close(vx, want_xyz, 2e-2)
+    close(vf, want_feat, 2e-2)
+    close(vf._sad_cl.float().transpose(1, 2), want_feat, 2e-2)
+    # the offsets alone (vote - seed): the bf16 bar at the scale of the MLP output, not of the coordinates
+    y = O.shared_mlp(sf[..., None], layers, pool=False, last_relu=False)[..., 0]
+    close(vx - cu(seed_xyz), y[:, :3, :].transpose(0, 2, 1), 2e-2)

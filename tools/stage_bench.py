@@ -89,6 +89,30 @@ def main():
         rows.append({"stage": name, "kernel": "general", "us": round(med, 1), "best_us": round(best, 1), "GFLOP": round(flops / 1e9, 2),
                      "TFLOPs": round(flops / med / 1e6, 1), "frac_of_peak": round(flops / med / 1e6 / peak, 3)})
         print(rows[-1], flush=True)
+    # the specialised point-wise kernel (FP: interpolation fused; voting: residual fused)
+    for (name, n, m_) in (("fp1", 512, 256), ("fp2", 1024, 512)):
+        kf = torch.randn(B, 256, m_, device=dev); kf._sad_cl = M.to_cl_bf16(kf)
+        uf = torch.randn(B, 256, n, device=dev); uf._sad_cl = M.to_cl_bf16(uf)
+        idx = torch.randint(0, m_, (B, n, 3), device=dev, dtype=torch.int32)
+        w = torch.rand(B, n, 3, device=dev); w = (w / w.sum(-1, keepdim=True)).contiguous()
+        m = layers([512, 256, 256])
+        flops = 2.0 * B * n * (512 * 256 + 256 * 256)
+        for fast in (False, True):
+            M.FAST_PW[0] = fast
+            med, best = t(lambda: M.fp_interp_mlp(kf, uf, idx, w, m))
+            rows.append({"stage": name + "+interp", "kernel": "fast-pw" if fast else "general+interp_cl", "us": round(med, 1),
+                         "best_us": round(best, 1), "GFLOP": round(flops / 1e9, 2), "TFLOPs": round(flops / med / 1e6, 1),
+                         "frac_of_peak": round(flops / med / 1e6 / peak, 3)})
+            print(rows[-1], flush=True)
+    sx = torch.rand(B, 1024, 3, device=dev)
+    sf = torch.randn(B, 256, 1024, device=dev); sf._sad_cl = M.to_cl_bf16(sf)
+    m = layers([256, 256, 256, 259])
+    flops = 2.0 * B * 1024 * (256 * 256 * 2 + 256 * 259)
+    med, best = t(lambda: M.vote_mlp_fast(sx, sf, m))
+    rows.append({"stage": "vote+residual", "kernel": "fast-pw", "us": round(med, 1), "best_us": round(best, 1),
+                 "GFLOP": round(flops / 1e9, 2), "TFLOPs": round(flops / med / 1e6, 1), "frac_of_peak": round(flops / med / 1e6 / peak, 3)})
+    print(rows[-1], flush=True)
+    M.FAST_PW[0] = True
     print(json.dumps({"tpc": args.tpc, "batch": B, "peak_tflops": peak, "rows": rows}))
 
 
