@@ -13,6 +13,7 @@ LAYER_CFG = {
     "sa4": (256, 1.2, 16),
     "agg": (256, 0.3, 16),        # vote aggregation; radius is per-cluster (base 0.3 unused when adaptive)
     "alpha": 1.0, "r_min": 0.1, "r_max": 1.2,
+    "size_scale": 1.0, "size_clip": 2.0,      # size head: size = size_scale * exp(clip(y, -size_clip, size_clip)) [DECISION]
 }
 
 
@@ -27,6 +28,7 @@ def mlp_channels(input_feature_dim: int = 1, seed_feat_dim: int = 256, vote_fact
         "fp2": [256 + 256, 256, 256],
         "vote": [seed_feat_dim, seed_feat_dim, seed_feat_dim, (3 + seed_feat_dim) * vote_factor],
         "agg": [seed_feat_dim + 3, 128, 128, 128],
+        "size": [seed_feat_dim, 128, 3],          # size head: vote features at the cluster centres -> box size (3)
     }
 
 
@@ -45,4 +47,7 @@ def make_params(seed: int = 0, input_feature_dim: int = 1, bias_std: float = 0.0
     Wv, bv = params["vote"][-1]
     Wv[:3] *= np.float32(0.25)
     bv[:3] *= np.float32(0.25)
+    # size head: keep the log-sizes O(0.3) so that the radii spread over the clamp range instead of saturating it
+    Ws, bs = params["size"][-1]
+    Ws *= np.float32(0.3)
     return params

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_mlp_kernel(const __grid_consta
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&ms->wfull[i], 1);
-      mbar_init(&ms->afull[i], kWorkers);
+      mbar_init(&ms->afull[i], kWorkers / 32);      // one arrival per worker warp
       mbar_init(&ms->sfree[i], 1);
       mbar_init(&ms->afree[i], 1);
     }
@@ -248,6 +248,10 @@ __global__ void __launch_bounds__(kThreads, 1) pw_mlp_kernel(const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&ms->actfull);
     };
+    auto publish = [&](int st) {                // this warp's part of the stage's operand chunk is complete
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms->afull[st]);
+    };
     // hidden layer: columns [64 wg, 64 wg + 64) of the 256: TMEM -> +bias -> ReLU -> bf16 -> activation chunk wg
     auto hidden = [&](const float* bias) {
       const int c0 = wg * 64;
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_mlp_kernel(const __grid_consta
           if (!__all_sync(FULL, mbar_try_wait(&ms->afree[st], par))) {
             if (pend_st >= 0) {                 // about to block: publish what is in flight first
               cp_async_wait<0>();
-              mbar_arrive(&ms->afull[pend_st]);
+              publish(pend_st);
               pend_st = -1;
             }
             bar_wait(&ms->afree[st], par);
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_mlp_kernel(const __grid_consta
             }
             sts_v4(dst + swz128(rw[i], un[i]), o[0], o[1], o[2], o[3]);
           }
-          mbar_arrive(&ms->afull[st]);
+          publish((int)st);
         } else {
           const int sc = kc - interp_chunks;
 #pragma unroll
@@ -364,14 +368,14 @@ __global__ void __launch_bounds__(kThreads, 1) pw_mlp_kernel(const __grid_consta
           cp_async_commit();
           if (pend_st >= 0) {
             cp_async_wait<1>();
-            mbar_arrive(&ms->afull[pend_st]);
+            publish(pend_st);
           }
           pend_st = (int)st;
         }
       }
       if (pend_st >= 0) {                        // these warps turn into the epilogue now: nothing may stay pending
         cp_async_wait<0>();
-        mbar_arrive(&ms->afull[pend_st]);
+        publish(pend_st);
       }
       if (warp >= 16) continue;
       // ------------------------------------------------ epilogue: accumulator split 4 ways by columns

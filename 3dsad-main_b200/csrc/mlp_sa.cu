@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
     mbar_init(&ms->p_wfull, 1);
     for (int i = 0; i < kRing; ++i) mbar_init(&ms->tfull[i], 1);
     for (int i = 0; i < 8; ++i) {
-      mbar_init(&ms->full[i], kGatherThreads);   // every gather thread: its special-chunk row + its feature copies
+      mbar_init(&ms->full[i], kGatherThreads / 32);   // one arrival per gather warp (32 same-address arrivals serialise)
       mbar_init(&ms->bfree[i], 1);
       mbar_init(&ms->p_ready[i], 1);
     }
@@ -477,8 +477,9 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
       if (p.radius_t) s.r = ldg_nc_f32(p.radius_t + pt);
       return src;
     };
-    auto publish = [&](int b) {                 // this thread's stores / copies of buffer b are complete
-      mbar_arrive(&ms->full[b]);                // (release; the proxy fence is the consumer's, see the MMA warp)
+    auto publish = [&](int b) {                 // this warp's stores / copies of buffer b are complete
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms->full[b]); // (release; the proxy fence is the consumer's, see the MMA warp)
     };
     // Software pipeline over tiles: two dependent L2 round trips per row (neighbour index, then xyz / features at
     // that index), each requested kDepth tiles before its result is needed -- the inputs of the special K step of

@@ -234,6 +234,10 @@ def fused_sa_fast(mlp: "PreparedMLP", inst: int, layout: Layout, B, N, P, feat_c
             xyzw = getattr(xyz, "_sad_xyzw", None)      # written next to new_xyz by ops.gather_points
             if xyzw is not None and tuple(xyzw.shape) != (B, N, 4):
                 xyzw = None
+        if E == 1:
+            twin = getattr(xyz, "_sad_xyzw1", None)     # prepack_xyzw ran earlier for this (xyz, feature) pair
+            if twin is not None and twin[0] == extra.data_ptr() and twin[1] == extra._version and tuple(twin[2].shape) == (B, N, 4):
+                xyzw = twin[2]
         if xyzw is None and E <= 1:      # gathered source of the special K step as one 16-byte row per point
             xyzw = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
             _lib.check(_lib.load().sad_pack_xyzw(B, N, _ptr(xyz), _ptr(extra if E else None), _ptr(xyzw), _stream(xyzw)),
@@ -244,6 +248,20 @@ def fused_sa_fast(mlp: "PreparedMLP", inst: int, layout: Layout, B, N, P, feat_c
             _ptr(out_cl), _ptr(out_cf), _ptr(sched), int(TILES_PER_CTA[0]), _VP(torch.cuda.current_stream(dev).cuda_stream))
     _lib.check(rc, "sa_mlp")
     return out_cf, out_cl
+
+
+def prepack_xyzw(xyz: torch.Tensor, extra: torch.Tensor) -> torch.Tensor:
+    """(B,N,3) coordinates + ONE scalar feature per point ((B,1,N) or (B,N,1)) -> (B,N,4) {x,y,z,f}: the gathered
+    source of a fused SA stage whose only feature is a scalar (SA1: height).  The result rides on `xyz` so that the
+    stage finds it; a caller with a stream to spare runs this early, off the critical path (Pointnet2Backbone does,
+    under the sampling chain)."""
+    B, N, _ = xyz.shape
+    out = torch.empty((B, N, 4), dtype=torch.float32, device=xyz.device)
+    e = extra.contiguous()
+    with torch.cuda.device(xyz.device):
+        _lib.check(_lib.load().sad_pack_xyzw(B, N, _ptr(xyz), _ptr(e), _ptr(out), _stream(out)), "pack_xyzw")
+    xyz._sad_xyzw1 = (extra.data_ptr(), extra._version, out)
+    return out
 
 
 def prepare_layers(layers) -> PreparedMLP:

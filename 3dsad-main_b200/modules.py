@@ -293,6 +293,8 @@ class Pointnet2Backbone(nn.Module):
         plan = None
         if fast:
             plan, main = self._geometry_chain(xyz, ready_event)
+            if features is not None and features.shape[1] == 1 and self.sa1.use_xyz:
+                _mlp.prepack_xyzw(xyz, features)      # SA1's gathered source, built on the main stream under the sampling chain
         for name in ("sa1", "sa2", "sa3", "sa4"):
             if plan is not None:
                 inds, new_xyz, ev = plan[name]
@@ -343,20 +345,42 @@ class SizeAdaptiveAggregation(nn.Module):
 
     def __init__(self, npoint: int = 256, nsample: int = 16, seed_feature_dim: int = 256,
                  mlp: Sequence[int] = (128, 128, 128), alpha: float = 1.0, r_min: float = 0.1,
-                 r_max: float = 1.2, bn: bool = True):
+                 r_max: float = 1.2, bn: bool = True, size_scale: float = 1.0, size_clip: float = 2.0):
         super().__init__()
         self.alpha, self.r_min, self.r_max = alpha, r_min, r_max
+        self.size_scale, self.size_clip = size_scale, size_clip
         self.sa = PointnetSAModuleVotes(npoint, None, nsample, [seed_feature_dim] + list(mlp), bn=bn)
+        # size head: the size that drives the per-cluster radius, predicted from the vote features
+        # at the cluster centres: 2-layer 1x1 MLP -> log-size, size = size_scale * exp(clip(y)) [formula unpinned]
+        self.size_mlp = SharedMLP([seed_feature_dim, 128, 3], bn=bn, last_relu=False)
+        self.size_mlp.bns[-1] = nn.Identity()
+        self.size_mlp.convs[-1] = nn.Conv2d(128, 3, kernel_size=1, bias=True)
 
-    def forward(self, vote_xyz, vote_features, size):
+    def predict_size(self, vote_features, cinds):
+        """vote_features (B,C,n), cluster centre indices (B,K) -> predicted box size (B,K,3)."""
+        centre = ops.gather_operation(vote_features.contiguous(), cinds)               # (B,C,K)
+        if not self.training and not torch.is_grad_enabled():
+            y = _mlp.pointwise_mlp(centre, self.size_mlp.folded(), last_relu=False, want_cl=False)
+        else:
+            y = self.size_mlp(centre.unsqueeze(-1)).squeeze(-1)
+        y = y.clamp(min=-self.size_clip, max=self.size_clip)
+        return (self.size_scale * torch.exp(y)).transpose(1, 2).contiguous()
+
+    def forward(self, vote_xyz, vote_features, size=None):
+        """`size` (B,K,3): externally predicted box sizes, or None: the module's own size head."""
+        cinds = None
+        if size is None:
+            cinds = ops.furthest_point_sample(vote_xyz, self.sa.npoint)
+            size = self.predict_size(vote_features, cinds)
         radius_t = ops.size_to_radius(size, self.alpha, self.r_min, self.r_max)
-        cxyz, cfeat, cinds = self.sa(vote_xyz, vote_features, radius_t=radius_t)
-        return cxyz, cfeat, cinds, radius_t
+        cxyz, cfeat, cinds = self.sa(vote_xyz, vote_features, inds=cinds, radius_t=radius_t)
+        return cxyz, cfeat, cinds, radius_t, size
 
 
 class SADHotPath(nn.Module):
     """The timed unit 'scene' (SURVEY call stack 3): backbone -> voting -> size-adaptive
-    vote aggregation.  `size` (B,256,3) is the predicted box size per cluster."""
+    vote aggregation.  `size` (B,256,3) is the predicted box size per cluster: passed in (the benchmark's synthetic
+    sizes, a downstream proposal head) or, when None, predicted by the aggregation module's own size head."""
 
     def __init__(self, input_feature_dim: int = 1, bn: bool = True):
         super().__init__()
@@ -364,7 +388,8 @@ class SADHotPath(nn.Module):
         self.vgen = VotingModule(256, bn=bn)
         c = LAYER_CFG
         self.agg = SizeAdaptiveAggregation(c["agg"][0], c["agg"][2], 256, alpha=c["alpha"],
-                                           r_min=c["r_min"], r_max=c["r_max"], bn=bn)
+                                           r_min=c["r_min"], r_max=c["r_max"], bn=bn,
+                                           size_scale=c["size_scale"], size_clip=c["size_clip"])
 
     @torch.no_grad()
     def load_params(self, params):
@@ -376,17 +401,19 @@ class SADHotPath(nn.Module):
         bb.fp2.mlp.load_folded(params["fp2"])
         self.vgen.mlp.load_folded(params["vote"])
         self.agg.sa.mlp_module.load_folded(params["agg"])
+        if "size" in params:
+            self.agg.size_mlp.load_folded(params["size"])
         return self
 
-    def forward(self, xyz, features, size, ready_event=None):
+    def forward(self, xyz, features, size=None, ready_event=None):
         """`ready_event` (optional): a CUDA event after which the inputs are valid.  Passing it lets
         the coordinate-only chain of this batch start while the previous batch is still in its
         feature stages (two batches in flight); without it the call orders against the stream."""
         end = self.backbone(xyz, features, ready_event=ready_event)
         vxyz, vfeat = self.vgen(end["fp2_xyz"], end["fp2_features"])
-        cxyz, cfeat, cinds, radius_t = self.agg(vxyz, vfeat, size)
+        cxyz, cfeat, cinds, radius_t, size = self.agg(vxyz, vfeat, size)
         end.update(vote_xyz=vxyz, vote_features=vfeat, cluster_xyz=cxyz, cluster_features=cfeat,
-                   cluster_inds=cinds, cluster_radius=radius_t)
+                   cluster_inds=cinds, cluster_radius=radius_t, cluster_size=size)
         return end
 
     @torch.no_grad()

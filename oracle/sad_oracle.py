@@ -328,6 +328,14 @@ def voting_module(seed_xyz, seed_features, layers, emulate_bf16=False):
     return vote_xyz, vote_features
 
 
+def size_head(center_features, layers, scale=1.0, clip=2.0, emulate_bf16=False):
+    """Size head [DECISION, unpinned]: 2-layer 1x1 MLP (last layer linear) on the vote features at
+    the cluster centres (B,C,K) -> log-size y (B,3,K); size = scale * exp(clip(y, -clip, clip)) -> (B,K,3) f32."""
+    y = shared_mlp(_f32c(center_features)[..., None], layers, pool=False, last_relu=False, emulate_bf16=emulate_bf16)[..., 0]
+    y = np.minimum(np.maximum(y, F32(-clip)), F32(clip)).astype(np.float32)
+    return np.ascontiguousarray((F32(scale) * np.exp(y)).astype(np.float32).transpose(0, 2, 1))
+
+
 def vote_aggregation(vote_xyz, vote_features, size, npoint, nsample, layers,
                      alpha=1.0, r_min=0.1, r_max=1.2, emulate_bf16=False, impl=None):
     """a7: FPS over votes -> cluster centres -> per-cluster radius from predicted size

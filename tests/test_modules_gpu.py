@@ -118,3 +118,35 @@ def test_folded_weights_follow_parameter_updates():
         y2 = M.pointwise_mlp(x, sm.folded())
         ref2 = sm(x.unsqueeze(-1)).squeeze(-1)
         assert float((y2 - ref2).abs().max()) <= 2e-2 * max(1e-6, float(ref2.abs().max()))
+
+
+def test_size_head_drives_the_adaptive_radius():
+    """SURVEY 8(f) rank 3 / VERDICT r1 missing item 4: with no sizes passed in, the aggregation module predicts them
+    from the vote features at the cluster centres (size head through the fused kernel) and feeds the radius of the
+    adaptive ball query.  Predicted sizes within the bf16 bar of the oracle's size head; with the GPU's own sizes the
+    oracle's clustering indices match bit for bit."""
+    import sad_b200  # noqa: F401
+    from sad_b200.config import LAYER_CFG, make_params
+    from sad_b200.modules import SADHotPath
+    from sad_b200.scenes import make_scenes
+    params = make_params(0)
+    model = SADHotPath(1).load_params(params).to(DEV).eval()
+    xyz, feat = make_scenes(2, 9000, "surface", first_scene=5)
+    with torch.no_grad():
+        got = model(torch.from_numpy(xyz).to(DEV), torch.from_numpy(feat).to(DEV))          # size=None: the head
+    vfeat = got["vote_features"].cpu().numpy()
+    vxyz = got["vote_xyz"].cpu().numpy()
+    cinds = got["cluster_inds"].cpu().numpy()
+    centre = np.stack([vfeat[b][:, cinds[b]] for b in range(2)])
+    want_size = O.size_head(centre, params["size"], LAYER_CFG["size_scale"], LAYER_CFG["size_clip"])
+    size = got["cluster_size"].cpu().numpy()
+    assert size.shape == (2, LAYER_CFG["agg"][0], 3)
+    assert float(np.abs(size - want_size).max()) <= 3e-2 * float(np.abs(want_size).max())
+    assert float(size.std()) > 1e-3                                   # the head actually differentiates clusters
+    npoint, _, nsample = LAYER_CFG["agg"]
+    cxyz, cfeat, winds, rt = O.vote_aggregation(vxyz, vfeat, size, npoint, nsample, params["agg"], alpha=LAYER_CFG["alpha"],
+                                                r_min=LAYER_CFG["r_min"], r_max=LAYER_CFG["r_max"], impl=C)
+    assert np.array_equal(cinds, winds) and np.array_equal(got["cluster_radius"].cpu().numpy(), rt)
+    assert np.array_equal(got["cluster_xyz"].cpu().numpy(), cxyz)
+    close(got["cluster_features"], cfeat)
+    assert float(rt.min()) < float(rt.max())                          # radii spread inside the clamp range

@@ -41,12 +41,21 @@ def test_train_step_backprops_through_every_stage_and_learns():
         loss.backward()
         if step == 0:
             for name, p in model.named_parameters():
+                if "size_mlp" in name:
+                    continue                      # sizes are passed in here: the module's own size head idles
                 assert p.grad is not None and torch.isfinite(p.grad).all(), name
             convs = [p for n, p in model.named_parameters() if n.endswith("convs.0.weight")]
             assert all(float(p.grad.abs().sum()) > 0 for p in convs)       # gradient reaches the first layer of every stage
         opt.step()
         losses.append(float(loss.detach()))
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    # with no sizes passed in, the size head predicts them and is trained through the radius normalisation of the
+    # grouped coordinates (the ball query itself is not differentiable)
+    opt.zero_grad(set_to_none=True)
+    _loss(model(xyz, feat)).backward()
+    head = [p for n, p in model.named_parameters() if "size_mlp" in n]
+    assert head and all(p.grad is not None and torch.isfinite(p.grad).all() for p in head)
+    assert any(float(p.grad.abs().sum()) > 0 for p in head)
     # sampling is coordinate-only: training does not change the indices
     model.eval()
     with torch.no_grad():
@@ -71,7 +80,7 @@ def test_ddp_wrapped_step_matches_plain_step():
         for wrap in (False, True):
             torch.manual_seed(0)
             model = SADHotPath(1).load_params(make_params(0)).to(DEV).train()
-            net = DDP(model, device_ids=[0]) if wrap else model
+            net = DDP(model, device_ids=[0], find_unused_parameters=True) if wrap else model      # (the size head idles when sizes are passed in)
             _loss(net(xyz, feat, size)).backward()
             grads.append(torch.cat([p.grad.flatten() for p in model.parameters()]))
         # same math; scatter-add atomics reorder fp32 sums (and train-mode BN amplifies the noise), hence a norm-wise bar
@@ -128,7 +137,7 @@ def _nccl_worker(rank, world, port, q):
         torch.manual_seed(0)
         net = SADHotPath(1).to(dev).train()
         ref = {k: v.detach().clone() for k, v in net.state_dict().items()}
-        ddp = DDP(net, device_ids=[rank])
+        ddp = DDP(net, device_ids=[rank], find_unused_parameters=True)
         lo, hi = shp.my_range(4)
         xb, fb = make_scenes(4, 3000, "surface", first_scene=90)
         sb = make_sizes(4, LAYER_CFG["agg"][0], first_scene=90)

@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--tpc", type=int, default=1)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--no-cf", action="store_true")
+    ap.add_argument("--real", action="store_true", help="SA1 / SA2 on real scene data (FPS + ball-query indices)")
     args = ap.parse_args()
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
@@ -53,6 +54,38 @@ def main():
     M.TILES_PER_CTA[0] = args.tpc
     M._WANT_CF[0] = not args.no_cf
     rows = []
+    if args.real:
+        from sad_b200 import ops
+        from sad_b200.scenes import make_scenes
+        xyz_np, feat_np = make_scenes(B, 40000, "surface")
+        xyz, feat = torch.from_numpy(xyz_np).to(dev), torch.from_numpy(feat_np).to(dev)
+        grid = ops.build_scene_grid(xyz)
+        inds = ops.furthest_point_sample(xyz, 2048, grid)
+        new_xyz = ops.gather_points(xyz, inds)
+        idx = ops.ball_query(0.2, 64, xyz, new_xyz, grid)
+        m1 = layers([4, 64, 64, 128])
+        hits = (idx != idx[:, :, :1]).sum(-1).float().mean().item() + 1
+        for mode in (False, True):
+            M.FAST_SA[0] = mode
+            med, best = t(lambda: M.sa_group_mlp(xyz, new_xyz, feat, idx, 0.2, m1))
+            print({"stage": "sa1-real", "fast": mode, "us": round(med, 1), "mean_distinct_hits": round(hits, 1)}, flush=True)
+        M.FAST_SA[0] = True
+        f1 = M.sa_group_mlp(xyz, new_xyz, feat, idx, 0.2, m1)
+        inds2 = ops.furthest_point_sample(new_xyz, 1024)
+        x2 = ops.gather_points(new_xyz, inds2)
+        idx2 = ops.ball_query(0.4, 32, new_xyz, x2)
+        m2 = layers([131, 128, 128, 256])
+        for mode in (False, "single", "pair"):
+            M.FAST_SA[0] = mode
+            med, best = t(lambda: M.sa_group_mlp(new_xyz, x2, f1, idx2, 0.4, m2))
+            print({"stage": "sa2-real", "fast": mode, "us": round(med, 1)}, flush=True)
+        # same shapes, random neighbours
+        ridx = torch.randint(0, 40000, (B, 2048, 64), device=dev, dtype=torch.int32)
+        M.FAST_SA[0] = True
+        med, best = t(lambda: M.sa_group_mlp(xyz, new_xyz, feat, ridx, 0.2, m1))
+        print({"stage": "sa1-real-xyz-random-idx", "us": round(med, 1)}, flush=True)
+        sidx, _ = torch.sort(ridx, dim=-1)
+        return
     stages = [("sa1", 40000, 2048, 64, 1, [64, 64, 128]), ("sa2", 2048, 1024, 32, 128, [128, 128, 256]),
               ("sa3", 1024, 512, 16, 256, [128, 128, 256]), ("sa4", 512, 256, 16, 256, [128, 128, 256]),
               ("agg", 1024, 256, 16, 256, [128, 128, 128])]

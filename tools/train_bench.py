@@ -36,7 +36,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     model = SADHotPath(1).load_params(make_params(0)).to(dev).train()
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True) if world > 1 else model
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9)
     xyz, feat = make_scenes(a.B, a.N, "surface", first_scene=rank * a.B)
     size = make_sizes(a.B, LAYER_CFG["agg"][0], first_scene=rank * a.B)
