@@ -44,7 +44,7 @@ def test_train_step_backprops_through_every_stage_and_learns():
                 if "size_mlp" in name:
                     continue                      # sizes are passed in here: the module's own size head idles
                 assert p.grad is not None and torch.isfinite(p.grad).all(), name
-            convs = [p for n, p in model.named_parameters() if n.endswith("convs.0.weight")]
+            convs = [p for n, p in model.named_parameters() if n.endswith("convs.0.weight") and "size_mlp" not in n]
             assert all(float(p.grad.abs().sum()) > 0 for p in convs)       # gradient reaches the first layer of every stage
         opt.step()
         losses.append(float(loss.detach()))
