@@ -51,6 +51,10 @@ SIGNATURES = {
     "sad_pack_xyzw": [_c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_sa_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_float, _vp, _c_int, _vp, _c_int, _vp, _vp,
                        _c_int, _vp, _vp, _vp, _c_int, _vp],
+    "sad_mlp_tf32_image_bytes": [_c_int, _c_int, _c_int],
+    "sad_mlp_tf32_pack": [_vp, _c_int, _c_int, _c_int, _vp],
+    "sad_mlp_tf32_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _c_float, _vp,
+                         _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _vp],
     "sad_pw_mlp_image_bytes": [_c_int],
     "sad_pw_mlp_pack": [_c_int, _vp, _vp, _vp, _c_int, _vp],
     "sad_pw_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp,
@@ -60,7 +64,8 @@ SIGNATURES = {
 }
 _RESTYPES = {"sad_last_error_string": ctypes.c_char_p,
              "sad_launch_count": ctypes.c_ulonglong, "sad_scene_grid_workspace_bytes": ctypes.c_longlong, "sad_mlp_weight_image_bytes": ctypes.c_longlong,
-             "sad_sa_mlp_image_bytes": ctypes.c_longlong, "sad_pw_mlp_image_bytes": ctypes.c_longlong}
+             "sad_sa_mlp_image_bytes": ctypes.c_longlong, "sad_pw_mlp_image_bytes": ctypes.c_longlong,
+             "sad_mlp_tf32_image_bytes": ctypes.c_longlong}
 
 class MlpOpts(ctypes.Structure):
     """include/sad_ops.h sad_mlp_opts"""
@@ -112,9 +117,13 @@ class CallProfiler:
         prof.summary() -> {entry_point: {"calls": n, "ms": total_device_ms}}
     """
 
-    def __init__(self):
+    def __init__(self, repeat=None):
+        """repeat: {entry_point: R} -- issue that (idempotent) call R times back to back inside ONE event pair and
+        record elapsed / R: the event pair's own cost (several microseconds around a 148-CTA launch) then does not
+        count as kernel time."""
         self.records = []
         self._saved = {}
+        self._repeat = dict(repeat or {})
 
     def __enter__(self):
         import torch
@@ -125,13 +134,16 @@ class CallProfiler:
             fn = getattr(lib, name)
             self._saved[name] = fn
 
-            def wrapped(*args, _fn=fn, _name=name):
+            def wrapped(*args, _fn=fn, _name=name, _reps=int(self._repeat.get(name, 1))):
                 a = torch.cuda.Event(enable_timing=True)
                 b = torch.cuda.Event(enable_timing=True)
                 a.record()
                 rc = _fn(*args)
+                for _ in range(_reps - 1):
+                    if rc == 0:
+                        rc = _fn(*args)
                 b.record()
-                self.records.append((_name, args, a, b))
+                self.records.append((_name, args, a, b, _reps))
                 return rc
 
             setattr(lib, name, wrapped)
@@ -146,7 +158,7 @@ class CallProfiler:
         return False
 
     def rows(self):
-        return [(name, args, a.elapsed_time(b)) for (name, args, a, b) in self.records]
+        return [(name, args, a.elapsed_time(b) / reps) for (name, args, a, b, reps) in self.records]
 
     def summary(self):
         out = {}

@@ -1,0 +1,468 @@
+// a6 (tf32 mode)  fused gather / interpolation -> shared MLP -> max-pool with fp32 activations and kind::tf32 MMAs
+// -- SURVEY.md section 8(a) row a6, BASELINE.json north_star ("tcgen05 bf16/tf32 GEMM with fused max-pool epilogue"),
+// VERDICT r1 item 6.  (No reference file exists to cite: /root/reference is README.md:1-2 only.)
+//
+// Same fusion as the bf16 kernels (mlp_sa.cu / mlp_pw.cu), one general kernel instead of shape-specialised ones:
+// features travel between stages as fp32 channel-last rows, the layer-1 operand is built in shared memory straight
+// from HBM (neighbour gather through idx, identity rows, or the three-nearest-neighbour interpolation itself, plus the
+// relative-xyz / scalar-feature K step), every layer's activations stay on chip in fp32 and the last layer is evaluated
+// transposed (lane = output channel) so the max over nsample is an in-register reduction.  Operands are rounded to
+// tf32 (cvt.rna, 10-bit mantissa) when they are written; accumulation, bias, ReLU and max are fp32.
+//
+//   shared memory   activations 128 rows x 256 ch x 4 B = 128 KB (K-major SWIZZLE_128B, 32-channel chunks of 16 KB)
+//                   A ring  2 x 16 KB   layer-1 operand chunks (128 rows x 32 channels)
+//                   W ring  2 x 32 KB   weight pieces, one TMA bulk copy each (<= 256 rows x 32 K values)
+//   TMEM            hidden accumulators in columns [0,256); last-layer blocks (128 channels x 128 rows) in 128-column
+//                   regions (columns 256.. when there are at most two blocks, so the next tile's first layers run under
+//                   the drain of this tile's last layer)
+//   warps           0-3 epilogue (thread = TMEM lane), 4-7 operand producers (thread = row), 8 MMA issue, 9 weight TMA
+//
+// One 128-row tile (row = (query point, sample)) is in flight per CTA; persistent CTAs take tiles round-robin.
+// Roofline: tensor (kind::tf32 peak = half the bf16 peak); algorithmic flops = 2 * rows * sum(Cin*Cout).
+#include <string.h>
+
+#include "sad_tc.cuh"
+
+namespace {
+
+using namespace sad;
+
+constexpr int kChunk = 16384;                 // 128 rows x 128 B = 32 fp32 channels per row
+constexpr int kActBytes = 8 * kChunk;         // 256 channels
+constexpr int kNSA = 2, kNSW = 2;
+constexpr int kWStage = 2 * kChunk;
+constexpr int kMisc = 1024;
+constexpr int kSmem = 1024 + kActBytes + kNSA * kChunk + kNSW * kWStage + kMisc;
+static_assert(kSmem <= 227 * 1024, "shared-memory budget");
+constexpr int kWarpProd = 4, kWarpMma = 8, kWarpTma = 9, kThreads = 10 * 32;
+constexpr int kMaxLayers = 3;
+
+struct TfParams {
+  int B, N, P, S, log2S;             // rows = B * P * S; source points per scene N (gather) / P (identity rows)
+  long long total_rows, total_points;
+  int num_tiles;
+  // layer-1 operand, K order [interp | feat | special]
+  const float* known_cl;             // (B, m, CI) fp32 channel-last, interpolation source, or null
+  const int32_t* nn_idx;             // (B*P, 3)
+  const float* nn_w;                 // (B*P, 3)
+  int m, CI;
+  const float* feat_cl;              // (B, N, CF) fp32 channel-last gathered through idx, or identity rows when idx == null
+  int CF;
+  const int32_t* idx;                // (B, P, S) or null
+  const float* xyz;                  // (B, N, 3): the special K step [dx,dy,dz,e0..e(E-1),0..] exists when non-null
+  const float* new_xyz;              // (B, P, 3)
+  const float* radius_t;             // (B, P) per-cluster radius or null
+  float radius;
+  int normalize;
+  const float* extra;                // (B, N, E) fp32 scalar features, E <= 4
+  int E;
+  // layers
+  int n_layers;
+  int c_out[kMaxLayers];             // real widths; hidden widths are multiples of 32 and <= 256
+  int kc[kMaxLayers];                // K chunks per layer (layer 1: interp + feat + special chunks)
+  const uint8_t* w_img[kMaxLayers];  // pieces in consumption order (see sad_mlp_tf32_pack)
+  const float* bias[kMaxLayers];     // last layer: padded to 128 * nblk
+  int nblk;                          // 128-channel blocks of the last layer (<= 4)
+  int last_relu;
+  float* out_cf;                     // (B, c_last, P) f32 or null
+  float* out_cl;                     // (B, P, c_last) f32 or null
+};
+
+struct Misc {
+  uint64_t wfull[kNSW], wfree[kNSW], afull[kNSA], afree[kNSA];
+  uint64_t dfull[1 + 4];             // [0] hidden layers, [1 + blk] last-layer blocks
+  uint64_t actfull, tfree;
+  uint32_t tmem_base;
+};
+
+__device__ __noinline__ void bar_timeout(uint32_t bar, uint32_t parity) {
+  printf("mlp_tf32: barrier %u parity %u timed out (block %d warp %d)\n", bar, parity, blockIdx.x, threadIdx.x >> 5);
+  __trap();
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  long long t0 = 0;
+  for (;;) {
+    if (mbar_try_wait_sleep(bar, parity)) return;
+    if ((++spins & 0xFFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) bar_timeout(smem_u32(bar), parity);
+    }
+  }
+}
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// instruction descriptor kind::tf32: D f32 (bit 4), A = B = tf32 (format 2 at bits 7 and 10), both K-major
+__device__ __forceinline__ uint32_t uidesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* act = base;
+  uint8_t* aring = act + kActBytes;
+  uint8_t* wring = aring + kNSA * kChunk;
+  Misc* ms = reinterpret_cast<Misc*>(wring + kNSW * kWStage);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NL = p.n_layers;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kNSW; ++i) { mbar_init(&ms->wfull[i], 1); mbar_init(&ms->wfree[i], 1); }
+    for (int i = 0; i < kNSA; ++i) { mbar_init(&ms->afull[i], 4); mbar_init(&ms->afree[i], 1); }
+    for (int i = 0; i < 5; ++i) mbar_init(&ms->dfull[i], 1);
+    mbar_init(&ms->actfull, 4);
+    mbar_init(&ms->tfree, 4);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<1>(&ms->tmem_base, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = ms->tmem_base;
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int kcI = (p.CI + 31) >> 5, kcF = (p.CF + 31) >> 5;
+  const bool special = p.xyz != nullptr;
+  const uint32_t last_col0 = p.nblk <= 2 ? 256u : 0u;
+
+  if (warp == kWarpTma) {
+    // ============================================================ weight pieces through the W ring
+    if (lane == 0) {
+      uint32_t w = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int l = 0; l < NL; ++l) {
+          const bool last = l == NL - 1;
+          const int pieces = last ? p.nblk * p.kc[l] : p.kc[l];
+          const uint32_t bytes = last ? 128u * 128u : (uint32_t)((p.c_out[l] + 15) & ~15) * 128u;
+          const uint8_t* src = p.w_img[l];
+          for (int i = 0; i < pieces; ++i, ++w) {
+            const int st = w % kNSW;
+            bar_wait(&ms->wfree[st], ((w / kNSW) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&ms->wfull[st], bytes);
+            tma_bulk_g2s(wring + st * kWStage, src + (size_t)i * bytes, bytes, &ms->wfull[st]);
+          }
+        }
+      }
+    }
+  } else if (warp == kWarpMma) {
+    // ============================================================ MMA issue
+    uint32_t w = 0, a = 0, n_act = 0;
+    const uint32_t act_addr = smem_u32(act);
+    for (int t = 0; t < my_tiles; ++t) {
+      if (t > 0 && p.nblk > 2) bar_wait(&ms->tfree, (uint32_t)(t - 1) & 1u);      // last-layer blocks overlap the hidden columns
+      for (int l = 0; l < NL; ++l) {
+        const bool last = l == NL - 1;
+        if (l > 0) {
+          bar_wait(&ms->actfull, (n_act++) & 1u);
+          if (last && t > 0 && p.nblk <= 2) bar_wait(&ms->tfree, (uint32_t)(t - 1) & 1u);
+        }
+        const int KC = p.kc[l];
+        const int nb = last ? p.nblk : 1;
+        const uint32_t idesc = last ? uidesc_tf32(128, 128) : uidesc_tf32(128, (p.c_out[l] + 15) & ~15);
+        for (int blk = 0; blk < nb; ++blk) {
+          const uint32_t d = tmem + (last ? last_col0 + 128u * blk : 0u);
+          for (int c = 0; c < KC; ++c, ++w) {
+            const int ws = w % kNSW;
+            bar_wait(&ms->wfull[ws], (w / kNSW) & 1u);
+            int as = 0;
+            int ksteps = 4;
+            if (l == 0) {
+              as = a % kNSA;
+              bar_wait(&ms->afull[as], (a / kNSA) & 1u);
+              if (special && c == KC - 1) ksteps = 1;
+            }
+            tc_fence_after_sync();
+            if (elect_one()) {
+              const uint32_t wa = smem_u32(wring + ws * kWStage);
+              const uint32_t xa = l == 0 ? smem_u32(aring + as * kChunk) : act_addr + (uint32_t)c * kChunk;
+              const uint64_t dw = udesc_sw128(wa), dx = udesc_sw128(xa);
+              for (int k = 0; k < ksteps; ++k) {
+                // hidden: D[rows, cout] = X . W^T; last: D[cout, rows] = W . X^T
+                if (last) umma_tf32(d, dw + 2 * k, dx + 2 * k, idesc, (c | k) != 0);
+                else umma_tf32(d, dx + 2 * k, dw + 2 * k, idesc, (c | k) != 0);
+              }
+              umma_commit_to<1>(&ms->wfree[ws]);
+              if (l == 0) umma_commit_to<1>(&ms->afree[as]);
+              if (c == KC - 1) umma_commit_to<1>(&ms->dfull[last ? 1 + blk : 0]);
+            }
+            __syncwarp();
+            if (l == 0) ++a;
+          }
+        }
+      }
+    }
+  } else if (warp >= kWarpProd && warp < kWarpProd + 4) {
+    // ============================================================ layer-1 operand producers: thread = row of the tile
+    const int r = (warp - kWarpProd) * 32 + lane;
+    uint32_t a = 0;
+    const long long PS = (long long)p.P * p.S;
+    for (int t = 0; t < my_tiles; ++t) {
+      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      const long long row = tile * 128 + r;
+      const bool live = row < p.total_rows;
+      int b = 0, j = 0;
+      long long pt = 0;
+      if (live) {
+        b = (int)(row / PS);
+        pt = row >> p.log2S;
+        j = p.idx ? __ldg(p.idx + row) : (int)(row - (long long)b * PS);
+      }
+      const int KC = p.kc[0];
+      for (int c = 0; c < KC; ++c, ++a) {
+        const int st = a % kNSA;
+        bar_wait(&ms->afree[st], ((a / kNSA) & 1u) ^ 1u);
+        const uint32_t dst = smem_u32(aring + st * kChunk);
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+        if (live) {
+          if (c < kcI) {
+            const int c0 = c * 32;
+            const int i0 = __ldg(p.nn_idx + pt * 3), i1 = __ldg(p.nn_idx + pt * 3 + 1), i2 = __ldg(p.nn_idx + pt * 3 + 2);
+            const float w0 = __ldg(p.nn_w + pt * 3), w1 = __ldg(p.nn_w + pt * 3 + 1), w2 = __ldg(p.nn_w + pt * 3 + 2);
+            const float* k0 = p.known_cl + ((size_t)b * p.m + i0) * p.CI + c0;
+            const float* k1 = p.known_cl + ((size_t)b * p.m + i1) * p.CI + c0;
+            const float* k2 = p.known_cl + ((size_t)b * p.m + i2) * p.CI + c0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (c0 + u * 4 < p.CI) {
+                const float4 f0 = __ldg(reinterpret_cast<const float4*>(k0) + u);
+                const float4 f1 = __ldg(reinterpret_cast<const float4*>(k1) + u);
+                const float4 f2 = __ldg(reinterpret_cast<const float4*>(k2) + u);
+                // ((w0*f0)+(w1*f1))+(w2*f2), one rounding per operation: the oracle's three_interpolate
+                v[u * 4 + 0] = tf32_rna(__fadd_rn(__fadd_rn(__fmul_rn(w0, f0.x), __fmul_rn(w1, f1.x)), __fmul_rn(w2, f2.x)));
+                v[u * 4 + 1] = tf32_rna(__fadd_rn(__fadd_rn(__fmul_rn(w0, f0.y), __fmul_rn(w1, f1.y)), __fmul_rn(w2, f2.y)));
+                v[u * 4 + 2] = tf32_rna(__fadd_rn(__fadd_rn(__fmul_rn(w0, f0.z), __fmul_rn(w1, f1.z)), __fmul_rn(w2, f2.z)));
+                v[u * 4 + 3] = tf32_rna(__fadd_rn(__fadd_rn(__fmul_rn(w0, f0.w), __fmul_rn(w1, f1.w)), __fmul_rn(w2, f2.w)));
+              }
+            }
+          } else if (c < kcI + kcF) {
+            const int c0 = (c - kcI) * 32;
+            const float* src = p.feat_cl + ((size_t)b * p.N + j) * p.CF + c0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (c0 + u * 4 < p.CF) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(src) + u);
+                v[u * 4 + 0] = tf32_rna(f.x);
+                v[u * 4 + 1] = tf32_rna(f.y);
+                v[u * 4 + 2] = tf32_rna(f.z);
+                v[u * 4 + 3] = tf32_rna(f.w);
+              }
+            }
+          } else {      // special K step: relative (optionally radius-normalised) xyz, then the scalar features
+            const float* q = p.xyz + ((size_t)b * p.N + j) * 3;
+            const float* o = p.new_xyz + (size_t)pt * 3;
+            float dx = __fsub_rn(__ldg(q), __ldg(o)), dy = __fsub_rn(__ldg(q + 1), __ldg(o + 1)), dz = __fsub_rn(__ldg(q + 2), __ldg(o + 2));
+            if (p.normalize) {
+              const float rad = p.radius_t ? __ldg(p.radius_t + pt) : p.radius;
+              dx = __fdiv_rn(dx, rad);
+              dy = __fdiv_rn(dy, rad);
+              dz = __fdiv_rn(dz, rad);
+            }
+            v[0] = tf32_rna(dx);
+            v[1] = tf32_rna(dy);
+            v[2] = tf32_rna(dz);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < p.E) v[3 + e] = tf32_rna(__ldg(p.extra + ((size_t)b * p.N + j) * p.E + e));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sts_v4(dst + swz128(r, u), v[u * 4], v[u * 4 + 1], v[u * 4 + 2], v[u * 4 + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ms->afull[st]);
+      }
+    }
+  } else if (warp < 4) {
+    // ============================================================ epilogue: thread = TMEM lane
+    const int q = warp;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    const int row = q * 32 + lane;
+    uint32_t n_d0 = 0;
+    const int c_last = p.c_out[NL - 1];
+    for (int t = 0; t < my_tiles; ++t) {
+      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      for (int l = 0; l < NL - 1; ++l) {
+        bar_wait(&ms->dfull[0], (n_d0++) & 1u);
+        tc_fence_after_sync();
+        const int groups = p.c_out[l] >> 5;
+        const float* bias = p.bias[l];
+        for (int g = 0; g < groups; ++g) {
+          uint32_t v[32];
+          tmem_ld_x32(lane_addr + (uint32_t)(g * 32), v);
+          tmem_ld_fence();
+          const uint32_t dst = smem_u32(act) + (uint32_t)g * kChunk;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              o[k] = tf32_rna(fmaxf(__fadd_rn(__uint_as_float(v[u * 4 + k]), __ldg(bias + g * 32 + u * 4 + k)), 0.f));
+            sts_v4(dst + swz128(row, u), o[0], o[1], o[2], o[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ms->actfull);
+      }
+      // last layer, transposed: lane = output channel, TMEM column = row of the tile
+      const long long pt0 = (tile * 128) >> p.log2S;       // first point of the tile (128 % S == 0)
+      for (int blk = 0; blk < p.nblk; ++blk) {
+        bar_wait(&ms->dfull[1 + blk], (uint32_t)t & 1u);
+        tc_fence_after_sync();
+        const int ch = blk * 128 + row;
+        const float bias = __ldg(p.bias[NL - 1] + ch);
+        const bool ch_ok = ch < c_last;
+        float mx = -INFINITY;
+        for (int g = 0; g < 4; ++g) {
+          uint32_t v[32];
+          tmem_ld_x32(lane_addr + last_col0 + (uint32_t)(blk * 128 + g * 32), v);
+          tmem_ld_fence();
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            mx = fmaxf(mx, __uint_as_float(v[jj]));
+            if (((g * 32 + jj + 1) & (p.S - 1)) == 0) {
+              const long long pt = pt0 + ((g * 32 + jj) >> p.log2S);
+              float y = __fadd_rn(mx, bias);
+              if (p.last_relu) y = fmaxf(y, 0.f);
+              mx = -INFINITY;
+              if (ch_ok && pt < p.total_points) {
+                if (p.out_cl) p.out_cl[(size_t)pt * c_last + ch] = y;
+                if (p.out_cf) {
+                  const long long b = pt / p.P;
+                  p.out_cf[((size_t)b * c_last + ch) * p.P + (pt - b * p.P)] = y;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms->tfree);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<1>(tmem, 512);
+}
+
+int fail(int code, const char* msg) {
+  sad_set_error("%s", msg);
+  return code;
+}
+
+int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ C ABI
+// Weight image of ONE layer in the order the kernel consumes it.  W is (c_out, c_in) row-major fp32 with the input
+// channels already in operand order and zero-padded by the caller to kc * 32 columns (c_in == kc * 32).
+//   hidden layer  kc pieces, piece = pad16(c_out) rows x 32 K values, K-major SWIZZLE_128B
+//   last layer    nblk * kc pieces (block-major), piece = 128 rows (output channels, zero padded) x 32 K values
+// Values are rounded to tf32 (round to nearest, ties away -- the cvt.rna the kernel applies to activations).
+extern "C" long long sad_mlp_tf32_image_bytes(int c_out, int kc, int last) {
+  if (c_out <= 0 || kc <= 0) return SAD_EINVAL;
+  if (last) return (long long)((c_out + 127) / 128) * kc * 128 * 128;
+  return (long long)kc * ((c_out + 15) & ~15) * 128;
+}
+
+extern "C" int sad_mlp_tf32_pack(const float* W, int c_out, int kc, int last, void* out) {
+  if (!W || !out || c_out <= 0 || kc <= 0) return fail(SAD_EINVAL, "mlp_tf32_pack: bad arguments");
+  const int c_in = kc * 32;
+  const long long bytes = sad_mlp_tf32_image_bytes(c_out, kc, last);
+  memset(out, 0, (size_t)bytes);
+  uint8_t* o = static_cast<uint8_t*>(out);
+  const int rows_piece = last ? 128 : ((c_out + 15) & ~15);
+  const int nblk = last ? (c_out + 127) / 128 : 1;
+  for (int blk = 0; blk < nblk; ++blk)
+    for (int c = 0; c < kc; ++c) {
+      uint8_t* piece = o + (size_t)(blk * kc + c) * rows_piece * 128;
+      for (int r = 0; r < rows_piece; ++r) {
+        const int n = blk * 128 + r;
+        if (n >= c_out) continue;
+        for (int k = 0; k < 32; ++k) {
+          float w = W[(size_t)n * c_in + c * 32 + k];
+          uint32_t u;
+          memcpy(&u, &w, 4);
+          if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x1000u) & ~0x1FFFu;      // rna to 10 mantissa bits
+          const size_t off = (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)(((k >> 2) ^ (r & 7)) << 4) + (k & 3) * 4;
+          memcpy(piece + off, &u, 4);
+        }
+      }
+    }
+  return SAD_OK;
+}
+
+extern "C" int sad_mlp_tf32_fwd(int B, int N, int P, int S, const float* known_cl, int m, int CI, const int32_t* nn_idx,
+                                const float* nn_w, const float* feat_cl, int CF, const int32_t* idx, const float* xyz,
+                                const float* new_xyz, float radius, const float* radius_t, int normalize_xyz,
+                                const float* extra, int E, int n_layers, const void* const* w_img, const float* const* bias,
+                                const int* c_out, int last_relu, float* out_cf, float* out_cl, sad_stream_t stream) {
+  if (B <= 0 || P <= 0 || S <= 0 || N <= 0) return fail(SAD_EINVAL, "mlp_tf32: bad shape");
+  if (n_layers < 2 || n_layers > kMaxLayers) return fail(SAD_EUNSUPPORTED, "mlp_tf32: 2-3 layers");
+  if ((S & (S - 1)) != 0 || S > 128) return fail(SAD_EUNSUPPORTED, "mlp_tf32: nsample must be a power of two <= 128");
+  if (!w_img || !bias || !c_out || (!out_cf && !out_cl)) return fail(SAD_EINVAL, "mlp_tf32: null pointer");
+  if ((CI & 3) || (CF & 3) || CI < 0 || CF < 0) return fail(SAD_EINVAL, "mlp_tf32: channel counts must be multiples of 4");
+  if (CI && (!known_cl || !nn_idx || !nn_w || m < 3 || S != 1)) return fail(SAD_EINVAL, "mlp_tf32: interpolation source");
+  if (CF && !feat_cl) return fail(SAD_EINVAL, "mlp_tf32: feat_cl is null");
+  if (!idx && (S != 1 || N != P)) return fail(SAD_EINVAL, "mlp_tf32: identity rows need nsample == 1 and N == P");
+  if (xyz && (!new_xyz || !idx || E < 0 || E > 4 || (E && !extra))) return fail(SAD_EINVAL, "mlp_tf32: special K step");
+  if (xyz && normalize_xyz && !radius_t && !(radius > 0.f)) return fail(SAD_EINVAL, "mlp_tf32: radius");
+  for (int l = 0; l < n_layers - 1; ++l)
+    if (c_out[l] <= 0 || c_out[l] > 256 || (c_out[l] & 31)) return fail(SAD_EUNSUPPORTED, "mlp_tf32: hidden widths % 32 == 0, <= 256");
+  if (c_out[n_layers - 1] <= 0 || c_out[n_layers - 1] > 512) return fail(SAD_EUNSUPPORTED, "mlp_tf32: last width <= 512");
+  TfParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.N = N; p.P = P; p.S = S; p.log2S = ilog2(S);
+  p.total_points = (long long)B * P;
+  p.total_rows = p.total_points * S;
+  p.num_tiles = (int)((p.total_rows + 127) / 128);
+  p.known_cl = CI ? known_cl : nullptr; p.nn_idx = nn_idx; p.nn_w = nn_w; p.m = m; p.CI = CI;
+  p.feat_cl = feat_cl; p.CF = CF; p.idx = idx;
+  p.xyz = xyz; p.new_xyz = new_xyz; p.radius_t = radius_t; p.radius = radius; p.normalize = normalize_xyz;
+  p.extra = extra; p.E = xyz ? E : 0;
+  p.n_layers = n_layers;
+  const int k1 = (CI + 31) / 32 + (CF + 31) / 32 + (xyz ? 1 : 0);
+  if (k1 == 0) return fail(SAD_EINVAL, "mlp_tf32: empty layer-1 operand");
+  for (int l = 0; l < n_layers; ++l) {
+    p.c_out[l] = c_out[l];
+    p.kc[l] = l == 0 ? k1 : c_out[l - 1] / 32;
+    p.w_img[l] = static_cast<const uint8_t*>(w_img[l]);
+    p.bias[l] = bias[l];
+    if (!w_img[l] || !bias[l]) return fail(SAD_EINVAL, "mlp_tf32: null layer");
+  }
+  p.nblk = (c_out[n_layers - 1] + 127) / 128;
+  p.last_relu = last_relu;
+  p.out_cf = out_cf; p.out_cl = out_cl;
+  static bool configured = false;
+  if (!configured) {
+    SAD_CUDA_OK(cudaFuncSetAttribute(mlp_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    configured = true;
+  }
+  int sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  mlp_tf32_kernel<<<grid, kThreads, kSmem, (cudaStream_t)stream>>>(p);
+  SAD_LAUNCH_CHECK("mlp_tf32_kernel");
+  return SAD_OK;
+}

@@ -8,10 +8,10 @@ the caller, and carry their cl twin in the `_sad_cl` attribute so the next stage
 the layout bridge.  Storage precision: bf16 operands, fp32 accumulate / bias / ReLU / max
 (2e-2 vs the fp32 oracle, BASELINE north_star).
 
-Shapes the kernel does not cover (hidden widths not a multiple of 64 or > 256, more than 3
-layers, nsample not a power of two) take `composed_*`: the same math composed from this
-repo's grouping kernels and torch matmuls -- still GPU-only, used by odd-shaped user
-modules and by the training path, never by the benchmarked detector configuration.
+Shapes the kernels do not cover (hidden widths not a multiple of 64 or > 256, more than 3
+layers, nsample not a power of two) are rejected with SAD_EUNSUPPORTED (`UnsupportedShape`):
+there is no library-matmul fallback in this package.  Training composes the same stage from
+the autograd operators of `ops.py` and `torch.nn` layers (modules.SharedMLP).
 """
 from __future__ import annotations
 
@@ -24,6 +24,17 @@ import torch
 from . import _lib, ops
 
 _VP = ctypes.c_void_p
+
+
+class UnsupportedShape(_lib.SadLibraryError):
+    """SAD_EUNSUPPORTED (-3) raised on the host side: the fused kernels are not built for this MLP shape."""
+    code = -3
+
+
+def _reject(what: str, mlp: "PreparedMLP", S: int):
+    raise UnsupportedShape(
+        f"{what}: SAD_EUNSUPPORTED -- fused MLP kernels take 2-3 layers, hidden widths % 64 (tf32: 32) == 0 and <= 256, last width "
+        f"<= 512, nsample a power of two <= 128; got widths {list(mlp.c_out)}, nsample {S}")
 
 # Hand 128-row tiles to the persistent CTAs through an atomic counter (robust when other streams hold SMs).
 DYNAMIC_TILES = True
@@ -133,7 +144,10 @@ class PreparedMLP:
     """BN-folded layers [(W (Cout,Cin) f32, b (Cout,) f32), ...] plus, lazily per layout, the
     packed bf16 weight images the tcgen05 kernel streams."""
 
-    def __init__(self, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]]):
+    def __init__(self, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], dtype: str = "bf16"):
+        if dtype not in ("bf16", "tf32"):
+            raise ValueError(f"PreparedMLP dtype must be 'bf16' or 'tf32', got {dtype!r}")
+        self.dtype = dtype            # operand precision of the fused kernels: bf16 (2e-2 bar) or tf32 (fp32 activations)
         self.layers = [(W.contiguous(), b.contiguous()) for (W, b) in layers]
         self.c_out = [int(W.shape[0]) for (W, _) in self.layers]
         self.c_in = int(self.layers[0][0].shape[1])
@@ -148,7 +162,8 @@ class PreparedMLP:
 
     def fusable(self, S: int) -> bool:
         n = len(self.layers)
-        hidden_ok = all(c % 64 == 0 and c <= 256 for c in self.c_out[:-1])
+        step = 32 if self.dtype == "tf32" else 64
+        hidden_ok = all(c % step == 0 and c <= 256 for c in self.c_out[:-1])
         return 2 <= n <= 3 and hidden_ok and self.c_out[-1] <= 512 and S in (1, 2, 4, 8, 16, 32, 64, 128)
 
     def packed(self, layout: Layout, S: int = 1):
@@ -264,8 +279,133 @@ def prepack_xyzw(xyz: torch.Tensor, extra: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def prepare_layers(layers) -> PreparedMLP:
-    return PreparedMLP(layers)
+def prepare_layers(layers, dtype: str = "bf16") -> PreparedMLP:
+    return PreparedMLP(layers, dtype)
+
+
+# ----------------------------------------------------------------------------- tf32 mode (csrc/mlp_tf32.cu)
+def to_cl_f32(features_cf: torch.Tensor) -> torch.Tensor:
+    """(B,C,N) f32 -> (B,N,C4) f32 channel-last, C padded to a multiple of 4; the twin a tf32 stage left on its
+    output is used when present."""
+    twin = getattr(features_cf, "_sad_cl32", None)
+    if twin is not None:
+        return twin
+    B, C, N = features_cf.shape
+    c4 = (C + 3) // 4 * 4
+    if c4 == C:
+        return features_cf.transpose(1, 2).contiguous()
+    out = torch.zeros((B, N, c4), dtype=torch.float32, device=features_cf.device)
+    out[:, :, :C] = features_cf.transpose(1, 2)
+    return out
+
+
+def _packed_tf32(mlp: PreparedMLP, ci: int, ci_real: int, cf: int, cf_real: int, special: bool, E: int, order: str):
+    """Per-layer weight images + biases for sad_mlp_tf32_fwd.  Layer-1 operand order is [interp | feat | special];
+    `order` says where those parts sit in the lineage weight matrix: "sa" = [xyz(3) | features] (features = the extras
+    when E > 0), "fp" = [interp | skip], "pw" = [features]."""
+    key = ("tf32", ci, ci_real, cf, cf_real, special, E, order)
+    if key not in mlp._packed:
+        lib = _lib.load()
+        dev = mlp.layers[0][0].device
+        n = len(mlp.layers)
+        kc_i, kc_f = (ci + 31) // 32, (cf + 31) // 32
+        kc1 = kc_i + kc_f + (1 if special else 0)
+        imgs, biases = [], []
+        for li, (W, b) in enumerate(mlp.layers):
+            Wn = np.ascontiguousarray(W.detach().cpu().numpy(), dtype=np.float32)
+            cout, cin = Wn.shape
+            last = int(li == n - 1)
+            if li == 0:
+                kc = kc1
+                Wp = np.zeros((cout, kc * 32), dtype=np.float32)
+                if order == "sa":
+                    x0 = 3 if special else 0
+                    if E:
+                        Wp[:, (kc_i + kc_f) * 32 + 3:(kc_i + kc_f) * 32 + 3 + E] = Wn[:, x0:x0 + E]
+                    else:
+                        Wp[:, kc_i * 32:kc_i * 32 + cf_real] = Wn[:, x0:x0 + cf_real]
+                    if special:
+                        Wp[:, (kc_i + kc_f) * 32:(kc_i + kc_f) * 32 + 3] = Wn[:, :3]
+                else:
+                    Wp[:, :ci_real] = Wn[:, :ci_real]
+                    Wp[:, kc_i * 32:kc_i * 32 + cf_real] = Wn[:, ci_real:ci_real + cf_real]
+            else:
+                kc = cin // 32
+                Wp = Wn
+            nbytes = lib.sad_mlp_tf32_image_bytes(cout, kc, last)
+            img = np.zeros(nbytes, dtype=np.uint8)
+            _lib.check(lib.sad_mlp_tf32_pack(_VP(np.ascontiguousarray(Wp).ctypes.data), cout, kc, last, _VP(img.ctypes.data)),
+                       "mlp_tf32_pack")
+            imgs.append(torch.from_numpy(img).to(dev))
+            bb = b.detach().float().cpu().numpy()
+            if last:
+                pad = np.zeros((cout + 127) // 128 * 128, dtype=np.float32)
+                pad[:cout] = bb
+                bb = pad
+            biases.append(torch.from_numpy(np.ascontiguousarray(bb)).to(dev))
+        mlp._packed[key] = (imgs, biases, (_VP * n)(*[t.data_ptr() for t in imgs]),
+                            (_VP * n)(*[t.data_ptr() for t in biases]), (ctypes.c_int * n)(*mlp.c_out))
+    return mlp._packed[key]
+
+
+def _attach32(cf: torch.Tensor, cl: torch.Tensor):
+    cf._sad_cl32 = cl
+    return cf
+
+
+def _tf32_launch(mlp, pk, B, N, P, S, known_cl, m, CI, nn_idx, nn_w, feat_cl, CF, idx, xyz, new_xyz, radius, radius_t,
+                 normalize, extra, E, last_relu):
+    _, _, wp, bp, cp = pk
+    dev = (feat_cl if feat_cl is not None else known_cl if known_cl is not None else xyz).device
+    c_last = mlp.c_out[-1]
+    out_cf = torch.empty((B, c_last, P), dtype=torch.float32, device=dev)
+    out_cl = torch.empty((B, P, c_last), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().sad_mlp_tf32_fwd(B, N, P, S, _ptr(known_cl), int(m), int(CI), _ptr(nn_idx), _ptr(nn_w), _ptr(feat_cl),
+                                          int(CF), _ptr(idx), _ptr(xyz), _ptr(new_xyz), float(radius), _ptr(radius_t),
+                                          int(bool(normalize)), _ptr(extra), int(E), len(mlp), wp, bp, cp, int(bool(last_relu)),
+                                          _ptr(out_cf), _ptr(out_cl), _VP(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "mlp_tf32")
+    return _attach32(out_cf, out_cl)
+
+
+def sa_group_mlp_tf32(xyz, new_xyz, features, idx, radius, mlp: PreparedMLP, use_xyz=True, normalize_xyz=True):
+    B, P, S = idx.shape
+    N = xyz.shape[1]
+    c_feat = 0 if features is None else features.shape[1]
+    special = bool(use_xyz or c_feat == 0)
+    E, feat_cl, extra, CF = 0, None, None, 0
+    if special and 0 < c_feat <= 4:
+        E = c_feat                                  # few scalar features ride in the special K step (SA1: height)
+        extra = features.contiguous() if c_feat == 1 else features.transpose(1, 2).contiguous()
+    elif c_feat:
+        feat_cl = to_cl_f32(features)
+        CF = feat_cl.shape[2]
+    radius_t = radius if torch.is_tensor(radius) else None
+    pk = _packed_tf32(mlp, 0, 0, CF, 0 if E else c_feat, special, E, "sa")
+    return _tf32_launch(mlp, pk, B, N, P, S, None, 0, 0, None, None, feat_cl, CF, idx, xyz if special else None, new_xyz,
+                        0.0 if radius_t is not None else float(radius), radius_t, normalize_xyz, extra, E, True)
+
+
+def fp_interp_mlp_tf32(known_feats, unknow_feats, idx, weight, mlp: PreparedMLP):
+    B, C2, m = known_feats.shape
+    n = idx.shape[1]
+    known_cl = to_cl_f32(known_feats)
+    skip_cl = to_cl_f32(unknow_feats) if unknow_feats is not None else None
+    c1 = 0 if unknow_feats is None else unknow_feats.shape[1]
+    CI, CF = known_cl.shape[2], 0 if skip_cl is None else skip_cl.shape[2]
+    pk = _packed_tf32(mlp, CI, C2, CF, c1, False, 0, "fp")
+    return _tf32_launch(mlp, pk, B, n, n, 1, known_cl, m, CI, idx, weight, skip_cl, CF, None, None, None, 0.0, None, False,
+                        None, 0, True)
+
+
+def pointwise_mlp_tf32(x, mlp: PreparedMLP, last_relu=True):
+    B, C, n = x.shape
+    x_cl = to_cl_f32(x)
+    CF = x_cl.shape[2]
+    pk = _packed_tf32(mlp, 0, 0, CF, C, False, 0, "pw")
+    return _tf32_launch(mlp, pk, B, n, n, 1, None, 0, 0, None, None, x_cl, CF, None, None, None, 0.0, None, False, None, 0,
+                        last_relu)
 
 
 # ----------------------------------------------------------------------------- layout bridge
@@ -381,7 +521,8 @@ def vote_mlp_fast(seed_xyz, seed_features, mlp: PreparedMLP):
 
 def vote_fast_ok(seed_features, mlp: PreparedMLP) -> bool:
     B, C, n = seed_features.shape
-    return bool(FAST_PW[0]) and C == 256 and n % 128 == 0 and mlp.c_out == [256, 256, 259] and seed_features.dtype == torch.float32
+    return (bool(FAST_PW[0]) and mlp.dtype == "bf16" and C == 256 and n % 128 == 0 and mlp.c_out == [256, 256, 259]
+            and seed_features.dtype == torch.float32)
 
 
 # ----------------------------------------------------------------------------- stage entry points
@@ -392,7 +533,9 @@ def sa_group_mlp(xyz, new_xyz, features, idx, radius, mlp: PreparedMLP, use_xyz=
     N = xyz.shape[1]
     c_feat = 0 if features is None else features.shape[1]
     if not mlp.fusable(S) or (c_feat == 0 and not use_xyz):
-        return composed_sa(xyz, new_xyz, features, idx, radius, mlp, use_xyz, normalize_xyz)
+        _reject("sa_group_mlp", mlp, S)
+    if mlp.dtype == "tf32":
+        return sa_group_mlp_tf32(xyz, new_xyz, features, idx, radius, mlp, use_xyz, normalize_xyz)
     layout = sa_layout(c_feat, use_xyz or c_feat == 0)
     feat_cl, extra = None, None
     if layout.c0:
@@ -419,9 +562,9 @@ def fp_interp_mlp(known_feats, unknow_feats, idx, weight, mlp: PreparedMLP):
     n = idx.shape[1]
     c_skip = 0 if unknow_feats is None else unknow_feats.shape[1]
     if not mlp.fusable(1):
-        interp = ops.three_interpolate(known_feats.contiguous(), idx, weight)
-        x = interp if unknow_feats is None else torch.cat([interp, unknow_feats], dim=1)
-        return composed_pointwise(x, mlp, last_relu=True)
+        _reject("fp_interp_mlp", mlp, 1)
+    if mlp.dtype == "tf32":
+        return fp_interp_mlp_tf32(known_feats, unknow_feats, idx, weight, mlp)
     if FAST_PW[0] and C2 == 256 and c_skip == 256 and n % 128 == 0 and mlp.c_out[0] == 256 and len(mlp) == 2 \
             and 8 <= mlp.c_out[1] <= 256:
         out_cf, out_cl = fp_interp_mlp_fast(to_cl_bf16(known_feats), to_cl_bf16(unknow_feats), idx, weight, mlp, B, m, n)
@@ -441,41 +584,10 @@ def pointwise_mlp(x: torch.Tensor, mlp: PreparedMLP, last_relu: bool = True, wan
     """x (B,C,n) -> (B,Cout,n) f32 (voting and other per-point stacks)."""
     B, C, n = x.shape
     if not mlp.fusable(1):
-        return composed_pointwise(x, mlp, last_relu)
+        _reject("pointwise_mlp", mlp, 1)
+    if mlp.dtype == "tf32":
+        return pointwise_mlp_tf32(x, mlp, last_relu)
     layout = Layout(c0=_round64(C), c0_cols=range(C))
     out_cf, out_cl = fused_mlp(mlp, layout, B, n, n, 1, feat_cl=to_cl_bf16(x, pad_to=layout.c0), last_relu=last_relu,
                                want_cl=want_cl)
     return _attach(out_cf, out_cl)
-
-
-# ----------------------------------------------------------------------------- composed (general-shape) path
-def _chain(rows: torch.Tensor, mlp: PreparedMLP, last_relu: bool) -> torch.Tensor:
-    h = rows.to(torch.bfloat16)
-    n = len(mlp)
-    for i, ((W, b), Wb) in enumerate(zip(mlp.layers, mlp.W_bf16)):
-        y = (h @ Wb.t()).float() + b
-        if i < n - 1 or last_relu:
-            y = torch.relu(y)
-        h = y.to(torch.bfloat16) if i < n - 1 else y
-    return h
-
-
-def composed_sa(xyz, new_xyz, features, idx, radius, mlp, use_xyz=True, normalize_xyz=True):
-    B, P, S = idx.shape
-    g = ops.grouping_operation(xyz.transpose(1, 2).contiguous(), idx)
-    g = g - new_xyz.transpose(1, 2).unsqueeze(-1)
-    if normalize_xyz:
-        g = g / (radius[:, None, :, None] if torch.is_tensor(radius) else float(radius))
-    if features is not None:
-        gf = ops.grouping_operation(features.contiguous(), idx)
-        g = torch.cat([g, gf], dim=1) if use_xyz else gf
-    rows = g.permute(0, 2, 3, 1).reshape(B * P * S, g.shape[1])
-    y = _chain(rows, mlp, last_relu=True)
-    return y.view(B, P, S, -1).max(dim=2)[0].transpose(1, 2).contiguous()
-
-
-def composed_pointwise(x, mlp, last_relu=True):
-    B, C, n = x.shape
-    rows = x.transpose(1, 2).reshape(B * n, C)
-    y = _chain(rows, mlp, last_relu)
-    return y.view(B, n, -1).transpose(1, 2).contiguous()

@@ -50,6 +50,7 @@ class SharedMLP(nn.Module):
             self.bns.append(nn.BatchNorm2d(cout) if bn else nn.Identity())
         self._folded = None
         self._folded_key = None
+        self.mlp_dtype = "bf16"      # operand precision of the fused inference kernels: "bf16" | "tf32" (mlp.PreparedMLP)
 
     def train(self, mode: bool = True):
         self._folded = None
@@ -65,6 +66,7 @@ class SharedMLP(nn.Module):
                 ts += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
             for t in ts:
                 key.append(None if t is None else (t.data_ptr(), t._version, t.device, t.dtype))
+        key.append(self.mlp_dtype)
         return tuple(key)
 
     @torch.no_grad()
@@ -99,7 +101,7 @@ class SharedMLP(nn.Module):
                     W = W * s[:, None]
                     b = (b - bn.running_mean) * s + bn.bias.detach()
                 out.append((W.contiguous(), b.contiguous()))
-            self._folded = _mlp.prepare_layers(out)
+            self._folded = _mlp.prepare_layers(out, self.mlp_dtype)
             self._folded_key = key
         return self._folded
 
@@ -382,7 +384,7 @@ class SADHotPath(nn.Module):
     vote aggregation.  `size` (B,256,3) is the predicted box size per cluster: passed in (the benchmark's synthetic
     sizes, a downstream proposal head) or, when None, predicted by the aggregation module's own size head."""
 
-    def __init__(self, input_feature_dim: int = 1, bn: bool = True):
+    def __init__(self, input_feature_dim: int = 1, bn: bool = True, mlp_dtype: str = "bf16"):
         super().__init__()
         self.backbone = Pointnet2Backbone(input_feature_dim, bn=bn)
         self.vgen = VotingModule(256, bn=bn)
@@ -390,6 +392,17 @@ class SADHotPath(nn.Module):
         self.agg = SizeAdaptiveAggregation(c["agg"][0], c["agg"][2], 256, alpha=c["alpha"],
                                            r_min=c["r_min"], r_max=c["r_max"], bn=bn,
                                            size_scale=c["size_scale"], size_clip=c["size_clip"])
+        self.set_mlp_dtype(mlp_dtype)
+
+    def set_mlp_dtype(self, mlp_dtype: str):
+        """Operand precision of every fused MLP stage: "bf16" (default; 2e-2 bar) or "tf32" (fp32 activations)."""
+        if mlp_dtype not in ("bf16", "tf32"):
+            raise ValueError(f"mlp_dtype must be 'bf16' or 'tf32', got {mlp_dtype!r}")
+        for mod in self.modules():
+            if isinstance(mod, SharedMLP):
+                mod.mlp_dtype = mlp_dtype
+        self.mlp_dtype = mlp_dtype
+        return self
 
     @torch.no_grad()
     def load_params(self, params):

@@ -228,6 +228,21 @@ def call_cost(name, a):
         flops = 2 * rows * (cin0 * H + H * H + H * c3)
         nbytes = rows * 4 + B * min(N, P * S) * (NF * 128 + 12 + E * 4) + B * P * c3 * 6
         return nbytes, flops
+    if name == "sad_pw_mlp_fwd":
+        # specialised fused point-wise stage: (kind, B, n, m, src_cl, known_cl, nn_idx, nn_w, ..., c_last [12], out_cf, out_cl, ...)
+        kind, B, n, m, c_last = v[0], v[1], v[2], v[3], v[12]
+        rows = B * n
+
+        def live(x):
+            return getattr(x, "value", x) not in (None, 0)
+        outs = (4 if live(a[13]) else 0) + (2 if live(a[14]) else 0)
+        if kind == 0:          # FP: [interp(known) 256 | skip 256] -> 256 -> 256
+            flops = 2 * rows * (512 * 256 + 256 * c_last)
+            nbytes = rows * (24 + 256 * 2 + c_last * outs) + B * m * 256 * 2
+        else:                  # voting: 256 -> 256 -> 256 -> 3 + 256, vote = seed + y
+            flops = 2 * rows * (256 * 256 * 2 + 256 * c_last)
+            nbytes = rows * (256 * 2 + 12 + 256 * 4 + 12 + 256 * outs)
+        return nbytes, flops
     if name == "sad_shared_mlp_fwd":
         # fused stage: bytes = idx + distinct gathered rows (bf16) + outputs; flops = 2*rows*sum(Cin*Cout)
         B, N, P, S, C0, C1in, E, nl = v[0], v[1], v[2], v[3], v[5], v[7], v[15], v[16]
@@ -241,6 +256,9 @@ def call_cost(name, a):
     return 0, 0
 
 
+MLP_REPEAT = 8      # fused-MLP launches are re-issued this many times inside one CUDA-event pair (same inputs, same outputs)
+
+
 def build_roofline(model, xyz, feat, size, reps=3):
     import torch
     from sad_b200 import _lib
@@ -248,7 +266,8 @@ def build_roofline(model, xyz, feat, size, reps=3):
     agg = {}
     stages = {}
     for _ in range(reps):
-        with _lib.CallProfiler() as prof:
+        with _lib.CallProfiler(repeat={"sad_sa_mlp_fwd": MLP_REPEAT, "sad_pw_mlp_fwd": MLP_REPEAT,
+                                       "sad_shared_mlp_fwd": MLP_REPEAT}) as prof:
             with torch.no_grad():
                 torch.cuda._sleep(60000000)      # ~30 ms: every launch of the forward is queued before the first one runs
                 model(xyz, feat, size)
@@ -283,19 +302,22 @@ def build_roofline(model, xyz, feat, size, reps=3):
         kernels.append(row)
     # ---- headline: the fused gather + MLP + max-pool launches (tensor roofline).  They own the largest share of the
     # step's SM-time; the FPS chain is a serial-latency kernel and is reported in its honest unit below.
-    mlp_rows = [k for k in kernels if k["kernel"] in ("shared_mlp", "sa_mlp")]
+    mlp_rows = [k for k in kernels if k["kernel"] in ("shared_mlp", "sa_mlp", "pw_mlp")]
     flops = sum(agg[k["kernel"]]["flops"] for k in mlp_rows)
     ms = sum(agg[k["kernel"]]["ms"] for k in mlp_rows)
     n_l = sum(agg[k["kernel"]]["launches"] for k in mlp_rows)
     tfs = flops / ms / 1e9 if ms > 0 else 0.0
     roof = {"bound": "tensor", "kernel": f"fused gather + shared MLP + max-pool ({n_l:.0f} launches per step: "
-                                         "5 specialised SA stages [sa_mlp_kernel], FP1/FP2/voting [fused_mlp_kernel])",
+                                         "SA1-SA4 + aggregation [sa_mlp_kernel], FP1/FP2/voting [pw_mlp_kernel])",
             "achieved": round(tfs, 1), "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": round(tfs / peaks["tensor"], 4),
             "traffic": None, "peak_source": peaks["src"], "alg_flops_per_launch": round(flops / max(1.0, n_l)),
             "launch_ms": round(ms / max(1.0, n_l), 4), "ms_per_step_all_launches": round(ms, 4),
             "note": "bf16 operands, fp32 accumulate; peak = sustained cuBLAS bf16 (MEASURED_PEAKS.json); algorithmic flops = "
                     "2 * rows * sum(Cin*Cout) with the real (unpadded) channel counts; device time by CUDA events, launches "
-                    "queued behind a busy stream so no host gap is inside an event pair"}
+                    "queued behind a busy stream so no host gap is inside an event pair; each fused-MLP call is issued "
+                    f"{MLP_REPEAT} times back to back inside its event pair (idempotent: same inputs and outputs) and the "
+                    "elapsed time divided, because one event pair around a single 148-CTA launch adds 6-19 us "
+                    "(tools/stage_bench.py --events vs graph replay, profiles/r02_stage_bench_*.txt)"}
     per_stage = []
     for k in mlp_rows:
         per_stage.append({"kernel": k["kernel"], "ms": k["ms_per_step"], "GFLOP": k.get("GFLOP_per_step"),
@@ -553,7 +575,7 @@ def attach_traffic(roof):
     (profiles/ncu_full_summary.json, written by tools/ncu_full_summary.py), per launch."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "ncu_full_summary.json")))
-        rows = [r for r in d.get("kernels", []) if r.get("roofline_key") in ("shared_mlp", "sa_mlp") and "dram_bytes_per_launch" in r]
+        rows = [r for r in d.get("kernels", []) if r.get("roofline_key") in ("shared_mlp", "sa_mlp", "pw_mlp") and "dram_bytes_per_launch" in r]
         if rows:
             roof["traffic"] = int(sum(r["dram_bytes_per_launch"] for r in rows) / len(rows))
             roof["traffic_source"] = "profiles/ncu_full_summary.json (ncu --set full, mean over the step's launches of this kernel)"

@@ -228,6 +228,30 @@ SAD_API int sad_pw_mlp_fwd(int kind, int B, int n, int m, const void* src_cl, co
                            const float* bias_last_padded, int c_last, float* out_cf, void* out_cl, const float* seed_xyz,
                            const float* seed_cf, float* vote_xyz, int tiles_per_cta, sad_stream_t stream);
 
+/* ---- a6, tf32 mode (csrc/mlp_tf32.cu): the same fused stage with fp32 channel-last activations and kind::tf32 MMAs
+ * (north_star "tcgen05 bf16/tf32 GEMM"); 1e-3-class agreement with the fp32 oracle instead of the bf16 path's 2e-2.
+ * Layer-1 operand, K order [interp | feat | special]:
+ *   interp   CI channels = three_interpolate(known_cl (B,m,CI), nn_idx (B*P,3), nn_w (B*P,3)) computed in the kernel
+ *            (nsample == 1 only), or CI == 0;
+ *   feat     CF channels of feat_cl (B,N,CF), row idx[b,p,s] (idx (B,P,S)), or row p itself when idx == NULL
+ *            (nsample == 1, N == P), or CF == 0;
+ *   special  when xyz != NULL: [(xyz[idx]-new_xyz)/r, extra[idx][0..E-1], 0..] as one 8-wide K step (E <= 4); r = radius
+ *            or radius_t[b,p] when normalize_xyz, else 1.
+ * CI, CF multiples of 4; each part is zero-padded to 32-channel chunks.  2-3 layers, hidden widths % 32 == 0 and
+ * <= 256, last width <= 512, nsample a power of two <= 128.  ReLU after every layer except (last_relu == 0) the last;
+ * max over nsample.  out_cf (B,c_last,P) f32 and / or out_cl (B,P,c_last) f32.
+ * Weights: per layer one image from sad_mlp_tf32_pack(W (c_out x kc*32) fp32 row-major, input channels in operand
+ * order, zero-padded per chunk; kc = that layer's 32-channel K chunks; last = 1 for the last layer) of
+ * sad_mlp_tf32_image_bytes(c_out, kc, last) bytes, device resident.  bias[l]: c_out[l] floats (last layer: padded
+ * with zeros to a multiple of 128). */
+SAD_API long long sad_mlp_tf32_image_bytes(int c_out, int kc, int last);
+SAD_API int sad_mlp_tf32_pack(const float* W, int c_out, int kc, int last, void* out);
+SAD_API int sad_mlp_tf32_fwd(int B, int N, int P, int S, const float* known_cl, int m, int CI, const int32_t* nn_idx,
+                             const float* nn_w, const float* feat_cl, int CF, const int32_t* idx, const float* xyz,
+                             const float* new_xyz, float radius, const float* radius_t, int normalize_xyz,
+                             const float* extra, int E, int n_layers, const void* const* w_img, const float* const* bias,
+                             const int* c_out, int last_relu, float* out_cf, float* out_cl, sad_stream_t stream);
+
 /* Scheduling options of one sad_shared_mlp_fwd launch (never change results); NULL = defaults.
  *   tiles_per_cta  at least this many 128-row tiles per CTA, i.e. a narrower grid for the small stages.  1 (default) =
  *                  one CTA per SM whenever there are that many tiles: shortest time for one launch.  A pipelined

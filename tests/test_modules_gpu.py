@@ -74,7 +74,7 @@ def test_train_mode_matches_eval_and_backprops(setup):
     rng = np.random.default_rng(3)
     xyz = cu((rng.random((2, 600, 3), dtype=np.float32) * 2).astype(np.float32))
     feat = cu(rng.standard_normal((2, 6, 600)).astype(np.float32)).requires_grad_(True)
-    sa = PointnetSAModuleVotes(64, 0.5, 8, [6, 16, 32]).to(DEV)
+    sa = PointnetSAModuleVotes(64, 0.5, 8, [6, 64, 32]).to(DEV)
     fp = PointnetFPModule([32 + 6, 16]).to(DEV)
     sa.eval(), fp.eval()
     new_xyz, f_train_path, inds = sa(xyz, feat)                    # grad enabled -> torch path

@@ -10,9 +10,30 @@ import sad_b200  # noqa
 from sad_b200 import mlp as M
 
 
+EVENTS = [False]
+
+
+def t_events(fn, it=20):
+    """One launch per CUDA-event pair, every launch queued behind a busy stream (what bench.py's per-call profile sees)."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(it):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(4000000)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return 1e3 * ts[len(ts) // 2], 1e3 * ts[0]
+
+
 def t(fn, it=20, reps=10):
     """Device time of one call: `reps` calls captured into a CUDA graph (no host overhead between the launches),
     median / best over `it` replays."""
+    if EVENTS[0]:
+        return t_events(fn, it)
     st = torch.cuda.Stream()
     with torch.cuda.stream(st):
         for _ in range(3):
@@ -45,7 +66,9 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--no-cf", action="store_true")
     ap.add_argument("--real", action="store_true", help="SA1 / SA2 on real scene data (FPS + ball-query indices)")
+    ap.add_argument("--events", action="store_true", help="time single launches with one event pair each (not graph replay)")
     args = ap.parse_args()
+    EVENTS[0] = args.events
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
     except Exception:
