@@ -227,6 +227,116 @@ interp_fwd_pm_kernel(int C, int m, int n, int groups_per_cta, const float* __res
   }
 }
 
+// Pipelined point-major variant (FP-module shapes, m <= 512): what held the two kernels above at 51-59 % of the HBM
+// peak was not their gather rate but that every CTA ran stage -> barrier -> compute, with its loads exposed in the
+// first phase and nothing but stores in flight in the second.  Here CTAs are persistent over (scene, 32-channel chunk)
+// work items and the chunk f[b, c0:c0+32, :] -- contiguous in the channel-first tensor -- arrives by ONE TMA bulk copy
+// that was issued a whole work item earlier:
+//   wait(raw full) -> transpose raw[c][k] -> s_f[k][32] (shared -> shared, conflict-free both ways) -> barrier ->
+//   thread 0 issues the bulk copy of the NEXT item into raw (already free) -> gather/compute/store from s_f -> barrier
+// so HBM reads stream in the background of the gather phase and the read and write streams overlap inside one CTA.
+// The gather phase is the point-major one of interp_fwd_pm_kernel (same lane roles, same transposition tile).
+template <int T>
+__global__ void __launch_bounds__(T, T == 256 ? 2 : 1)
+interp_fwd_pipe_kernel(int B, int C, int m, int n, int ychunks, const float* __restrict__ features,
+                       const int32_t* __restrict__ idx, const float* __restrict__ weight, float* __restrict__ out) {
+  extern __shared__ __align__(128) float s_dyn[];
+  __shared__ __align__(8) uint64_t s_bar;
+  using namespace sad;
+  constexpr int CN = 32;
+  float* s_t = s_dyn;                                       // [warps][32 channels][32 points]
+  float* s_f = s_t + (T / 32) * TIP_TILE;               // [m][32], 16-byte units swizzled by (k & 7)
+  float* s_raw = s_f + (size_t)m * CN;                      // [32][m]: the bulk copy's landing zone
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int items = B * ychunks;
+  const int per = (items + gridDim.x - 1) / gridDim.x;      // contiguous ranges: a CTA stays on one scene's idx / weights
+  const int w_begin = blockIdx.x * per, w_end = min(items, w_begin + per);
+  auto issue = [&](int w) {
+    const int b = w / ychunks, c0 = (w - b * ychunks) * CN;
+    const uint32_t bytes = (uint32_t)min(CN, C - c0) * (uint32_t)m * 4u;
+    mbar_arrive_expect_tx(&s_bar, bytes);
+    tma_bulk_g2s(s_raw, features + ((size_t)b * C + c0) * m, bytes, &s_bar);
+  };
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    if (w_begin < w_end) issue(w_begin);
+  }
+  __syncthreads();
+  const int Q = lane >> 3, q = lane & 7;
+  float* tile = s_t + warp * TIP_TILE;
+  const int groups = (n + 31) >> 5;
+  uint32_t phase = 0;
+  for (int w = w_begin; w < w_end; ++w, phase ^= 1u) {
+    const int b = w / ychunks, c0 = (w - b * ychunks) * CN;
+    mbar_wait(&s_bar, phase);
+    // ---- transpose: thread = known point k; 32 conflict-free 4-byte reads, eight conflict-free 16-byte writes
+    for (int k = tid; k < m; k += T) {
+      float v[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = s_raw[(size_t)e * m + k];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<float4*>(s_f + (size_t)k * CN + 4 * (u ^ (k & 7))) =
+            make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+    }
+    __syncthreads();
+    if (tid == 0 && w + 1 < w_end) issue(w + 1);            // raw is free: the next chunk streams in under the gathers
+    // ---- gather: a warp = 32 unknown points per step (two half-steps of 16 points)
+    const int4* ib = reinterpret_cast<const int4*>(idx + (size_t)b * n * 3);
+    const float4* wb = reinterpret_cast<const float4*>(weight + (size_t)b * n * 3);
+    for (int g = warp; g < groups; g += T / 32) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int i4 = g * 32 + half * 16 + 4 * Q;
+        int id[12];
+        float wt[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+          id[e] = 0;
+          wt[e] = 0.f;
+        }
+        if (i4 < n) {
+#pragma unroll
+          for (int e = 0; e < 3; ++e) {
+            const int4 a = __ldg(ib + (size_t)(i4 >> 2) * 3 + e);
+            const float4 ww = __ldg(wb + (size_t)(i4 >> 2) * 3 + e);
+            id[4 * e] = a.x; id[4 * e + 1] = a.y; id[4 * e + 2] = a.z; id[4 * e + 3] = a.w;
+            wt[4 * e] = ww.x; wt[4 * e + 1] = ww.y; wt[4 * e + 2] = ww.z; wt[4 * e + 3] = ww.w;
+          }
+        }
+        float acc[4][4];
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+          const int r0 = id[3 * pp], r1 = id[3 * pp + 1], r2 = id[3 * pp + 2];
+          const float4 f0 = *reinterpret_cast<const float4*>(s_f + (size_t)r0 * CN + 4 * (q ^ (r0 & 7)));
+          const float4 f1 = *reinterpret_cast<const float4*>(s_f + (size_t)r1 * CN + 4 * (q ^ (r1 & 7)));
+          const float4 f2 = *reinterpret_cast<const float4*>(s_f + (size_t)r2 * CN + 4 * (q ^ (r2 & 7)));
+          const float a0 = wt[3 * pp], a1 = wt[3 * pp + 1], a2 = wt[3 * pp + 2];
+          acc[pp][0] = interp3(a0, f0.x, a1, f1.x, a2, f2.x);
+          acc[pp][1] = interp3(a0, f0.y, a1, f1.y, a2, f2.y);
+          acc[pp][2] = interp3(a0, f0.z, a1, f1.z, a2, f2.z);
+          acc[pp][3] = interp3(a0, f0.w, a1, f1.w, a2, f2.w);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(tile + (4 * q + j) * 32 + 4 * ((Q + 4 * half) ^ q)) =
+              make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = Q + 4 * it;
+        const float4 v = *reinterpret_cast<const float4*>(tile + row * 32 + 4 * (q ^ ((row >> 2) & 7)));
+        const int c = c0 + row, i = g * 32 + 4 * q;
+        if (c < C && i < n) __stcs(reinterpret_cast<float4*>(out + ((size_t)b * C + c) * n + i), v);
+      }
+      __syncwarp();
+    }
+    __syncthreads();                                        // s_f is rewritten by the next item's transposition
+  }
+}
+
 __global__ void __launch_bounds__(TI_T)
 interp_bwd_kernel(int C, int n, int m, const float* __restrict__ grad_out, const int32_t* __restrict__ idx,
                   const float* __restrict__ weight, float* __restrict__ grad_features) {
@@ -266,6 +376,36 @@ extern "C" int sad_three_interpolate_fwd(int B, int C, int m, int n, const float
   // (measured, B = 256, C = 256: n=1024/m=512 58.6 % of the HBM peak vs 57.6 % row-staged; n=512/m=256 51 % vs 53 % --
   // both kernels sit at ~70 % of the SM's LSU wavefront rate; the point-major kernel takes
   // the larger-m shapes, where its lower wavefront count per output wins)
+  // pipelined point-major kernel: FP-module shapes (the chunk, its transposed copy and the tiles fit one CTA)
+  if (n % 4 == 0 && m % 4 == 0 && aligned16(out) && aligned16(idx) && aligned16(weight) && aligned16(features) && m >= 64 &&
+      m <= 512 && 2LL * n >= m && n >= 256 && !sad_tool_env("SAD_INTERP_LEGACY")) {
+    const int ychunks = sad_ceil_div(C, 32);
+    const long long items = (long long)B * ychunks;
+    // two 256-thread CTAs per SM while they fit (m <= 256), else one 512-thread CTA
+    const bool small = ((size_t)m * 64 + 8 * TIP_TILE) * sizeof(float) <= 100 * 1024;
+    const int threads = small ? 256 : 512;
+    const size_t smem = ((size_t)m * 64 + (threads / 32) * TIP_TILE) * sizeof(float);
+    const int ctas_per_sm = small ? 2 : 1;
+    static thread_local int configured_dev_pipe = -1;
+    int dev = 0;
+    SAD_CUDA_OK(cudaGetDevice(&dev));
+    if (configured_dev_pipe != dev) {
+      SAD_CUDA_OK(cudaFuncSetAttribute(interp_fwd_pipe_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      SAD_CUDA_OK(cudaFuncSetAttribute(interp_fwd_pipe_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (512 * 64 + 16 * TIP_TILE) * 4));
+      configured_dev_pipe = dev;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long grid = (long long)sms * ctas_per_sm;
+    if (grid > items) grid = items;
+    if (small)
+      interp_fwd_pipe_kernel<256><<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(B, C, m, n, ychunks, features, idx, weight, out);
+    else
+      interp_fwd_pipe_kernel<512><<<(unsigned)grid, 512, smem, (cudaStream_t)stream>>>(B, C, m, n, ychunks, features, idx, weight, out);
+    SAD_LAUNCH_CHECK("three_interpolate");
+    return SAD_OK;
+  }
   if (n % 4 == 0 && aligned16(out) && aligned16(idx) && aligned16(weight) && m >= 384 && m <= 1408 && 2LL * n >= m &&
       !sad_tool_env("SAD_INTERP_LEGACY")) {
     const int cn = (m <= 128 && C > 32) ? 64 : 32;

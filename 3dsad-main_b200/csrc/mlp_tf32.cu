@@ -9,13 +9,16 @@
 // transposed (lane = output channel) so the max over nsample is an in-register reduction.  Operands are rounded to
 // tf32 (cvt.rna, 10-bit mantissa) when they are written; accumulation, bias, ReLU and max are fp32.
 //
-//   shared memory   activations 128 rows x 256 ch x 4 B = 128 KB (K-major SWIZZLE_128B, 32-channel chunks of 16 KB)
-//                   A ring  2 x 16 KB   layer-1 operand chunks (128 rows x 32 channels)
-//                   W ring  2 x 32 KB   weight pieces, one TMA bulk copy each (<= 256 rows x 32 K values)
+//   shared memory   activations 128 rows x widest hidden layer x 4 B (<= 128 KB; K-major SWIZZLE_128B, 32-channel
+//                   chunks of 16 KB)
+//                   W ring  2-8 stages of one weight piece (<= 256 rows x 32 K values = 32 KB), one TMA bulk copy
+//                   each: the pieces are re-streamed from L2 for every tile, the ring depth is the prefetch distance
+//                   A ring  2-4 x 16 KB   layer-1 operand chunks (128 rows x 32 channels)
 //   TMEM            hidden accumulators in columns [0,256); last-layer blocks (128 channels x 128 rows) in 128-column
 //                   regions (columns 256.. when there are at most two blocks, so the next tile's first layers run under
 //                   the drain of this tile's last layer)
-//   warps           0-3 epilogue (thread = TMEM lane), 4-7 operand producers (thread = row), 8 MMA issue, 9 weight TMA
+//   warps           0-15 epilogue (4 column groups x 4 TMEM lane quarters), 16-19 operand producers (thread = row),
+//                   20 MMA issue, 21 weight TMA
 //
 // One 128-row tile (row = (query point, sample)) is in flight per CTA; persistent CTAs take tiles round-robin.
 // Roofline: tensor (kind::tf32 peak = half the bf16 peak); algorithmic flops = 2 * rows * sum(Cin*Cout).
@@ -28,13 +31,10 @@ namespace {
 using namespace sad;
 
 constexpr int kChunk = 16384;                 // 128 rows x 128 B = 32 fp32 channels per row
-constexpr int kActBytes = 8 * kChunk;         // 256 channels
-constexpr int kNSA = 2, kNSW = 2;
-constexpr int kWStage = 2 * kChunk;
+constexpr int kMaxNSA = 4, kMaxNSW = 8;       // ring depths are chosen per launch from what the activations leave free
 constexpr int kMisc = 1024;
-constexpr int kSmem = 1024 + kActBytes + kNSA * kChunk + kNSW * kWStage + kMisc;
-static_assert(kSmem <= 227 * 1024, "shared-memory budget");
-constexpr int kWarpProd = 4, kWarpMma = 8, kWarpTma = 9, kThreads = 10 * 32;
+constexpr int kSmemMax = 227 * 1024;
+constexpr int kEpiWarps = 16, kWarpProd = 16, kWarpMma = 20, kWarpTma = 21, kThreads = 22 * 32;
 constexpr int kMaxLayers = 3;
 
 struct TfParams {
@@ -66,10 +66,12 @@ struct TfParams {
   int last_relu;
   float* out_cf;                     // (B, c_last, P) f32 or null
   float* out_cl;                     // (B, P, c_last) f32 or null
+  // shared-memory carve-up
+  int act_bytes, nsa, nsw, wstage;
 };
 
 struct Misc {
-  uint64_t wfull[kNSW], wfree[kNSW], afull[kNSA], afree[kNSA];
+  uint64_t wfull[kMaxNSW], wfree[kMaxNSW], afull[kMaxNSA], afree[kMaxNSA];
   uint64_t dfull[1 + 4];             // [0] hidden layers, [1 + blk] last-layer blocks
   uint64_t actfull, tfree;
   uint32_t tmem_base;
@@ -83,7 +85,11 @@ __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   long long t0 = 0;
   for (;;) {
+#ifdef SAD_TF32_SPIN
+    if (mbar_try_wait(bar, parity)) return;
+#else
     if (mbar_try_wait_sleep(bar, parity)) return;
+#endif
     if ((++spins & 0xFFu) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
@@ -91,6 +97,20 @@ __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+#ifdef SAD_TF32_PROFILE
+#define TFP_DECL long long tfp_wait[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long tfp_t0 = clock64();
+#define TFP_WAIT(slot, bar, par) do { const long long t_ = clock64(); bar_wait(bar, par); tfp_wait[slot] += clock64() - t_; } while (0)
+#define TFP_T(var) const long long var = clock64()
+#define TFP_ADD(slot, a, b) tfp_wait[slot] += (b) - (a)
+#define TFP_REPORT(role) do { if (blockIdx.x == 0 && lane == 0) printf("tf32 %s total %lld waits %lld %lld %lld %lld %lld %lld | %lld %lld %lld %lld tiles %d\n", role, clock64() - tfp_t0, tfp_wait[0], tfp_wait[1], tfp_wait[2], tfp_wait[3], tfp_wait[4], tfp_wait[5], tfp_wait[6], tfp_wait[7], tfp_wait[8], tfp_wait[9], my_tiles); } while (0)
+#else
+#define TFP_DECL
+#define TFP_WAIT(slot, bar, par) bar_wait(bar, par)
+#define TFP_T(var)
+#define TFP_ADD(slot, a, b)
+#define TFP_REPORT(role)
+#endif
+
 __device__ __forceinline__ uint32_t tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -108,22 +128,66 @@ __device__ __forceinline__ uint32_t uidesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Output cursor of one lane (= one output channel) of the transposed last layer.
+struct OutCursor {
+  float* pcl;          // out_cl + pt * c_last + ch, or null
+  float* pcf;          // out_cf + (b * c_last + ch) * P + p, or null
+  long long rem;       // outputs this lane may still write (0 for padded channels / past the end)
+  int op, P, c_last;
+  size_t cf_wrap;      // (c_last - 1) * P: from the end of one scene's row to the next scene's row of this channel
+  float bias;
+  int relu;
+  __device__ __forceinline__ void emit(float mx) {
+    float y = __fadd_rn(mx, bias);
+    if (relu) y = fmaxf(y, 0.f);
+    if (rem > 0) {
+      if (pcl) *pcl = y;
+      if (pcf) *pcf = y;
+    }
+    --rem;
+    if (pcl) pcl += c_last;
+    if (pcf) {
+      ++pcf;
+      if (++op == P) {
+        op = 0;
+        pcf += cf_wrap;
+      }
+    }
+  }
+};
+// One 32-column group of the transposed last layer: max over windows of S columns (compile-time S: the reduction is
+// an in-register tree, no per-column branch), one emit per finished window.
+template <int S>
+__device__ __forceinline__ void pool_group(const uint32_t (&v)[32], float& mx, bool window_ends, OutCursor& oc) {
+  if constexpr (S <= 32) {
+#pragma unroll
+    for (int k = 0; k < 32 / S; ++k) oc.emit(vmax_tree<S>(v + k * S));
+  } else {
+    mx = fmaxf(mx, vmax_tree<32>(v));
+    if (window_ends) {
+      oc.emit(mx);
+      mx = -INFINITY;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* act = base;
-  uint8_t* aring = act + kActBytes;
+  const int kNSA = p.nsa, kNSW = p.nsw, kWStage = p.wstage;
+  uint8_t* aring = act + p.act_bytes;
   uint8_t* wring = aring + kNSA * kChunk;
   Misc* ms = reinterpret_cast<Misc*>(wring + kNSW * kWStage);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NL = p.n_layers;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kNSW; ++i) { mbar_init(&ms->wfull[i], 1); mbar_init(&ms->wfree[i], 1); }
-    for (int i = 0; i < kNSA; ++i) { mbar_init(&ms->afull[i], 4); mbar_init(&ms->afree[i], 1); }
+    for (int i = 0; i < kMaxNSW; ++i) { mbar_init(&ms->wfull[i], 1); mbar_init(&ms->wfree[i], 1); }
+    for (int i = 0; i < kMaxNSA; ++i) { mbar_init(&ms->afull[i], 4); mbar_init(&ms->afree[i], 1); }
     for (int i = 0; i < 5; ++i) mbar_init(&ms->dfull[i], 1);
-    mbar_init(&ms->actfull, 4);
-    mbar_init(&ms->tfree, 4);
+    mbar_init(&ms->actfull, kEpiWarps);
+    mbar_init(&ms->tfree, kEpiWarps);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<1>(&ms->tmem_base, 512);
@@ -135,6 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
   const int kcI = (p.CI + 31) >> 5, kcF = (p.CF + 31) >> 5;
   const bool special = p.xyz != nullptr;
   const uint32_t last_col0 = p.nblk <= 2 ? 256u : 0u;
+  TFP_DECL
 
   if (warp == kWarpTma) {
     // ============================================================ weight pieces through the W ring
@@ -148,24 +213,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
           const uint8_t* src = p.w_img[l];
           for (int i = 0; i < pieces; ++i, ++w) {
             const int st = w % kNSW;
-            bar_wait(&ms->wfree[st], ((w / kNSW) & 1u) ^ 1u);
+            TFP_WAIT(0, &ms->wfree[st], ((w / kNSW) & 1u) ^ 1u);
             mbar_arrive_expect_tx(&ms->wfull[st], bytes);
             tma_bulk_g2s(wring + st * kWStage, src + (size_t)i * bytes, bytes, &ms->wfull[st]);
           }
         }
       }
+      TFP_REPORT("loader  ");
     }
   } else if (warp == kWarpMma) {
     // ============================================================ MMA issue
     uint32_t w = 0, a = 0, n_act = 0;
     const uint32_t act_addr = smem_u32(act);
     for (int t = 0; t < my_tiles; ++t) {
-      if (t > 0 && p.nblk > 2) bar_wait(&ms->tfree, (uint32_t)(t - 1) & 1u);      // last-layer blocks overlap the hidden columns
+      if (t > 0 && p.nblk > 2) TFP_WAIT(3, &ms->tfree, (uint32_t)(t - 1) & 1u);      // last-layer blocks overlap the hidden columns
       for (int l = 0; l < NL; ++l) {
         const bool last = l == NL - 1;
         if (l > 0) {
-          bar_wait(&ms->actfull, (n_act++) & 1u);
-          if (last && t > 0 && p.nblk <= 2) bar_wait(&ms->tfree, (uint32_t)(t - 1) & 1u);
+          TFP_WAIT(2, &ms->actfull, (n_act++) & 1u);
+          if (last && t > 0 && p.nblk <= 2) TFP_WAIT(3, &ms->tfree, (uint32_t)(t - 1) & 1u);
         }
         const int KC = p.kc[l];
         const int nb = last ? p.nblk : 1;
@@ -174,12 +240,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
           const uint32_t d = tmem + (last ? last_col0 + 128u * blk : 0u);
           for (int c = 0; c < KC; ++c, ++w) {
             const int ws = w % kNSW;
-            bar_wait(&ms->wfull[ws], (w / kNSW) & 1u);
+            TFP_WAIT(0, &ms->wfull[ws], (w / kNSW) & 1u);
             int as = 0;
             int ksteps = 4;
             if (l == 0) {
               as = a % kNSA;
-              bar_wait(&ms->afull[as], (a / kNSA) & 1u);
+              TFP_WAIT(1, &ms->afull[as], (a / kNSA) & 1u);
               if (special && c == KC - 1) ksteps = 1;
             }
             tc_fence_after_sync();
@@ -202,6 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
         }
       }
     }
+    TFP_REPORT("mma     ");
   } else if (warp >= kWarpProd && warp < kWarpProd + 4) {
     // ============================================================ layer-1 operand producers: thread = row of the tile
     const int r = (warp - kWarpProd) * 32 + lane;
@@ -221,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
       const int KC = p.kc[0];
       for (int c = 0; c < KC; ++c, ++a) {
         const int st = a % kNSA;
-        bar_wait(&ms->afree[st], ((a / kNSA) & 1u) ^ 1u);
+        TFP_WAIT(1, &ms->afree[st], ((a / kNSA) & 1u) ^ 1u);
         const uint32_t dst = smem_u32(aring + st * kChunk);
         uint32_t v[32];
 #pragma unroll
@@ -285,75 +352,114 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
         if (lane == 0) mbar_arrive(&ms->afull[st]);
       }
     }
-  } else if (warp < 4) {
-    // ============================================================ epilogue: thread = TMEM lane
-    const int q = warp;
+    if (warp == kWarpProd) TFP_REPORT("producer");
+  } else if (warp < kEpiWarps) {
+    // ============================================================ epilogue: 16 warps = 4 column groups x 4 lane quarters
+    const int eg = warp >> 2, q = warp & 3;       // a warp may only read TMEM lanes 32 * (warp % 4) .. + 31
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     const int row = q * 32 + lane;
     uint32_t n_d0 = 0;
     const int c_last = p.c_out[NL - 1];
+    // last layer: a unit = the 32-column groups one max-pool window spans (1 for nsample <= 32, 2 for 64, 4 for 128)
+    const int ug = p.S <= 32 ? 1 : p.S >> 5;
+    const int upb = 4 / ug;
+    const int items = p.nblk * upb;
     for (int t = 0; t < my_tiles; ++t) {
       const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
       for (int l = 0; l < NL - 1; ++l) {
-        bar_wait(&ms->dfull[0], (n_d0++) & 1u);
+        TFP_WAIT(4, &ms->dfull[0], (n_d0++) & 1u);
         tc_fence_after_sync();
         const int groups = p.c_out[l] >> 5;
         const float* bias = p.bias[l];
-        for (int g = 0; g < groups; ++g) {
+        for (int g = eg; g < groups; g += 4) {
           uint32_t v[32];
+          TFP_T(e0);
           tmem_ld_x32(lane_addr + (uint32_t)(g * 32), v);
+          float bv[32];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + g * 32) + u);
+            bv[4 * u] = b4.x; bv[4 * u + 1] = b4.y; bv[4 * u + 2] = b4.z; bv[4 * u + 3] = b4.w;
+          }
           tmem_ld_fence();
+          TFP_T(e1);
+          TFP_ADD(0, e0, e1);
           const uint32_t dst = smem_u32(act) + (uint32_t)g * kChunk;
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             uint32_t o[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              o[k] = tf32_rna(fmaxf(__fadd_rn(__uint_as_float(v[u * 4 + k]), __ldg(bias + g * 32 + u * 4 + k)), 0.f));
+              o[k] = tf32_rna(fmaxf(__fadd_rn(__uint_as_float(v[u * 4 + k]), bv[u * 4 + k]), 0.f));
             sts_v4(dst + swz128(row, u), o[0], o[1], o[2], o[3]);
           }
+          TFP_T(e2);
+          TFP_ADD(1, e1, e2);
         }
+        TFP_T(e3);
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ms->actfull);
+        TFP_T(e4);
+        TFP_ADD(2, e3, e4);
       }
       // last layer, transposed: lane = output channel, TMEM column = row of the tile
       const long long pt0 = (tile * 128) >> p.log2S;       // first point of the tile (128 % S == 0)
       for (int blk = 0; blk < p.nblk; ++blk) {
-        bar_wait(&ms->dfull[1 + blk], (uint32_t)t & 1u);
-        tc_fence_after_sync();
+        TFP_WAIT(5, &ms->dfull[1 + blk], (uint32_t)t & 1u);
+      }
+      tc_fence_after_sync();
+      TFP_T(e5);
+      for (int item = eg; item < items; item += 4) {
+        const int blk = item / upb, g0 = (item - blk * upb) * ug;
         const int ch = blk * 128 + row;
         const float bias = __ldg(p.bias[NL - 1] + ch);
         const bool ch_ok = ch < c_last;
+        TFP_T(f0);
+        // (scene, point) of the unit's first output, advanced incrementally: one division per unit.  The emit is kept
+        // to a dozen instructions because it is inlined 32 times (instruction-cache footprint of the column loop).
+        const long long pt = pt0 + ((g0 * 32) >> p.log2S);
+        const int ob = (int)(pt / p.P);
+        OutCursor oc;
+        oc.op = (int)(pt - (long long)ob * p.P);
+        oc.P = p.P;
+        oc.c_last = c_last;
+        oc.rem = ch_ok ? p.total_points - pt : 0;
+        oc.pcl = p.out_cl ? p.out_cl + (size_t)pt * c_last + ch : nullptr;
+        oc.pcf = p.out_cf ? p.out_cf + ((size_t)ob * c_last + ch) * p.P + oc.op : nullptr;
+        oc.cf_wrap = (size_t)(c_last - 1) * p.P;
+        oc.bias = bias;
+        oc.relu = p.last_relu;
         float mx = -INFINITY;
-        for (int g = 0; g < 4; ++g) {
+        TFP_T(f1);
+        TFP_ADD(6, f0, f1);
+        for (int g = g0; g < g0 + ug; ++g) {
           uint32_t v[32];
+          TFP_T(f2);
           tmem_ld_x32(lane_addr + last_col0 + (uint32_t)(blk * 128 + g * 32), v);
           tmem_ld_fence();
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            mx = fmaxf(mx, __uint_as_float(v[jj]));
-            if (((g * 32 + jj + 1) & (p.S - 1)) == 0) {
-              const long long pt = pt0 + ((g * 32 + jj) >> p.log2S);
-              float y = __fadd_rn(mx, bias);
-              if (p.last_relu) y = fmaxf(y, 0.f);
-              mx = -INFINITY;
-              if (ch_ok && pt < p.total_points) {
-                if (p.out_cl) p.out_cl[(size_t)pt * c_last + ch] = y;
-                if (p.out_cf) {
-                  const long long b = pt / p.P;
-                  p.out_cf[((size_t)b * c_last + ch) * p.P + (pt - b * p.P)] = y;
-                }
-              }
-            }
+          TFP_T(f3);
+          TFP_ADD(7, f2, f3);
+          const bool ends = g == g0 + ug - 1;
+          switch (p.log2S) {
+            case 0: pool_group<1>(v, mx, ends, oc); break;
+            case 1: pool_group<2>(v, mx, ends, oc); break;
+            case 2: pool_group<4>(v, mx, ends, oc); break;
+            case 3: pool_group<8>(v, mx, ends, oc); break;
+            case 4: pool_group<16>(v, mx, ends, oc); break;
+            case 5: pool_group<32>(v, mx, ends, oc); break;
+            default: pool_group<64>(v, mx, ends, oc); break;
           }
         }
       }
+      TFP_T(e6);
+      TFP_ADD(3, e5, e6);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ms->tfree);
     }
+    if (warp == 0) TFP_REPORT("epilogue");
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -453,9 +559,26 @@ extern "C" int sad_mlp_tf32_fwd(int B, int N, int P, int S, const float* known_c
   p.nblk = (c_out[n_layers - 1] + 127) / 128;
   p.last_relu = last_relu;
   p.out_cf = out_cf; p.out_cl = out_cl;
+  // shared memory: activations sized by the widest hidden layer; what is left goes to the weight ring (every piece
+  // is re-streamed from L2 per tile, so its depth is the prefetch distance), then to the layer-1 operand ring
+  int max_h = 0, piece = 16384;
+  for (int l = 0; l < n_layers - 1; ++l) {
+    if (c_out[l] > max_h) max_h = c_out[l];
+    const int b = ((c_out[l] + 15) & ~15) * 128;
+    if (b > piece) piece = b;
+  }
+  p.act_bytes = (max_h / 32) * kChunk;
+  p.wstage = (piece + 1023) & ~1023;
+  const int usable = kSmemMax - 1024 - kMisc;
+  p.nsw = (usable - p.act_bytes - 2 * kChunk) / p.wstage;
+  if (p.nsw > kMaxNSW) p.nsw = kMaxNSW;
+  if (p.nsw < 2) return fail(SAD_EUNSUPPORTED, "mlp_tf32: layers too wide for shared memory");
+  p.nsa = 2 + (usable - p.act_bytes - p.nsw * p.wstage - 2 * kChunk) / kChunk;
+  if (p.nsa > kMaxNSA) p.nsa = kMaxNSA;
+  const int kSmem = 1024 + p.act_bytes + p.nsa * kChunk + p.nsw * p.wstage + kMisc;
   static bool configured = false;
   if (!configured) {
-    SAD_CUDA_OK(cudaFuncSetAttribute(mlp_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    SAD_CUDA_OK(cudaFuncSetAttribute(mlp_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     configured = true;
   }
   int sms = 148;

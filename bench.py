@@ -48,7 +48,9 @@ WORKLOAD = "configs[1]: VoteNet-style backbone (4 SA + 2 FP) + voting + size-ada
 def workload_config(n_gpus):
     """`config` of the JSON line: the workload only, identical in both arms (what differs between the arms -- pipeline
     depth, FPS scheduling, dtypes of the MLP -- is in `run`)."""
-    return {"workload": WORKLOAD, "scenes_per_gpu_per_step": B_PER_GPU, "points_per_scene": N_POINTS,
+    wl = WORKLOAD if (B_PER_GPU, N_POINTS) == (8, 40000) else \
+        f"configs[4] sweep point: the configs[1] path at B={B_PER_GPU} x {N_POINTS}-point scenes per GPU (--batch / --points)"
+    return {"workload": wl, "scenes_per_gpu_per_step": B_PER_GPU, "points_per_scene": N_POINTS,
             "scene_kind": "surface (floor + walls + 12 boxes, 5 mm noise), seeded", "input_feature": "height (1 channel)",
             "layers": "SA1 2048x64 r0.2 [4,64,64,128] | SA2 1024x32 r0.4 [131,128,128,256] | SA3 512x16 r0.8 [259,128,128,256] | "
                       "SA4 256x16 r1.2 [259,128,128,256] | FP1,FP2 [512,256,256] | vote [256,256,256,259] | "
@@ -243,6 +245,16 @@ def call_cost(name, a):
             flops = 2 * rows * (256 * 256 * 2 + 256 * c_last)
             nbytes = rows * (256 * 2 + 12 + 256 * 4 + 12 + 256 * outs)
         return nbytes, flops
+    if name == "sad_mlp_tf32_fwd":
+        # tf32 fused stage: (B, N, P, S, known, m, CI, nn_idx, nn_w, feat, CF, idx, xyz, ..., E [18], n_layers, w, b, c_out [22], ...)
+        B, N, P, S, CI, CF, E = v[0], v[1], v[2], v[3], v[6], v[10], v[18]
+        has_xyz = getattr(a[12], "value", a[12]) not in (None, 0)
+        cout = list(a[22])
+        rows = B * P * S
+        cin0 = CI + CF + (3 + E if has_xyz else 0)
+        flops = 2 * rows * sum(ci * co for ci, co in zip([cin0] + cout[:-1], cout))
+        nbytes = rows * 4 + B * min(N, P * S) * (CF * 4 + (12 + E * 4 if has_xyz else 0)) + B * P * cout[-1] * 8
+        return nbytes, flops
     if name == "sad_shared_mlp_fwd":
         # fused stage: bytes = idx + distinct gathered rows (bf16) + outputs; flops = 2*rows*sum(Cin*Cout)
         B, N, P, S, C0, C1in, E, nl = v[0], v[1], v[2], v[3], v[5], v[7], v[15], v[16]
@@ -256,6 +268,7 @@ def call_cost(name, a):
     return 0, 0
 
 
+MLP_DTYPE = ["bf16"]
 MLP_REPEAT = 8      # fused-MLP launches are re-issued this many times inside one CUDA-event pair (same inputs, same outputs)
 
 
@@ -263,11 +276,13 @@ def build_roofline(model, xyz, feat, size, reps=3):
     import torch
     from sad_b200 import _lib
     peaks = measured_peaks()
+    if MLP_DTYPE[0] == "tf32":      # kind::tf32 runs at half the kind::f16 rate; only the bf16 peak is measured on this pool
+        peaks = dict(peaks, tensor=peaks["tensor"] / 2, src=peaks["src"] + " (bf16 sustained / 2 for tf32)")
     agg = {}
     stages = {}
     for _ in range(reps):
         with _lib.CallProfiler(repeat={"sad_sa_mlp_fwd": MLP_REPEAT, "sad_pw_mlp_fwd": MLP_REPEAT,
-                                       "sad_shared_mlp_fwd": MLP_REPEAT}) as prof:
+                                       "sad_shared_mlp_fwd": MLP_REPEAT, "sad_mlp_tf32_fwd": MLP_REPEAT}) as prof:
             with torch.no_grad():
                 torch.cuda._sleep(60000000)      # ~30 ms: every launch of the forward is queued before the first one runs
                 model(xyz, feat, size)
@@ -282,7 +297,7 @@ def build_roofline(model, xyz, feat, size, reps=3):
                 picks = int(a[2])
             d = agg.setdefault(key, {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0, "picks": picks})
             if flops:      # one row per fused-MLP launch, in call order (SA1..SA4, FP1, FP2, voting, aggregation)
-                sk = (name, tuple(x for x in a[:4] if isinstance(x, int)))
+                sk = (name, tuple(x for x in a[:11] if isinstance(x, int)))
                 st = stages.setdefault(sk, {"ms": 0.0, "flops": flops, "order": len(stages)})
                 st["ms"] += ms / reps
             d["ms"] += ms / reps
@@ -302,17 +317,20 @@ def build_roofline(model, xyz, feat, size, reps=3):
         kernels.append(row)
     # ---- headline: the fused gather + MLP + max-pool launches (tensor roofline).  They own the largest share of the
     # step's SM-time; the FPS chain is a serial-latency kernel and is reported in its honest unit below.
-    mlp_rows = [k for k in kernels if k["kernel"] in ("shared_mlp", "sa_mlp", "pw_mlp")]
+    mlp_rows = [k for k in kernels if k["kernel"] in ("shared_mlp", "sa_mlp", "pw_mlp", "mlp_tf32")]
     flops = sum(agg[k["kernel"]]["flops"] for k in mlp_rows)
     ms = sum(agg[k["kernel"]]["ms"] for k in mlp_rows)
     n_l = sum(agg[k["kernel"]]["launches"] for k in mlp_rows)
     tfs = flops / ms / 1e9 if ms > 0 else 0.0
     roof = {"bound": "tensor", "kernel": f"fused gather + shared MLP + max-pool ({n_l:.0f} launches per step: "
-                                         "SA1-SA4 + aggregation [sa_mlp_kernel], FP1/FP2/voting [pw_mlp_kernel])",
+                                         + ("SA1-SA4 + aggregation [sa_mlp_kernel], FP1/FP2/voting [pw_mlp_kernel])" if MLP_DTYPE[0] == "bf16"
+                                            else "mlp_tf32_kernel, fp32 activations, kind::tf32)"),
             "achieved": round(tfs, 1), "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": round(tfs / peaks["tensor"], 4),
             "traffic": None, "peak_source": peaks["src"], "alg_flops_per_launch": round(flops / max(1.0, n_l)),
             "launch_ms": round(ms / max(1.0, n_l), 4), "ms_per_step_all_launches": round(ms, 4),
-            "note": "bf16 operands, fp32 accumulate; peak = sustained cuBLAS bf16 (MEASURED_PEAKS.json); algorithmic flops = "
+            "note": ("bf16 operands, fp32 accumulate; peak = sustained cuBLAS bf16 (MEASURED_PEAKS.json)" if MLP_DTYPE[0] == "bf16"
+                     else "tf32 operands, fp32 accumulate; peak = half the sustained cuBLAS bf16 figure (MEASURED_PEAKS.json)")
+                    + "; algorithmic flops = "
                     "2 * rows * sum(Cin*Cout) with the real (unpadded) channel counts; device time by CUDA events, launches "
                     "queued behind a busy stream so no host gap is inside an event pair; each fused-MLP call is issued "
                     f"{MLP_REPEAT} times back to back inside its event pair (idempotent: same inputs and outputs) and the "
@@ -328,7 +346,7 @@ def build_roofline(model, xyz, feat, size, reps=3):
     for i, (sk, st) in enumerate(sorted(stages.items(), key=lambda kv: kv[1]["order"])):
         t = st["flops"] / st["ms"] / 1e9 if st["ms"] > 0 else 0.0
         roof["by_launch"].append({"stage": names[i] if i < len(names) else str(i), "entry": sk[0].replace("sad_", ""),
-                                  "dims": list(sk[1]), "us": round(1e3 * st["ms"], 1), "GFLOP": round(st["flops"] / 1e9, 2),
+                                  "dims": list(sk[1][:4]), "us": round(1e3 * st["ms"], 1), "GFLOP": round(st["flops"] / 1e9, 2),
                                   "TFLOPs": round(t, 1), "frac": round(t / peaks["tensor"], 4)})
     # ---- FPS in its own unit: dependent picks per second
     fps_rows = []
@@ -435,7 +453,8 @@ def run_ours(args):
     from sad_b200.scenes import make_scenes, make_sizes
 
     _lib.load()
-    model = SADHotPath(input_feature_dim=1).load_params(make_params(0)).to(dev).eval()
+    MLP_DTYPE[0] = args.mlp_dtype
+    model = SADHotPath(input_feature_dim=1, mlp_dtype=args.mlp_dtype).load_params(make_params(0)).to(dev).eval()
 
     # distinct scenes per rank and per rotating input set; the sets together exceed L2 (126 MB),
     # so no step finds its inputs cached from an earlier one
@@ -538,7 +557,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": args.mlp_dtype, "data": "synthetic",
             "config": workload_config(world),
             "run": {"l2": f"{NSETS} rotating input sets x {set_bytes / 1e6:.1f} MB = {NSETS * set_bytes / 1e6:.0f} MB "
                           "> 126 MB L2 (inputs larger than L2, no flush)",
@@ -552,7 +571,7 @@ def run_ours(args):
                                   "4-SM cluster per scene; identical indices)",
                     "batch_latency_loaded_ms": round(eng.slots * (total_ms / args.steps), 4),
                     "batch_latency_ms": round(lat[len(lat) // 2], 4),
-                    "search_dtype": "f32 (bit-exact indices)", "mlp_dtype": "bf16 in / f32 accumulate"},
+                    "search_dtype": "f32 (bit-exact indices)", "mlp_dtype": f"{args.mlp_dtype} in / f32 accumulate"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms / args.steps, 4), "checksum": round(checksum, 4)},
             "gpu_launches": int(eng.launches_per_batch * args.steps),
@@ -601,9 +620,15 @@ def main():
     ap.add_argument("--fps-policy", default="throughput", choices=["throughput", "throughput_paired", "latency"],
                     help="scheduling of the 40k-point FPS (same indices either way)")
     ap.add_argument("--sets", type=int, default=32, help="rotating input sets (32 x 5.1 MB > L2)")
+    ap.add_argument("--batch", type=int, default=8, help="scenes per GPU per step (default = configs[1]; other values = sweep points)")
+    ap.add_argument("--points", type=int, default=40000, help="points per scene (default = configs[1])")
+    ap.add_argument("--mlp-dtype", default="bf16", choices=["bf16", "tf32"],
+                    help="operand precision of the fused MLP stages (tf32: fp32 activations, csrc/mlp_tf32.cu)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-hbm", action="store_true", help="skip the hbm_kernels micro-benchmark block")
     args = ap.parse_args()
+    global B_PER_GPU, N_POINTS
+    B_PER_GPU, N_POINTS = args.batch, args.points
     # stdout carries exactly ONE JSON line: anything a library prints to fd 1 during the run (NCCL's version banner
     # under NCCL_DEBUG=VERSION, for one) is sent to stderr, and the line is written to the original stdout
     global _RESULT_FD

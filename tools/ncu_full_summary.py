@@ -35,6 +35,14 @@ def key_of(name, grid, block):
     n = name
     if "fused_mlp" in n:
         return "shared_mlp"
+    if "sa_mlp_kernel" in n:
+        return "sa_mlp"
+    if "pw_mlp_kernel" in n:
+        return "pw_mlp"
+    if "mlp_tf32" in n:
+        return "mlp_tf32"
+    if "interp_fwd" in n:
+        return "three_interpolate"
     if "fps_cull" in n:
         return "furthest_point_sample_grid"
     if "fps_kernel" in n:
@@ -88,7 +96,8 @@ def main():
     rows = []
     for rep in reps:
         rows += rows_of(rep)
-    json.dump({"note": "one row per profiled launch of `python tools/profile_step.py` (B=8 x 40k step); ncu --set full "
+    json.dump({"note": "one row per profiled launch (tools/ncu_target.py: the fused-MLP kernels at the benchmark's shapes, "
+                       "B = 8 x 40k surface scenes; tf32 SA2; three_interpolate at the FP2 shape, B = 256); ncu --set full "
                        "--clock-control none; times are cold-cache and serialised",
                "kernels": rows}, open(out, "w"), indent=1)
     for d in rows:

@@ -44,5 +44,15 @@ for _ in range(reps):
 mv = layers([256, 256, 256, 259])
 for _ in range(reps):
     vx, vf = M.vote_mlp_fast(x2, fp, mv)
+# tf32 mode of the SA2 stage, and the drop-in three_interpolate at the FP2 shape with B = 256 (working set > L2)
+m2t = M.prepare_layers(m2.layers, dtype="tf32")
+for _ in range(reps):
+    M.sa_group_mlp(x1, x2, f1, idx2, 0.4, m2t)
+Bi, n, m = 256, 1024, 512
+u, k = torch.rand(Bi, n, 3, device=dev) * 6, torch.rand(Bi, m, 3, device=dev) * 6
+_, ii, ww = ops.three_nn_weights(u, k)
+ff = torch.randn(Bi, 256, m, device=dev)
+for _ in range(reps):
+    ops.three_interpolate(ff, ii, ww)
 torch.cuda.synchronize()
 print("ok")
