@@ -12,7 +12,7 @@ or calling them on CPU tensors, raises.
 from . import _lib  # noqa: F401
 from .ops import (  # noqa: F401
     furthest_point_sample, gather_operation, ball_query, ball_query_adaptive,
-    grouping_operation, three_nn, three_interpolate, size_to_radius,
+    grouping_operation, three_nn, three_interpolate, size_to_radius, set_deterministic,
     FurthestPointSampling, GatherOperation, BallQuery, BallQueryAdaptive,
     GroupingOperation, ThreeNN, ThreeInterpolate,
 )

@@ -51,6 +51,10 @@ SIGNATURES = {
     "sad_pack_xyzw": [_c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_sa_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_float, _vp, _c_int, _vp, _c_int, _vp, _vp,
                        _c_int, _vp, _vp, _vp, _c_int, _vp],
+    "sad_scatter_plan_build": [_c_int, _c_int, ctypes.c_longlong, _vp, _vp, _vp, _vp],
+    "sad_interp_plan_build": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
+    "sad_scatter_add_det": [_c_int, _c_int, _c_int, ctypes.c_longlong, _vp, _vp, _vp, _vp, _vp],
+    "sad_three_interpolate_bwd_det": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp],
     "sad_mlp_tf32_image_bytes": [_c_int, _c_int, _c_int],
     "sad_mlp_tf32_pack": [_vp, _c_int, _c_int, _c_int, _vp],
     "sad_mlp_tf32_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _c_float, _vp,

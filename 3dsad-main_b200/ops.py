@@ -92,6 +92,33 @@ def build_scene_grid(xyz: torch.Tensor) -> SceneGrid:
 # Scenes at least this large get a scene grid built on the fly by furthest_point_sample / ball_query
 # when the caller passes none (the build costs one short kernel; below it the plain kernels win).
 GRID_MIN_POINTS = 8192
+
+# Backward of gather / grouping / three_interpolate: False = fp32 atomics (fastest; the summation order, hence the last
+# bits, vary from run to run), True = sort-by-destination plan + sequential per-destination sums (csrc/scatter.cu):
+# reproducible bit for bit and equal to the oracle's index-order accumulation.
+DETERMINISTIC = [False]
+
+
+def set_deterministic(on: bool = True) -> bool:
+    """Switch the scatter-add backward kernels to the deterministic mode; returns the previous setting."""
+    prev = DETERMINISTIC[0]
+    DETERMINISTIC[0] = bool(on)
+    return prev
+
+
+def _scatter_add_det(grad_out3, idx2, N):
+    """grad_out3 (B,C,PS) f32, idx2 (B,PS) i32 -> (B,C,N) f32, deterministic."""
+    B, C, PS = grad_out3.shape
+    dev = grad_out3.device
+    order = torch.empty((B, max(PS, 1)), dtype=torch.int32, device=dev)
+    offsets = torch.empty((B, N + 1), dtype=torch.int32, device=dev)
+    g = torch.empty((B, C, N), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.sad_scatter_plan_build(B, N, PS, _p(idx2), _p(order), _p(offsets), _stream(grad_out3)), "scatter_plan_build")
+        _lib.check(lib.sad_scatter_add_det(B, C, N, PS, _p(grad_out3), _p(order), _p(offsets), _p(g), _stream(grad_out3)),
+                   "scatter_add_det")
+    return g
 FPS_POLICIES = {"latency": 0, "throughput": 1, "throughput_paired": 2}   # include/sad_ops.h SAD_FPS_*
 
 
@@ -171,6 +198,8 @@ class GatherOperation(Function):
         (idx,) = ctx.saved_tensors
         grad_out = grad_out.contiguous()
         B, C, npoint = grad_out.shape
+        if DETERMINISTIC[0]:
+            return _scatter_add_det(grad_out, idx, ctx.N), None
         g = torch.empty((B, C, ctx.N), dtype=torch.float32, device=grad_out.device)
         with torch.cuda.device(grad_out.device):
             _lib.check(_lib.load().sad_gather_operation_bwd(B, C, ctx.N, npoint, _p(grad_out), _p(idx), _p(g),
@@ -277,6 +306,8 @@ class GroupingOperation(Function):
         (idx,) = ctx.saved_tensors
         grad_out = grad_out.contiguous()
         B, C, npoint, nsample = grad_out.shape
+        if DETERMINISTIC[0]:
+            return _scatter_add_det(grad_out.view(B, C, npoint * nsample), idx.view(B, npoint * nsample), ctx.N), None
         g = torch.empty((B, C, ctx.N), dtype=torch.float32, device=grad_out.device)
         with torch.cuda.device(grad_out.device):
             _lib.check(_lib.load().sad_grouping_operation_bwd(B, C, ctx.N, npoint, nsample, _p(grad_out), _p(idx),
@@ -340,6 +371,16 @@ class ThreeInterpolate(Function):
         grad_out = grad_out.contiguous()
         B, C, n = grad_out.shape
         g = torch.empty((B, C, ctx.m), dtype=torch.float32, device=grad_out.device)
+        if DETERMINISTIC[0]:
+            order = torch.empty((B, max(3 * n, 1)), dtype=torch.int32, device=grad_out.device)
+            offsets = torch.empty((B, ctx.m + 1), dtype=torch.int32, device=grad_out.device)
+            lib = _lib.load()
+            with torch.cuda.device(grad_out.device):
+                _lib.check(lib.sad_interp_plan_build(B, n, ctx.m, _p(idx), _p(order), _p(offsets), _stream(grad_out)),
+                           "interp_plan_build")
+                _lib.check(lib.sad_three_interpolate_bwd_det(B, C, n, ctx.m, _p(grad_out), _p(weight), _p(order), _p(offsets),
+                                                             _p(g), _stream(grad_out)), "three_interpolate_bwd_det")
+            return g, None, None
         with torch.cuda.device(grad_out.device):
             _lib.check(_lib.load().sad_three_interpolate_bwd(B, C, n, ctx.m, _p(grad_out), _p(idx), _p(weight),
                                                              _p(g), _stream(grad_out)), "three_interpolate_bwd")

@@ -228,6 +228,25 @@ SAD_API int sad_pw_mlp_fwd(int kind, int B, int n, int m, const void* src_cl, co
                            const float* bias_last_padded, int c_last, float* out_cf, void* out_cl, const float* seed_xyz,
                            const float* seed_cf, float* vote_xyz, int tiles_per_cta, sad_stream_t stream);
 
+/* ---- a2 / a5 / a9 backward, deterministic mode (csrc/scatter.cu).  The default *_bwd entry points scatter
+ * with fp32 atomics (summation order varies from run to run).  These turn the scatter into a gather with a fixed order:
+ *   sad_scatter_plan_build  idx (B,PS) destinations in [0,N) -> order (B,PS), offsets (B,N+1): the source positions of
+ *                           every destination, ascending (stable counting sort; out-of-range indices are skipped);
+ *   sad_interp_plan_build   the same for three_interpolate's idx (B,n,3) over m destinations, position key t*n + i;
+ *   sad_scatter_add_det     grad_features (B,C,N) = per destination the sequential fp32 sum of grad_out (B,C,PS) over
+ *                           its segment (grouping: PS = npoint*nsample; gather: PS = npoint); no memset needed;
+ *   sad_three_interpolate_bwd_det  ... of grad_out[b,c,i] * weight[b,i,t].
+ * Results are reproducible bit for bit and equal the oracle's index-order accumulation. */
+SAD_API int sad_scatter_plan_build(int B, int N, long long PS, const int32_t* idx, int32_t* order, int32_t* offsets,
+                                   sad_stream_t stream);
+SAD_API int sad_interp_plan_build(int B, int n, int m, const int32_t* idx, int32_t* order, int32_t* offsets,
+                                  sad_stream_t stream);
+SAD_API int sad_scatter_add_det(int B, int C, int N, long long PS, const float* grad_out, const int32_t* order,
+                                const int32_t* offsets, float* grad_features, sad_stream_t stream);
+SAD_API int sad_three_interpolate_bwd_det(int B, int C, int n, int m, const float* grad_out, const float* weight,
+                                          const int32_t* order, const int32_t* offsets, float* grad_features,
+                                          sad_stream_t stream);
+
 /* ---- a6, tf32 mode (csrc/mlp_tf32.cu): the same fused stage with fp32 channel-last activations and kind::tf32 MMAs
  * (north_star "tcgen05 bf16/tf32 GEMM"); 1e-3-class agreement with the fp32 oracle instead of the bf16 path's 2e-2.
  * Layer-1 operand, K order [interp | feat | special]:

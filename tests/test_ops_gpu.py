@@ -289,3 +289,71 @@ def test_glue_kernels_match_their_torch_expressions():
     for (alpha, lo, hi) in ((1.0, 0.1, 1.2), (0.7, 0.05, 0.9)):
         r = ops.size_to_radius(cu(size), alpha, lo, hi)
         assert np.array_equal(r.cpu().numpy(), O.size_to_radius(size, alpha, lo, hi))
+
+
+# ----------------------------------------------------------------------------- deterministic scatter-add
+@pytest.fixture
+def deterministic(ops):
+    prev = ops.set_deterministic(True)
+    yield ops
+    ops.set_deterministic(prev)
+
+
+@pytest.mark.parametrize("B,C_,N,P,S_", [(2, 19, 500, 64, 16), (1, 4, 20000, 2048, 64), (3, 64, 1024, 333, 8),
+                                          (1, 3, 60000, 128, 32),       # N beyond the shared-memory cursor array
+                                          (1, 5, 16, 200, 64)])         # every destination hit hundreds of times
+def test_deterministic_grouping_backward_is_bit_exact(deterministic, B, C_, N, P, S_):
+    """The sort-by-destination backward adds each destination's addends in ascending source position -- the order of the
+    oracle's np.add.at -- so it equals the oracle bit for bit and itself from run to run; the atomic kernel only agrees
+    to rounding."""
+    ops = deterministic
+    rng = np.random.default_rng(N + P)
+    idx = rng.integers(0, N, (B, P, S_)).astype(np.int32)
+    idx[:, :, S_ // 2:] = idx[:, :, :1]                    # first-hit padding: heavy duplication inside a ball
+    go = rng.standard_normal((B, C_, P, S_)).astype(np.float32)
+    want = O.grouping_operation_grad(go, idx, N)
+    f = torch.zeros(B, C_, N, device=DEV, requires_grad=True)
+    runs = []
+    for _ in range(3):
+        f.grad = None
+        ops.grouping_operation(f, cu(idx)).backward(cu(go))
+        runs.append(f.grad.cpu().numpy().copy())
+    assert np.array_equal(runs[0], want)
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+    # gather_operation shares the kernels
+    gi = rng.integers(0, N, (B, P)).astype(np.int32)
+    go2 = rng.standard_normal((B, C_, P)).astype(np.float32)
+    f.grad = None
+    ops.gather_operation(f, cu(gi)).backward(cu(go2))
+    assert np.array_equal(f.grad.cpu().numpy(), O.gather_operation_grad(go2, gi, N))
+
+
+@pytest.mark.parametrize("B,C_,m,n", [(2, 5, 40, 333), (2, 256, 256, 512), (1, 70, 3, 1000), (1, 8, 512, 1024)])
+def test_deterministic_three_interpolate_backward_is_bit_exact(deterministic, B, C_, m, n):
+    ops = deterministic
+    rng = np.random.default_rng(m + n)
+    f = cu(rng.standard_normal((B, C_, m)).astype(np.float32)).requires_grad_(True)
+    idx = rng.integers(0, m, (B, n, 3)).astype(np.int32)
+    w = O.interpolation_weights(rng.random((B, n, 3), dtype=np.float32))
+    go = rng.standard_normal((B, C_, n)).astype(np.float32)
+    want = O.three_interpolate_grad(go, idx, w, m)
+    for _ in range(2):
+        f.grad = None
+        ops.three_interpolate(f, cu(idx), cu(w)).backward(cu(go))
+        assert np.array_equal(f.grad.cpu().numpy(), want)
+
+
+def test_scatter_plan_skips_out_of_range_indices(ops):
+    """indices outside [0, N) never reach memory in the deterministic path; they are dropped from the plan."""
+    import ctypes
+    from sad_b200 import _lib
+    lib = _lib.load()
+    vp = ctypes.c_void_p
+    B, N, PS = 1, 10, 64
+    idx = torch.arange(PS, dtype=torch.int32, device=DEV).view(B, PS) - 20          # -20 .. 43: 10 valid
+    order = torch.full((B, PS), -7, dtype=torch.int32, device=DEV)
+    offsets = torch.empty((B, N + 1), dtype=torch.int32, device=DEV)
+    st = vp(torch.cuda.current_stream().cuda_stream)
+    assert lib.sad_scatter_plan_build(B, N, PS, vp(idx.data_ptr()), vp(order.data_ptr()), vp(offsets.data_ptr()), st) == 0
+    assert offsets.cpu().tolist() == [list(range(11))]
+    assert order[0, :10].cpu().tolist() == list(range(20, 30)) and int((order[0, 10:] != -7).sum()) == 0

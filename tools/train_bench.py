@@ -27,7 +27,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--amp", action="store_true", help="bf16 autocast around the point-wise MLPs")
+    ap.add_argument("--deterministic", action="store_true",
+                    help="sort-by-destination scatter-add backward (csrc/scatter.cu) instead of fp32 atomics")
     a = ap.parse_args()
+    from sad_b200 import dist as D, ops as _ops
+    _ops.set_deterministic(a.deterministic)
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
@@ -38,8 +42,9 @@ def main():
     model = SADHotPath(1).load_params(make_params(0)).to(dev).train()
     net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True) if world > 1 else model
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9)
-    xyz, feat = make_scenes(a.B, a.N, "surface", first_scene=rank * a.B)
-    size = make_sizes(a.B, LAYER_CFG["agg"][0], first_scene=rank * a.B)
+    first = D.weak_scaling_first_scene(rank, a.B)
+    xyz, feat = make_scenes(a.B, a.N, "surface", first_scene=first)
+    size = make_sizes(a.B, LAYER_CFG["agg"][0], first_scene=first)
     x, f, s = (torch.from_numpy(t).to(dev) for t in (xyz, feat, size))
     n_param = sum(p.numel() for p in model.parameters())
 
@@ -56,17 +61,14 @@ def main():
     for _ in range(a.warmup):
         loss = step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    D.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
         loss = step()
     e1.record()
     torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    (ms,) = D.reduce_scalars([e0.elapsed_time(e1)], "max", device=dev)
     if rank == 0:
         per = float(ms) / a.steps
         print(json.dumps({"config": "configs[3]: forward+backward+SGD step, DDP (NCCL gradient all-reduce)",
@@ -74,9 +76,10 @@ def main():
                           "ms_per_step": round(per, 3), "train_scenes_per_s": round(world * a.B / per * 1e3, 1),
                           "mlp_dtype": "bf16 autocast" if a.amp else "f32 (TF32 off)",
                           "allreduce_bytes_per_step": 4 * n_param if world > 1 else 0,
+                          "scatter_add_backward": "deterministic (sorted segments)" if a.deterministic else "fp32 atomics",
                           "final_loss": float(loss.detach())}), flush=True)
+    D.barrier()
     if world > 1:
-        dist.barrier()
         dist.destroy_process_group()
 
 
