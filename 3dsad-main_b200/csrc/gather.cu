@@ -19,6 +19,14 @@
 namespace {
 
 constexpr int GR_T = 256;
+// Indices are untrusted input: forward gathers clamp them into [0, N) (one unsigned min; a negative index becomes N - 1),
+// backward scatters skip anything outside -- no out-of-bounds access either way.
+__device__ __forceinline__ int clamp_idx(int i, int N) { return (int)min((unsigned)i, (unsigned)(N - 1)); }
+__device__ __forceinline__ int4 clamp_idx4(int4 i, int N) {
+  return make_int4(clamp_idx(i.x, N), clamp_idx(i.y, N), clamp_idx(i.z, N), clamp_idx(i.w, N));
+}
+__device__ __forceinline__ bool idx_ok(int i, int N) { return (unsigned)i < (unsigned)N; }
+
 constexpr int GR_CCH = 16;   // channels per thread (grid.y splits the rest)
 
 template <bool VEC>
@@ -32,7 +40,7 @@ group_fwd_kernel(int C, int N, long long PS, const float* __restrict__ features,
   const float* f = features + ((size_t)b * C + c0) * N;
   if (VEC) {
     if (t * 4 >= PS) return;
-    const int4 id = __ldg(reinterpret_cast<const int4*>(idx + (size_t)b * PS) + t);
+    const int4 id = clamp_idx4(__ldg(reinterpret_cast<const int4*>(idx + (size_t)b * PS) + t), N);
     float* o = out + ((size_t)b * C + c0) * PS + t * 4;
     int c = 0;
     for (; c + 4 <= cn; c += 4) {
@@ -52,7 +60,7 @@ group_fwd_kernel(int C, int N, long long PS, const float* __restrict__ features,
     }
   } else {
     if (t >= PS) return;
-    const int id = __ldg(idx + (size_t)b * PS + t);
+    const int id = clamp_idx(__ldg(idx + (size_t)b * PS + t), N);
     float* o = out + ((size_t)b * C + c0) * PS + t;
 #pragma unroll 4
     for (int c = 0; c < cn; ++c) __stcs(o + (size_t)c * PS, __ldg(f + (size_t)c * N + id));
@@ -82,11 +90,11 @@ group_fwd_staged_kernel(int C, int N, long long quads, int cch, const float* __r
   const int4* ip = reinterpret_cast<const int4*>(idx) + (size_t)b * quads;
   float4* op = reinterpret_cast<float4*>(out) + ((size_t)b * C + c0) * quads;
   long long q = q0 + threadIdx.x;
-  int4 id = (q < q1) ? __ldg(ip + q) : make_int4(0, 0, 0, 0);
+  int4 id = (q < q1) ? clamp_idx4(__ldg(ip + q), N) : make_int4(0, 0, 0, 0);
   mbar_wait(&s_bar, 0);
   for (; q < q1; q += GR_T) {
     const long long qn = q + GR_T;
-    const int4 nxt = (qn < q1) ? __ldg(ip + qn) : make_int4(0, 0, 0, 0);      // next indices while this quad gathers
+    const int4 nxt = (qn < q1) ? clamp_idx4(__ldg(ip + qn), N) : make_int4(0, 0, 0, 0);      // next indices while this quad gathers
 #pragma unroll 4
     for (int c = 0; c < cn; ++c) {
       const float* r = s_rows + (size_t)c * N;
@@ -113,14 +121,15 @@ group_bwd_kernel(int C, int N, long long PS, const float* __restrict__ grad_out,
     for (int c = 0; c < cn; ++c) {
       const float4 v = __ldcs(reinterpret_cast<const float4*>(go + (size_t)c * PS));
       float* gc = g + (size_t)c * N;
-      atomicAdd(gc + id.x, v.x);
-      atomicAdd(gc + id.y, v.y);
-      atomicAdd(gc + id.z, v.z);
-      atomicAdd(gc + id.w, v.w);
+      if (idx_ok(id.x, N)) atomicAdd(gc + id.x, v.x);
+      if (idx_ok(id.y, N)) atomicAdd(gc + id.y, v.y);
+      if (idx_ok(id.z, N)) atomicAdd(gc + id.z, v.z);
+      if (idx_ok(id.w, N)) atomicAdd(gc + id.w, v.w);
     }
   } else {
     if (t >= PS) return;
     const int id = __ldg(idx + (size_t)b * PS + t);
+    if (!idx_ok(id, N)) return;
     const float* go = grad_out + ((size_t)b * C + c0) * PS + t;
 #pragma unroll 4
     for (int c = 0; c < cn; ++c) atomicAdd(g + (size_t)c * N + id, __ldcs(go + (size_t)c * PS));

@@ -16,6 +16,9 @@ namespace {
 constexpr int TI_T = 128;
 constexpr int TI_CCH = 16;
 
+// untrusted indices: forward gathers clamp into [0, m), the backward scatter skips anything outside
+__device__ __forceinline__ int clamp_idx(int i, int m) { return (int)min((unsigned)i, (unsigned)(m - 1)); }
+
 __device__ __forceinline__ float interp3(float w0, float f0, float w1, float f1, float w2, float f2) {
   return __fadd_rn(__fadd_rn(__fmul_rn(w0, f0), __fmul_rn(w1, f1)), __fmul_rn(w2, f2));
 }
@@ -39,7 +42,7 @@ interp_fwd_kernel(int C, int m, int n, const float* __restrict__ features, const
     for (int u = 0; u < 3; ++u) {
       const int4 a = __ldg(ip + u);
       const float4 ww = __ldg(wp + u);
-      id[4 * u] = a.x; id[4 * u + 1] = a.y; id[4 * u + 2] = a.z; id[4 * u + 3] = a.w;
+      id[4 * u] = clamp_idx(a.x, m); id[4 * u + 1] = clamp_idx(a.y, m); id[4 * u + 2] = clamp_idx(a.z, m); id[4 * u + 3] = clamp_idx(a.w, m);
       w[4 * u] = ww.x; w[4 * u + 1] = ww.y; w[4 * u + 2] = ww.z; w[4 * u + 3] = ww.w;
     }
     float* o = out + ((size_t)b * C + c0) * n + (size_t)t * 4;
@@ -60,7 +63,7 @@ interp_fwd_kernel(int C, int m, int n, const float* __restrict__ features, const
     if (t >= n) return;
     const int32_t* ip = idx + ((size_t)b * n + t) * 3;
     const float* wp = weight + ((size_t)b * n + t) * 3;
-    const int i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+    const int i0 = clamp_idx(__ldg(ip), m), i1 = clamp_idx(__ldg(ip + 1), m), i2 = clamp_idx(__ldg(ip + 2), m);
     const float w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
     float* o = out + ((size_t)b * C + c0) * n + t;
 #pragma unroll 4
@@ -107,7 +110,7 @@ interp_fwd_staged_kernel(int C, int m, int quads, int cch, const float* __restri
     for (int u = 0; u < 3; ++u) {
       const int4 a = __ldg(ipb + (size_t)q * 3 + u);
       const float4 ww = __ldg(wpb + (size_t)q * 3 + u);
-      id[4 * u] = a.x; id[4 * u + 1] = a.y; id[4 * u + 2] = a.z; id[4 * u + 3] = a.w;
+      id[4 * u] = clamp_idx(a.x, m); id[4 * u + 1] = clamp_idx(a.y, m); id[4 * u + 2] = clamp_idx(a.z, m); id[4 * u + 3] = clamp_idx(a.w, m);
       w[4 * u] = ww.x; w[4 * u + 1] = ww.y; w[4 * u + 2] = ww.z; w[4 * u + 3] = ww.w;
     }
     if (!waited) {
@@ -191,7 +194,7 @@ interp_fwd_pm_kernel(int C, int m, int n, int groups_per_cta, const float* __res
         for (int e = 0; e < 3; ++e) {
           const int4 a = __ldg(ib + (size_t)(i4 >> 2) * 3 + e);
           const float4 ww = __ldg(wb + (size_t)(i4 >> 2) * 3 + e);
-          id[4 * e] = a.x; id[4 * e + 1] = a.y; id[4 * e + 2] = a.z; id[4 * e + 3] = a.w;
+          id[4 * e] = clamp_idx(a.x, m); id[4 * e + 1] = clamp_idx(a.y, m); id[4 * e + 2] = clamp_idx(a.z, m); id[4 * e + 3] = clamp_idx(a.w, m);
           w[4 * e] = ww.x; w[4 * e + 1] = ww.y; w[4 * e + 2] = ww.z; w[4 * e + 3] = ww.w;
         }
       }
@@ -301,7 +304,7 @@ interp_fwd_pipe_kernel(int B, int C, int m, int n, int ychunks, const float* __r
           for (int e = 0; e < 3; ++e) {
             const int4 a = __ldg(ib + (size_t)(i4 >> 2) * 3 + e);
             const float4 ww = __ldg(wb + (size_t)(i4 >> 2) * 3 + e);
-            id[4 * e] = a.x; id[4 * e + 1] = a.y; id[4 * e + 2] = a.z; id[4 * e + 3] = a.w;
+            id[4 * e] = clamp_idx(a.x, m); id[4 * e + 1] = clamp_idx(a.y, m); id[4 * e + 2] = clamp_idx(a.z, m); id[4 * e + 3] = clamp_idx(a.w, m);
             wt[4 * e] = ww.x; wt[4 * e + 1] = ww.y; wt[4 * e + 2] = ww.z; wt[4 * e + 3] = ww.w;
           }
         }
@@ -355,9 +358,9 @@ interp_bwd_kernel(int C, int n, int m, const float* __restrict__ grad_out, const
   for (int c = 0; c < cn; ++c) {
     const float v = __ldcs(go + (size_t)c * n);
     float* gc = g + (size_t)c * m;
-    atomicAdd(gc + i0, __fmul_rn(v, w0));
-    atomicAdd(gc + i1, __fmul_rn(v, w1));
-    atomicAdd(gc + i2, __fmul_rn(v, w2));
+    if ((unsigned)i0 < (unsigned)m) atomicAdd(gc + i0, __fmul_rn(v, w0));
+    if ((unsigned)i1 < (unsigned)m) atomicAdd(gc + i1, __fmul_rn(v, w1));
+    if ((unsigned)i2 < (unsigned)m) atomicAdd(gc + i2, __fmul_rn(v, w2));
   }
 }
 

@@ -288,7 +288,7 @@ def to_cl_f32(features_cf: torch.Tensor) -> torch.Tensor:
     """(B,C,N) f32 -> (B,N,C4) f32 channel-last, C padded to a multiple of 4; the twin a tf32 stage left on its
     output is used when present."""
     twin = getattr(features_cf, "_sad_cl32", None)
-    if twin is not None:
+    if twin is not None and getattr(features_cf, "_sad_cl_v", None) == features_cf._version:
         return twin
     B, C, N = features_cf.shape
     c4 = (C + 3) // 4 * 4
@@ -350,6 +350,7 @@ def _packed_tf32(mlp: PreparedMLP, ci: int, ci_real: int, cf: int, cf_real: int,
 
 def _attach32(cf: torch.Tensor, cl: torch.Tensor):
     cf._sad_cl32 = cl
+    cf._sad_cl_v = cf._version
     return cf
 
 
@@ -413,8 +414,8 @@ def to_cl_bf16(features_cf: torch.Tensor, pad_to: Optional[int] = None) -> torch
     """(B,C,N) f32 -> (B,N,Cpad) bf16 channel-last; reuses the `_sad_cl` twin when present."""
     B, C, N = features_cf.shape
     cpad = pad_to or C
-    twin = getattr(features_cf, "_sad_cl", None)
-    if twin is not None and tuple(twin.shape) == (B, N, cpad):
+    twin = getattr(features_cf, "_sad_cl", None)      # valid while the f32 tensor has not been written in place since
+    if twin is not None and tuple(twin.shape) == (B, N, cpad) and getattr(features_cf, "_sad_cl_v", None) == features_cf._version:
         return twin
     x = features_cf.contiguous()
     if x.dtype != torch.float32:
@@ -432,6 +433,7 @@ def to_cl_bf16(features_cf: torch.Tensor, pad_to: Optional[int] = None) -> torch
 def _attach(cf: Optional[torch.Tensor], cl: Optional[torch.Tensor]):
     if cf is not None and cl is not None:
         cf._sad_cl = cl
+        cf._sad_cl_v = cf._version
     return cf
 
 

@@ -65,11 +65,12 @@ class SceneGrid:
     cell offsets.  Built once per coordinate tensor and shared by the culled FPS and the grid ball
     query over the same `xyz`; results of both are bit-identical to the plain kernels."""
 
-    __slots__ = ("xyz", "B", "N", "workspace")
+    __slots__ = ("xyz", "B", "N", "workspace", "version")
 
     def __init__(self, xyz: torch.Tensor):
         _req(xyz, "xyz", torch.float32, 3, 3)
         self.xyz, (self.B, self.N) = xyz, xyz.shape[:2]
+        self.version = xyz._version
         lib = _lib.load()
         nbytes = int(lib.sad_scene_grid_workspace_bytes(self.B, self.N))
         if nbytes < 0:
@@ -80,8 +81,14 @@ class SceneGrid:
                        "scene_grid_build")
 
     def check(self, xyz: torch.Tensor):
+        """The grid holds its own sorted copy of the coordinates: it is valid for the tensor it was built from, as long
+        as that tensor has not been written since (in-place updates bump `_version`).  A grid is single-stream: the
+        culled FPS kernels keep their min-distance scratch in its workspace."""
         if xyz.data_ptr() != self.xyz.data_ptr() or tuple(xyz.shape) != tuple(self.xyz.shape):
             raise ValueError("SceneGrid was built for a different xyz tensor")
+        if xyz._version != self.version:
+            raise ValueError("SceneGrid is stale: xyz was modified in place after the grid was built (rebuild it with "
+                             "build_scene_grid)")
         return self
 
 

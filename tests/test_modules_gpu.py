@@ -150,3 +150,20 @@ def test_size_head_drives_the_adaptive_radius():
     assert np.array_equal(got["cluster_xyz"].cpu().numpy(), cxyz)
     close(got["cluster_features"], cfeat)
     assert float(rt.min()) < float(rt.max())                          # radii spread inside the clamp range
+
+
+def test_channel_last_twin_is_dropped_after_an_in_place_edit():
+    """a fused stage leaves a bf16 channel-last twin on its f32 output for the next stage; editing the f32
+    tensor in place must invalidate it."""
+    from sad_b200 import mlp as M
+    torch.manual_seed(1)
+    layers = [(torch.randn(64, 64, device=DEV) / 8, torch.zeros(64, device=DEV)) for _ in range(2)]
+    mlp = M.prepare_layers(layers)
+    x = torch.randn(2, 64, 256, device=DEV)
+    y = M.pointwise_mlp(x, mlp)
+    assert M.to_cl_bf16(y) is y._sad_cl
+    z0 = M.pointwise_mlp(y, mlp).clone()
+    y.mul_(2.0)
+    assert M.to_cl_bf16(y) is not y._sad_cl
+    z1 = M.pointwise_mlp(y, mlp)
+    assert not torch.allclose(z0, z1)

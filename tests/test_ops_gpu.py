@@ -357,3 +357,51 @@ def test_scatter_plan_skips_out_of_range_indices(ops):
     assert lib.sad_scatter_plan_build(B, N, PS, vp(idx.data_ptr()), vp(order.data_ptr()), vp(offsets.data_ptr()), st) == 0
     assert offsets.cpu().tolist() == [list(range(11))]
     assert order[0, :10].cpu().tolist() == list(range(20, 30)) and int((order[0, 10:] != -7).sum()) == 0
+
+
+def test_out_of_range_indices_never_touch_memory_out_of_bounds(ops):
+    """user-supplied idx is untrusted.  Forward gathers clamp into [0, N) (negative -> N - 1), backward
+    scatters skip; the in-range part of the result is unaffected."""
+    rng = np.random.default_rng(0)
+    B, C_, N, P, S_ = 2, 20, 300, 64, 16
+    f = rng.standard_normal((B, C_, N)).astype(np.float32)
+    idx = rng.integers(0, N, (B, P, S_)).astype(np.int32)
+    bad = idx.copy()
+    bad[0, 0, 0], bad[1, 3, 5], bad[1, 7, 1] = N, -5, 2 ** 31 - 1
+    ref = idx.copy()
+    ref[0, 0, 0], ref[1, 3, 5], ref[1, 7, 1] = N - 1, N - 1, N - 1
+    ft = cu(f).requires_grad_(True)
+    out = ops.grouping_operation(ft, cu(bad))
+    assert np.array_equal(out.detach().cpu().numpy(), O.grouping_operation(f, ref))
+    go = rng.standard_normal((B, C_, P, S_)).astype(np.float32)
+    out.backward(cu(go))
+    go_ref = go.copy()
+    go_ref[0, :, 0, 0] = 0
+    go_ref[1, :, 3, 5] = 0
+    go_ref[1, :, 7, 1] = 0
+    want = O.grouping_operation_grad(go_ref, idx, N)
+    np.testing.assert_allclose(ft.grad.cpu().numpy(), want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+    # three_interpolate: same policy
+    m, n = 40, 256
+    kf = rng.standard_normal((B, C_, m)).astype(np.float32)
+    ii = rng.integers(0, m, (B, n, 3)).astype(np.int32)
+    w = O.interpolation_weights(rng.random((B, n, 3), dtype=np.float32))
+    ib = ii.copy()
+    ib[0, 0, 0], ib[1, 9, 2] = m + 7, -1
+    ir = ii.copy()
+    ir[0, 0, 0], ir[1, 9, 2] = m - 1, m - 1
+    kt = cu(kf).requires_grad_(True)
+    o2 = ops.three_interpolate(kt, cu(ib), cu(w))
+    assert np.array_equal(o2.detach().cpu().numpy(), O.three_interpolate(kf, ir, w))
+    o2.backward(torch.ones_like(o2))
+    assert torch.isfinite(kt.grad).all()
+
+
+def test_scene_grid_goes_stale_when_xyz_is_written_in_place(ops):
+    from sad_b200 import ops as _ops
+    xyz = torch.rand(1, 9000, 3, device=DEV) * 4
+    grid = _ops.build_scene_grid(xyz)
+    _ops.furthest_point_sample(xyz, 64, grid)
+    xyz.mul_(0.5)
+    with pytest.raises(ValueError, match="stale"):
+        _ops.furthest_point_sample(xyz, 64, grid)
