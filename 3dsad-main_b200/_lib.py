@@ -51,6 +51,9 @@ SIGNATURES = {
     "sad_pack_xyzw": [_c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_sa_mlp_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_float, _vp, _c_int, _vp, _c_int, _vp, _vp,
                        _c_int, _vp, _vp, _vp, _c_int, _vp],
+    "sad_sa_mlp_dedup_workspace_bytes": [_c_int, _c_int],
+    "sad_sa_mlp_dedup_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_float, _vp, _c_int, _vp, _c_int, _vp, _vp,
+                             _c_int, _vp, _vp, _vp, _vp, _c_int, _vp],
     "sad_scatter_plan_build": [_c_int, _c_int, ctypes.c_longlong, _vp, _vp, _vp, _vp],
     "sad_interp_plan_build": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_scatter_add_det": [_c_int, _c_int, _c_int, ctypes.c_longlong, _vp, _vp, _vp, _vp, _vp],
@@ -69,7 +72,7 @@ SIGNATURES = {
 _RESTYPES = {"sad_last_error_string": ctypes.c_char_p,
              "sad_launch_count": ctypes.c_ulonglong, "sad_scene_grid_workspace_bytes": ctypes.c_longlong, "sad_mlp_weight_image_bytes": ctypes.c_longlong,
              "sad_sa_mlp_image_bytes": ctypes.c_longlong, "sad_pw_mlp_image_bytes": ctypes.c_longlong,
-             "sad_mlp_tf32_image_bytes": ctypes.c_longlong}
+             "sad_mlp_tf32_image_bytes": ctypes.c_longlong, "sad_sa_mlp_dedup_workspace_bytes": ctypes.c_longlong}
 
 class MlpOpts(ctypes.Structure):
     """include/sad_ops.h sad_mlp_opts"""

@@ -99,6 +99,14 @@ struct SaParams {
   int c3_real;                    // channels actually stored
   __nv_bfloat16* out_cl;          // (B,P,c3_real) bf16 or null
   float* out_cf;                  // (B,c3_real,P) f32 or null
+  // Duplicate-free ("planned") mode, see sad_sa_mlp_dedup_fwd: the launch works on SLOTS of S consecutive samples
+  // instead of points.  idx then holds GLOBAL source rows (b * N + neighbour) per slot, q4 the slot's query point
+  // {x, y, z, radius}, pid its real point id; consecutive slots with the same pid are one point (max-combined in the
+  // epilogue).  The slot count is only known on the device: plan_counts = {runs of 4, runs of 2, single slots}.
+  const int* plan_counts;
+  const float4* q4;
+  const int32_t* pid;
+  uint32_t plan_points;           // real points B * P: the three run classes live in regions of 4, 2 and 1 x plan_points slots
   int* sched;                     // [0] next unit (zero between launches: the kernel resets it), [1] clusters done
   int static_sched;               // few units per cluster: unit(ordinal) = cluster + ordinal * clusters, no scheduler
   int claim;                      // dynamic scheduling: units claimed per atomic
@@ -207,6 +215,28 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int cluster_id = (int)blockIdx.x / CG, num_clusters = (int)gridDim.x / CG;
   const bool leader = (rank == 0);
+  // problem size: launch arguments, or (planned mode) the slot counts the plan kernels left on the device
+  long long total_rows = p.total_rows;
+  uint32_t total_points = p.total_points;
+  int num_units = p.num_units;
+  constexpr bool kCanPlan = (CG == 1 && C::S == 16);      // only the 16-sample single-CTA instances run plans
+  const bool planned = kCanPlan && p.plan_counts != nullptr;
+  uint32_t n4x = 0, n42x = 0;      // slots of the 4-runs, of the 4- and 2-runs
+  if (planned) {
+    n4x = 4u * (uint32_t)__ldg(p.plan_counts);
+    n42x = n4x + 2u * (uint32_t)__ldg(p.plan_counts + 1);
+    const int n = (int)n42x + __ldg(p.plan_counts + 2);
+    total_points = (uint32_t)n;
+    total_rows = (long long)n << p.log2S;
+    num_units = (int)(((total_rows + 127) / 128 + CG - 1) / CG);
+  }
+  // few units per cluster: fixed assignment (see the host side); decided here when the size is only known on the device
+  const bool static_sched = planned ? (long long)num_clusters * 8 >= num_units : p.static_sched != 0;
+
+  // planned mode: logical slot (dense: 4-runs, then 2-runs, then singles) -> slot in the plan's three regions
+  auto slot_addr = [&](uint32_t sl) -> uint32_t {
+    return sl < n4x ? sl : (sl < n42x ? 4u * p.plan_points + (sl - n4x) : 6u * p.plan_points + (sl - n42x));
+  };
 
   if (tid == 0) {
     mbar_init(&ms->wfull, 1);
@@ -247,9 +277,9 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
 
   // unit of ordinal o (tile / tile pair), -1 = no more work
   auto get_unit = [&](int o) -> int {
-    if (p.static_sched) {
+    if (static_sched) {
       const long long u = (long long)cluster_id + (long long)o * num_clusters;
-      return u < p.num_units ? (int)u : -1;
+      return u < num_units ? (int)u : -1;
     }
     bar_wait<CG>(&ms->tfull[o & (kRing - 1)], (uint32_t)((o / kRing) & 1));
     return *reinterpret_cast<volatile int*>(&ms->units[o & (kRing - 1)]);
@@ -279,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
     // may fall arbitrarily far behind the pipeline (a slow atomic), and a parity wait that is two phases late
     // deadlocks.  Every consumer, in both CTAs of a pair, has read ordinal x once the gather warps have passed the
     // "buffer free" wait of ordinal x + NB, so the ring slot of x may be rewritten (ordinal x + kRing) then.
-    if (leader && lane == 0 && !p.static_sched) {
+    if (leader && lane == 0 && !static_sched) {
       constexpr int kEndMarks = G > 7 ? G : 7;      // -1 marks past the last unit (every role's look-ahead)
       int pub = 0, n_end = 0;
       bool ended = false;
@@ -294,9 +324,13 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
       // The cluster's own first unit, then units claimed `claim` at a time from the global counter.  One atomic per
       // unit would cap the whole GPU at one tile per ~11 cycles (same-address atomics serialise in L2: 8192 tiles of
       // SA1 = 47 us) and every cluster at one unit per atomic round trip; two claims are kept in flight.
-      const int claim = p.claim;
+      int claim = p.claim;
+      if (planned) {      // sized on the device like the problem itself
+        const int fair = num_units / num_clusters / 6;
+        claim = fair < 1 ? 1 : (fair > 8 ? 8 : fair);
+      }
       int raw_a = atomicAdd(p.sched, claim), raw_b = atomicAdd(p.sched, claim);
-      push(cluster_id < p.num_units ? cluster_id : -1);
+      push(cluster_id < num_units ? cluster_id : -1);
       long long cur = (long long)num_clusters + raw_a;
       int rem = claim;
       while (n_end < kEndMarks) {
@@ -305,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
           rem = claim;
           raw_b = atomicAdd(p.sched, claim);      // next round trip under the publications of this chunk
         }
-        push((ended || cur >= p.num_units) ? -1 : (int)cur);
+        push((ended || cur >= num_units) ? -1 : (int)cur);
         ++cur;
         --rem;
       }
@@ -442,7 +476,9 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
     auto issue_idx = [&](int unit_id) -> int {
       if (unit_id < 0) return 0;
       const long long R = tile_of(unit_id) * 128 + gt;
-      return R < p.total_rows ? ldg_nc_s32(p.idx + R) : 0;
+      if (R >= total_rows) return 0;
+      if (planned) return ldg_nc_s32(p.idx + ((size_t)slot_addr((uint32_t)(R >> p.log2S)) << p.log2S) + (R & ((1 << p.log2S) - 1)));
+      return ldg_nc_s32(p.idx + R);
     };
     // source row (b * N + idx) of this thread's row, kNoRow past the end; starts the loads of the special K step
     auto load_sp = [&](int unit_id, int raw, Sp& s) -> uint32_t {
@@ -452,9 +488,9 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
       for (int e = 0; e < 4; ++e) s.e[e] = 0.f;
       if (unit_id < 0) return kNoRow;
       const long long R = tile_of(unit_id) * 128 + gt;
-      if (R >= p.total_rows) return kNoRow;
+      if (R >= total_rows) return kNoRow;
       const uint32_t pt = (uint32_t)(R >> p.log2S);
-      const uint32_t src = (pt >> p.log2P) * (uint32_t)p.N + (uint32_t)raw;
+      const uint32_t src = planned ? (uint32_t)raw : (pt >> p.log2P) * (uint32_t)p.N + (uint32_t)raw;
       const float* q = p.new_xyz + (size_t)pt * 3;
       if (p.xyzw) {
         const float4 v = ldg_nc_f32x4(p.xyzw + src);
@@ -471,10 +507,18 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
         for (int e = 0; e < 4; ++e)
           if (e < p.E) s.e[e] = ldg_nc_f32(p.extra + (size_t)src * p.E + e);
       }
-      s.qx = ldg_nc_f32(q);
-      s.qy = ldg_nc_f32(q + 1);
-      s.qz = ldg_nc_f32(q + 2);
-      if (p.radius_t) s.r = ldg_nc_f32(p.radius_t + pt);
+      if (planned) {
+        const float4 qq = ldg_nc_f32x4(p.q4 + slot_addr(pt));
+        s.qx = qq.x;
+        s.qy = qq.y;
+        s.qz = qq.z;
+        s.r = qq.w;
+      } else {
+        s.qx = ldg_nc_f32(q);
+        s.qy = ldg_nc_f32(q + 1);
+        s.qz = ldg_nc_f32(q + 2);
+        if (p.radius_t) s.r = ldg_nc_f32(p.radius_t + pt);
+      }
       return src;
     };
     auto publish = [&](int b) {                 // this warp's stores / copies of buffer b are complete
@@ -640,6 +684,13 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
       hidden(buf);
       done_phase();
       if (warp == 0 || warp == 4) { SALOG(warp, 2500 + 10 * t) }
+      // planned mode: the tile's point ids, requested under the wait for the last layer's MMAs
+      int id[C::PTS];
+      if (planned) {
+        const uint32_t s0 = (uint32_t)(tile_of(unit) * C::PTS);
+#pragma unroll
+        for (int i = 0; i < C::PTS; ++i) id[i] = s0 + i < total_points ? __ldg(p.pid + slot_addr(s0 + i)) : -1;
+      }
       bar_wait<CG>(&ms->dfull[c], (uint32_t)(3 * t + 2) & 1u);
       tc_fence_after_sync();
       if (warp == 0 || warp == 4) { SALOG(warp, 3000 + 10 * t) }
@@ -664,11 +715,69 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
           if (g + 1 < 8) tmem_ld_fence();
         }
         const uint32_t pt0 = (uint32_t)(tile * C::PTS);
-        if (ch < p.c3_real && pt0 < p.total_points) {
+        if (planned) {
+          // slots -> points: consecutive slots with one pid are one point (runs never straddle a tile); the run's last
+          // slot carries the combined maximum.  The plan keeps neighbouring points in neighbouring slots, so the usual
+          // tile is 8 consecutive points (1-slot runs) or 4 (2-slot runs): those store float4s like the plain path.
+          if (ch < p.c3_real && pt0 < total_points) {
+#pragma unroll
+            for (int i = 1; i < C::PTS; ++i)
+              if (id[i] == id[i - 1]) y[i] = fmaxf(y[i], y[i - 1]);
+#pragma unroll
+            for (int i = 0; i < C::PTS; ++i) y[i] = fmaxf(y[i] + bias, 0.f);
+            bool seq = id[0] >= 0 && (id[0] & 3) == 0, pair = seq;
+            if constexpr (C::PTS == 8) {
+#pragma unroll
+              for (int i = 1; i < 8; ++i) {
+                seq = seq && id[i] == id[0] + i;
+                pair = pair && id[i] == id[0] + (i >> 1);
+              }
+              seq = seq && (uint32_t)(id[0] & (p.P - 1)) + 8u <= (uint32_t)p.P;
+              pair = pair && (uint32_t)(id[0] & (p.P - 1)) + 4u <= (uint32_t)p.P;
+            } else {
+              seq = pair = false;
+            }
+            if (seq || pair) {
+              const uint32_t rp = (uint32_t)id[0], bb = rp >> p.log2P, jj = rp - (bb << p.log2P);
+              if (p.out_cf) {
+                float* o_cf = p.out_cf + ((size_t)bb * p.c3_real + ch) * p.P + jj;
+                if constexpr (C::PTS == 8) {
+                  if (seq) {
+                    *reinterpret_cast<float4*>(o_cf) = make_float4(y[0], y[1], y[2], y[3]);
+                    *reinterpret_cast<float4*>(o_cf + 4) = make_float4(y[4], y[5], y[6], y[7]);
+                  } else {
+                    *reinterpret_cast<float4*>(o_cf) = make_float4(y[1], y[3], y[5], y[7]);
+                  }
+                }
+              }
+              if (p.out_cl) {
+                if constexpr (C::PTS == 8) {
+                  if (seq) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) p.out_cl[(size_t)(rp + i) * p.c3_real + ch] = __float2bfloat16_rn(y[i]);
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) p.out_cl[(size_t)(rp + i) * p.c3_real + ch] = __float2bfloat16_rn(y[2 * i + 1]);
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < C::PTS; ++i) {
+                const bool last = i + 1 == C::PTS || id[i + 1] != id[i];
+                if (last && id[i] >= 0) {
+                  const uint32_t rp = (uint32_t)id[i], bb = rp >> p.log2P, jj = rp - (bb << p.log2P);
+                  if (p.out_cf) p.out_cf[((size_t)bb * p.c3_real + ch) * p.P + jj] = y[i];
+                  if (p.out_cl) p.out_cl[(size_t)rp * p.c3_real + ch] = __float2bfloat16_rn(y[i]);
+                }
+              }
+            }
+          }
+        } else if (ch < p.c3_real && pt0 < total_points) {
 #pragma unroll
           for (int i = 0; i < C::PTS; ++i) y[i] = fmaxf(y[i] + bias, 0.f);
           const uint32_t b0 = pt0 >> p.log2P, j0 = pt0 - (b0 << p.log2P);
-          const bool whole = pt0 + C::PTS <= p.total_points && j0 + C::PTS <= (uint32_t)p.P;
+          const bool whole = pt0 + C::PTS <= total_points && j0 + C::PTS <= (uint32_t)p.P;
           if (p.out_cf) {
             float* o_cf = p.out_cf + ((size_t)b0 * p.c3_real + ch) * p.P + j0;
             if (whole) {
@@ -682,7 +791,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
 #pragma unroll
               for (int i = 0; i < C::PTS; ++i) {
                 const uint32_t pt = pt0 + i;
-                if (pt < p.total_points) {
+                if (pt < total_points) {
                   const uint32_t bb = pt >> p.log2P, jj = pt - (bb << p.log2P);
                   p.out_cf[((size_t)bb * p.c3_real + ch) * p.P + jj] = y[i];
                 }
@@ -692,7 +801,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
           if (p.out_cl) {
 #pragma unroll
             for (int i = 0; i < C::PTS; ++i)
-              if (pt0 + i < p.total_points) p.out_cl[(size_t)(pt0 + i) * p.c3_real + ch] = __float2bfloat16_rn(y[i]);
+              if (pt0 + i < total_points) p.out_cl[(size_t)(pt0 + i) * p.c3_real + ch] = __float2bfloat16_rn(y[i]);
           }
         }
       }
@@ -712,6 +821,10 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
     if (atomicAdd(p.sched + 1, 1) == num_clusters - 1) {
       p.sched[0] = 0;
       p.sched[1] = 0;
+      if (planned) {
+        int* c = const_cast<int*>(p.plan_counts);
+        c[0] = c[1] = c[2] = 0;
+      }
     }
   }
 }
@@ -752,12 +865,15 @@ using CfgSA1 = Cfg<1, 0, 64, 128, 64>;      // SA1: xyz + 1 scalar feature -> 64
 using CfgSA2 = Cfg<2, 2, 128, 256, 32>;     // SA2: 128 features + xyz -> 128 -> 128 -> 256, nsample 32 (CTA pair)
 using CfgSA3 = Cfg<2, 4, 128, 256, 16>;     // SA3 / SA4 / vote aggregation (128 outputs zero-padded), nsample 16 (CTA pair)
 using CfgSA2s = Cfg<1, 2, 128, 256, 32>;    // SA2 on one CTA (no cluster): bring-up / comparison
+using CfgSA1d = Cfg<1, 0, 64, 128, 16>;     // SA1 / SA2 on 16-sample slots: the duplicate-free mode (sad_sa_mlp_dedup_fwd)
+using CfgSA2d = Cfg<1, 2, 128, 256, 16>;
 
 const Instance* instances(int* n) {
   // order = preference among instances that fit the same stage (SA2: the single-CTA instance measures 51 us against
   // 58 us for the pair at 8 x 1024 x 32 rows -- the relayed barriers cost more than the halved weight footprint buys)
-  static const Instance tab[] = {make_inst<CfgSA1>(0), make_inst<CfgSA2s>(3), make_inst<CfgSA2>(1), make_inst<CfgSA3>(2)};
-  *n = 4;
+  static const Instance tab[] = {make_inst<CfgSA1>(0), make_inst<CfgSA2s>(3), make_inst<CfgSA2>(1), make_inst<CfgSA3>(2),
+                                 make_inst<CfgSA1d>(4), make_inst<CfgSA2d>(5)};
+  *n = 6;
   return tab;
 }
 const Instance* instance_by_id(int id) {
@@ -892,11 +1008,119 @@ extern "C" int sad_pack_xyzw(int B, int N, const float* xyz, const float* extra1
   return SAD_OK;
 }
 
+// ---- duplicate-free mode: the plan.  A ball query pads a neighbourhood that has fewer than nsample hits with copies of
+// its first hit, and max-pooling ignores copies, so only the leading samples need to go through the MLP.  A point
+// becomes a RUN of r slots of 16 consecutive samples, r the smallest of {1, 2, 4} (nsample 64) / {1, 2} (nsample 32) such
+// that every sample from 16 r on equals sample 0 (checked, not assumed: any idx is handled exactly).  The three run
+// classes are compacted into three regions (4 / 2 / 1 x points slots): per slot 16 GLOBAL source rows, the query point
+// {x, y, z, radius} and the point id.  One warp per point, 32 points per block, one atomic per class and block.
+constexpr int kPlanWarps = 32;
+__global__ void __launch_bounds__(kPlanWarps * 32)
+sa_plan_kernel(uint32_t total_points, int N, int log2P, int S, const int32_t* __restrict__ idx,
+               const float* __restrict__ new_xyz, const float* __restrict__ radius_t, int* __restrict__ counts,
+               int32_t* __restrict__ idxc, float4* __restrict__ q4, int32_t* __restrict__ pid) {
+  __shared__ int s_cls[kPlanWarps], s_base[3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t pt = blockIdx.x * kPlanWarps + warp;
+  int r = 0, cls = 3;
+  int v0 = 0, v1 = 0;
+  if (pt < total_points) {
+    const int32_t* row = idx + (size_t)pt * S;
+    v0 = lane < S ? __ldg(row + lane) : 0;
+    v1 = S > 32 ? __ldg(row + 32 + lane) : 0;
+    const int first = __shfl_sync(0xFFFFFFFFu, v0, 0);
+    const unsigned e0 = __ballot_sync(0xFFFFFFFFu, v0 == first || lane >= S);
+    const unsigned e1 = S > 32 ? __ballot_sync(0xFFFFFFFFu, v1 == first) : 0xFFFFFFFFu;
+    const bool d1 = (e0 >> 16) == 0xFFFFu, d23 = e1 == 0xFFFFFFFFu;
+    r = (S <= 16 || (d1 && d23)) ? 1 : ((S <= 32 || d23) ? 2 : 4);
+    cls = r == 4 ? 0 : (r == 2 ? 1 : 2);
+  }
+  if (lane == 0) s_cls[warp] = cls;
+  __syncthreads();
+  // rank of this point among the block's points of its class, in point order: the 32 consecutive points of a block
+  // stay consecutive inside their class, which is what lets the MLP kernel store float4s of neighbouring points
+  const int other = s_cls[lane];
+  const unsigned same = __ballot_sync(0xFFFFFFFFu, other == cls);
+  const int rank = __popc(same & ((1u << warp) - 1u));
+  if (warp == 0) {
+    const unsigned m0 = __ballot_sync(0xFFFFFFFFu, other == 0), m1 = __ballot_sync(0xFFFFFFFFu, other == 1),
+                   m2 = __ballot_sync(0xFFFFFFFFu, other == 2);
+    if (lane < 3) {
+      const int c = __popc(lane == 0 ? m0 : (lane == 1 ? m1 : m2));
+      s_base[lane] = c ? atomicAdd(counts + lane, c) : 0;
+    }
+  }
+  __syncthreads();
+  if (pt >= total_points) return;
+  const uint32_t region = cls == 0 ? 0u : (cls == 1 ? 4u * total_points : 6u * total_points);
+  const uint32_t slot0 = region + (uint32_t)(s_base[cls] + rank) * (uint32_t)r;
+  const int src_base = (int)(pt >> log2P) * N;
+  // samples 0 .. 16 r - 1 as global source rows; out-of-range neighbours are clamped like every other gather
+  auto fix = [&](int v) { return src_base + (int)min((unsigned)v, (unsigned)(N - 1)); };
+  if (lane < 16 * r) idxc[(size_t)slot0 * 16 + lane] = fix(v0);
+  if (r == 4) idxc[(size_t)slot0 * 16 + 32 + lane] = fix(v1);
+  if (lane < r) {
+    const float* q = new_xyz + (size_t)pt * 3;
+    q4[slot0 + lane] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), radius_t ? __ldg(radius_t + pt) : 1.f);
+    pid[slot0 + lane] = (int32_t)pt;
+  }
+}
+
+extern "C" long long sad_sa_mlp_dedup_workspace_bytes(int B, int P) {
+  if (B < 0 || P < 0) return SAD_EINVAL;
+  return (long long)B * P * 7 * (16 * 4 + 16 + 4) + 256;      // 7 slots per point at most: idx rows, q4, pid
+}
+
+namespace {
+struct PlanArgs {
+  void* workspace;      // null = plain launch
+  int s_full;           // nsample of idx
+};
+int sa_mlp_launch(int instance, int B, int N, int P, const void* feat_cl, const float* xyz, const void* xyzw,
+                  const float* new_xyz, const int32_t* idx, float radius, const float* radius_t, int normalize_xyz,
+                  const float* extra, int E, const void* w_image, const float* bias3_padded, int c3, void* out_cl_bf16,
+                  float* out_cf_f32, int* sched, int tiles_per_cta, cudaStream_t stream, PlanArgs plan);
+}  // namespace
+
 extern "C" int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* feat_cl, const float* xyz, const void* xyzw,
                               const float* new_xyz, const int32_t* idx, float radius, const float* radius_t,
                               int normalize_xyz, const float* extra, int E, const void* w_image, const float* bias3_padded, int c3, void* out_cl_bf16,
                               float* out_cf_f32, int* sched, int tiles_per_cta, sad_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+  return sa_mlp_launch(instance, B, N, P, feat_cl, xyz, xyzw, new_xyz, idx, radius, radius_t, normalize_xyz, extra, E, w_image,
+                       bias3_padded, c3, out_cl_bf16, out_cf_f32, sched, tiles_per_cta, (cudaStream_t)stream_, PlanArgs{nullptr, 0});
+}
+
+// Same stage, duplicate-free: `instance` is the stage's ordinary instance (nsample 32 or 64, single-CTA); the launch runs
+// its 16-sample sibling over the plan's slots.  workspace: sad_sa_mlp_dedup_workspace_bytes(B, P) bytes, 16-byte
+// aligned.  sched: 32 zero-initialised ints that the kernel re-zeroes ([0..1] scheduler, [16..18] the plan's counters).
+// Results are bit-identical to sad_sa_mlp_fwd.
+extern "C" int sad_sa_mlp_dedup_fwd(int instance, int B, int N, int P, const void* feat_cl, const float* xyz, const void* xyzw,
+                                    const float* new_xyz, const int32_t* idx, float radius, const float* radius_t,
+                                    int normalize_xyz, const float* extra, int E, const void* w_image, const float* bias3_padded,
+                                    int c3, void* out_cl_bf16, float* out_cf_f32, int* sched, void* workspace,
+                                    int tiles_per_cta, sad_stream_t stream_) {
+  const Instance* full = instance_by_id(instance);
+  SAD_REQUIRE(full, "sa_mlp_dedup: unknown instance %d", instance);
+  SAD_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "sa_mlp_dedup: workspace null / misaligned");
+  int n;
+  const Instance* t = instances(&n);
+  const Instance* sib = nullptr;
+  for (int i = 0; i < n; ++i)
+    if (t[i].CG == 1 && t[i].S == 16 && t[i].NF == full->NF && t[i].H == full->H && t[i].C3 == full->C3) sib = &t[i];
+  if (!sib || full->CG != 1 || (full->S != 32 && full->S != 64)) {
+    sad_set_error("sa_mlp_dedup: instance %d has no 16-sample sibling", instance);
+    return SAD_EUNSUPPORTED;
+  }
+  return sa_mlp_launch(sib->id, B, N, P, feat_cl, xyz, xyzw, new_xyz, idx, radius, radius_t, normalize_xyz, extra, E, w_image,
+                       bias3_padded, c3, out_cl_bf16, out_cf_f32, sched, tiles_per_cta, (cudaStream_t)stream_,
+                       PlanArgs{workspace, full->S});
+}
+
+namespace {
+int sa_mlp_launch(int instance, int B, int N, int P, const void* feat_cl, const float* xyz, const void* xyzw,
+                  const float* new_xyz, const int32_t* idx, float radius, const float* radius_t, int normalize_xyz,
+                  const float* extra, int E, const void* w_image, const float* bias3_padded, int c3, void* out_cl_bf16,
+                  float* out_cf_f32, int* sched, int tiles_per_cta, cudaStream_t stream, PlanArgs plan) {
   const Instance* in = instance_by_id(instance);
   SAD_REQUIRE(in, "sa_mlp: unknown instance %d", instance);
   SAD_REQUIRE(B >= 0 && N >= 1 && P >= 0, "sa_mlp: bad sizes B=%d N=%d P=%d", B, N, P);
@@ -918,7 +1142,8 @@ extern "C" int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* fea
   memset(&p, 0, sizeof(p));
   p.N = N; p.P = P; p.log2P = log2P;
   for (p.log2S = 0; (1 << p.log2S) < in->S; ++p.log2S) {}
-  p.total_rows = (long long)B * P * in->S;
+  const int s_idx = plan.workspace ? plan.s_full : in->S;      // nsample of the idx tensor
+  p.total_rows = (long long)B * P * s_idx;                      // (planned mode: the upper bound; the kernel reads the counts)
   p.total_points = (uint32_t)((long long)B * P);
   const long long tiles = (p.total_rows + 127) / 128;
   SAD_REQUIRE(tiles < 0x3FFFFFFFLL, "sa_mlp: too many rows");
@@ -933,6 +1158,22 @@ extern "C" int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* fea
   p.bias3 = bias3_padded; p.c3_real = c3;
   p.out_cl = static_cast<__nv_bfloat16*>(out_cl_bf16); p.out_cf = out_cf_f32;
   p.sched = sched;
+  if (plan.workspace) {
+    // workspace: idx rows (7 * points slots x 16) | q4 | pid
+    const size_t slots = (size_t)B * P * 7;
+    int32_t* idxc = static_cast<int32_t*>(plan.workspace);
+    float4* q4 = reinterpret_cast<float4*>(idxc + slots * 16);
+    int32_t* pid = reinterpret_cast<int32_t*>(q4 + slots);
+    int* counts = sched + 16;
+    sa_plan_kernel<<<(unsigned)((p.total_points + kPlanWarps - 1) / kPlanWarps), kPlanWarps * 32, 0, stream>>>(
+        p.total_points, N, log2P, plan.s_full, idx, new_xyz, (normalize_xyz && radius_t) ? radius_t : nullptr, counts, idxc, q4, pid);
+    SAD_LAUNCH_CHECK("sa_plan_kernel");
+    p.idx = idxc;
+    p.q4 = q4;
+    p.pid = pid;
+    p.plan_counts = counts;
+    p.plan_points = p.total_points;
+  }
 
   int dev = 0, sms = 0;
   SAD_CUDA_OK(cudaGetDevice(&dev));
@@ -953,7 +1194,7 @@ extern "C" int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* fea
   if (clusters > max_clusters) clusters = max_clusters;
   // Few units per cluster: a fixed assignment (no scheduler round trips, and no cluster that claims units ahead of
   // need while others idle).  Many: units are handed out dynamically, a few ahead of use.
-  p.static_sched = (long long)clusters * 8 >= p.num_units ? 1 : 0;
+  p.static_sched = (!plan.workspace && (long long)clusters * 8 >= p.num_units) ? 1 : 0;
   {
     const long long fair = p.num_units / clusters;      // units per cluster if all ran equally fast
     p.claim = (int)(fair / 6 < 1 ? 1 : (fair / 6 > 8 ? 8 : fair / 6));
@@ -962,3 +1203,4 @@ extern "C" int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* fea
   SAD_LAUNCH_CHECK("sa_mlp_kernel");
   return SAD_OK;
 }
+}  // namespace

@@ -41,6 +41,14 @@ DYNAMIC_TILES = True
 
 # Shape-specialised SA kernel (csrc/mlp_sa.cu): True = use it whenever an instance matches the stage, "single" / "pair"
 # = prefer the instances that run on single CTAs / CTA pairs, False = always the general kernel (tests compare them).
+# Duplicate-free SA stages (sad_sa_mlp_dedup_fwd): a ball query pads short neighbourhoods with copies of the first hit and
+# the max-pool ignores copies, so only each point's leading samples go through the MLP.  Bit-identical results; applies
+# to the single-CTA instances with nsample 32 / 64 (SA1, SA2).
+DEDUP_SA = [True]
+# nsample values it is applied to: at nsample 64 (SA1: 30 of 64 samples distinct on average, 63 % of the rows remain) the
+# 16-sample instance's higher cost per tile eats the saving; at nsample 32 (SA2: 7 of 32 distinct, half the rows remain)
+# it pays.  The C entry point accepts both.
+DEDUP_NSAMPLE = (32,)
 FAST_SA = [True]
 # Scheduling hint for the fused-MLP launches issued from Python (never changes results): minimum 128-row tiles per
 # CTA.  engine.PipelinedHotPath raises it while it captures its graphs (narrower grids for the small stages).
@@ -199,6 +207,19 @@ class PreparedMLP:
         return self._packed[key]
 
 
+_DEDUP_OK = {}
+
+
+def _dedup_ok(inst: int) -> bool:
+    """The instance is a single-CTA one with nsample 32 / 64 (the duplicate-free launch has a 16-sample sibling for it)."""
+    if inst not in _DEDUP_OK:
+        info = (ctypes.c_int * 5)()
+        _lib.check(_lib.load().sad_sa_mlp_instance_info(int(inst), info), "sa_mlp_instance_info")
+        cg, _, _, _, s_ = list(info)
+        _DEDUP_OK[inst] = cg == 1 and s_ in DEDUP_NSAMPLE
+    return _DEDUP_OK[inst]
+
+
 def _fast_instance(mlp: "PreparedMLP", layout: Layout, S: int, P: int) -> int:
     """Instance id of the shape-specialised kernel for this stage, or -1 (general kernel)."""
     if not FAST_SA[0] or len(mlp) != 3 or layout.c1 or layout.xyz_cols is None or P & (P - 1) or P < 1:
@@ -257,10 +278,16 @@ def fused_sa_fast(mlp: "PreparedMLP", inst: int, layout: Layout, B, N, P, feat_c
             xyzw = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
             _lib.check(_lib.load().sad_pack_xyzw(B, N, _ptr(xyz), _ptr(extra if E else None), _ptr(xyzw), _stream(xyzw)),
                        "pack_xyzw")
-        rc = _lib.load().sad_sa_mlp_fwd(
-            inst, B, N, P, _ptr(feat_cl), _ptr(xyz), _ptr(xyzw), _ptr(new_xyz), _ptr(idx), float(radius), _ptr(radius_t),
-            int(bool(normalize_xyz)), _ptr(extra), len(layout.extra_cols), _ptr(img), _ptr(b3p), c3,
-            _ptr(out_cl), _ptr(out_cf), _ptr(sched), int(TILES_PER_CTA[0]), _VP(torch.cuda.current_stream(dev).cuda_stream))
+        lib = _lib.load()
+        common = (inst, B, N, P, _ptr(feat_cl), _ptr(xyz), _ptr(xyzw), _ptr(new_xyz), _ptr(idx), float(radius), _ptr(radius_t),
+                  int(bool(normalize_xyz)), _ptr(extra), len(layout.extra_cols), _ptr(img), _ptr(b3p), c3,
+                  _ptr(out_cl), _ptr(out_cf), _ptr(sched))
+        stream = _VP(torch.cuda.current_stream(dev).cuda_stream)
+        if DEDUP_SA[0] and _dedup_ok(inst):
+            ws = torch.empty(int(lib.sad_sa_mlp_dedup_workspace_bytes(B, P)), dtype=torch.uint8, device=dev)
+            rc = lib.sad_sa_mlp_dedup_fwd(*common, _ptr(ws), int(TILES_PER_CTA[0]), stream)
+        else:
+            rc = lib.sad_sa_mlp_fwd(*common, int(TILES_PER_CTA[0]), stream)
     _lib.check(rc, "sa_mlp")
     return out_cf, out_cl
 

@@ -217,7 +217,7 @@ def call_cost(name, a):
     if name == "sad_cf_to_cl_bf16":
         B, C, N = v[:3]
         return B * C * N * 6, 0
-    if name == "sad_sa_mlp_fwd":
+    if name in ("sad_sa_mlp_fwd", "sad_sa_mlp_dedup_fwd"):
         # specialised fused SA stage: (inst, B, N, P, feat_cl, xyz, xyzw, new_xyz, idx, radius, radius_t, norm, extra, E, ...)
         from sad_b200 import _lib as _L
         import ctypes as _ct
@@ -281,7 +281,7 @@ def build_roofline(model, xyz, feat, size, reps=3):
     agg = {}
     stages = {}
     for _ in range(reps):
-        with _lib.CallProfiler(repeat={"sad_sa_mlp_fwd": MLP_REPEAT, "sad_pw_mlp_fwd": MLP_REPEAT,
+        with _lib.CallProfiler(repeat={"sad_sa_mlp_fwd": MLP_REPEAT, "sad_sa_mlp_dedup_fwd": MLP_REPEAT, "sad_pw_mlp_fwd": MLP_REPEAT,
                                        "sad_shared_mlp_fwd": MLP_REPEAT, "sad_mlp_tf32_fwd": MLP_REPEAT}) as prof:
             with torch.no_grad():
                 torch.cuda._sleep(60000000)      # ~30 ms: every launch of the forward is queued before the first one runs
@@ -317,7 +317,7 @@ def build_roofline(model, xyz, feat, size, reps=3):
         kernels.append(row)
     # ---- headline: the fused gather + MLP + max-pool launches (tensor roofline).  They own the largest share of the
     # step's SM-time; the FPS chain is a serial-latency kernel and is reported in its honest unit below.
-    mlp_rows = [k for k in kernels if k["kernel"] in ("shared_mlp", "sa_mlp", "pw_mlp", "mlp_tf32")]
+    mlp_rows = [k for k in kernels if k["kernel"] in ("shared_mlp", "sa_mlp", "sa_mlp_dedup", "pw_mlp", "mlp_tf32")]
     flops = sum(agg[k["kernel"]]["flops"] for k in mlp_rows)
     ms = sum(agg[k["kernel"]]["ms"] for k in mlp_rows)
     n_l = sum(agg[k["kernel"]]["launches"] for k in mlp_rows)
@@ -335,6 +335,9 @@ def build_roofline(model, xyz, feat, size, reps=3):
                     "queued behind a busy stream so no host gap is inside an event pair; each fused-MLP call is issued "
                     f"{MLP_REPEAT} times back to back inside its event pair (idempotent: same inputs and outputs) and the "
                     "elapsed time divided, because one event pair around a single 148-CTA launch adds 6-19 us "
+                    "(sa_mlp_dedup = SA1 / SA2 run duplicate-free: the flops are the algorithmic ones of SURVEY 8(d), every "
+                    "(point, sample) row counted; the launch, plan kernel included, executes only the rows that are not "
+                    "padding copies of a neighbourhood's first hit) "
                     "(tools/stage_bench.py --events vs graph replay, profiles/r02_stage_bench_*.txt)"}
     per_stage = []
     for k in mlp_rows:

@@ -150,3 +150,72 @@ def test_fast_voting_stage(B, n, tpc, monkeypatch):
     # the offsets alone (vote - seed): the bf16 bar at the scale of the MLP output, not of the coordinates
     y = O.shared_mlp(sf[..., None], layers, pool=False, last_relu=False)[..., 0]
     close(vx - cu(seed_xyz), y[:, :3, :].transpose(0, 2, 1), 2e-2)
+
+
+# ----------------------------------------------------------------------------- duplicate-free SA stages
+def _ball_idx(rng, B, N, P, S, radius):
+    xyz = (rng.random((B, N, 3), dtype=np.float32) * 3).astype(np.float32)
+    inds = C.furthest_point_sample(xyz, P)
+    new_xyz = np.stack([xyz[b][inds[b]] for b in range(B)])
+    return xyz, new_xyz, C.ball_query(radius, S, xyz, new_xyz)
+
+
+@pytest.mark.parametrize("which,B,N,P,radius,tpc", [
+    ("sa1", 2, 6000, 256, 0.2, 1),        # sparse balls: mostly 1- and 2-slot runs
+    ("sa1", 1, 6000, 128, 0.6, 1),        # dense balls: every point needs all 64 samples (4-slot runs)
+    ("sa1", 3, 9000, 512, 0.3, 6),        # mixed, narrow grid
+    ("sa2", 2, 2048, 256, 0.25, 1),       # nsample 32: 1- and 2-slot runs
+    ("sa2", 2, 2048, 128, 1.5, 1),        # all 2-slot runs
+    ("sa2", 1, 2048, 64, 0.02, 6),        # nearly empty balls: 1 slot per point, a single partial tile
+])
+def test_duplicate_free_stage_is_bit_identical(which, B, N, P, radius, tpc, monkeypatch):
+    """sad_sa_mlp_dedup_fwd (plan kernel + 16-sample sibling instance over slots) against the ordinary launch of the same
+    stage: identical bits in both output layouts, and both within the bf16 bar of the oracle."""
+    from sad_b200 import mlp as M
+    monkeypatch.setattr(M, "TILES_PER_CTA", [tpc])
+    monkeypatch.setattr(M, "DEDUP_NSAMPLE", (32, 64))      # (nsample 64 is off by default: it does not pay there)
+    monkeypatch.setattr(M, "_DEDUP_OK", {})
+    rng = np.random.default_rng(P + int(radius * 100))
+    S, Cf, hidden = (64, 1, [64, 64, 128]) if which == "sa1" else (32, 128, [128, 128, 256])
+    xyz, new_xyz, idx = _ball_idx(rng, B, N, P, S, radius)
+    feat = rng.standard_normal((B, Cf, N)).astype(np.float32)
+    layers = make_layers(rng, [Cf + 3] + hidden)
+    mlp = M.prepare_layers([(cu(W), cu(b)) for W, b in layers])
+    outs = {}
+    for dedup in (False, True):
+        monkeypatch.setattr(M, "DEDUP_SA", [dedup])
+        got = M.sa_group_mlp(cu(xyz), cu(new_xyz), cu(feat), cu(idx), radius, mlp, use_xyz=True, normalize_xyz=True)
+        outs[dedup] = (got.cpu().numpy().copy(), got._sad_cl.float().cpu().numpy().copy())
+    assert np.array_equal(outs[True][0], outs[False][0]) and np.array_equal(outs[True][1], outs[False][1])
+    want = O.shared_mlp(O.query_and_group(xyz, new_xyz, feat, idx, np.float32(radius), True, True), layers, pool=True)
+    close(torch.from_numpy(outs[True][0]), want, 2e-2)
+    # the slot statistics the plan is built on: how much of the stage is padding
+    first = idx[..., :1]
+    dup_tail16 = float((idx[..., 16:] == first).all(-1).mean())
+    assert 0.0 <= dup_tail16 <= 1.0
+
+
+def test_duplicate_free_stage_handles_arbitrary_indices(monkeypatch):
+    """idx that is not a ball query's (no padding structure, duplicates in the middle, per-cluster radius): the plan
+    checks the tail per point, so the result is still exact."""
+    from sad_b200 import mlp as M
+    monkeypatch.setattr(M, "_DEDUP_OK", {})
+    rng = np.random.default_rng(3)
+    B, N, P, S = 2, 3000, 128, 32
+    xyz = (rng.random((B, N, 3), dtype=np.float32) * 3).astype(np.float32)
+    new_xyz = xyz[:, :P].copy()
+    idx = rng.integers(0, N, (B, P, S)).astype(np.int32)
+    idx[0, :40, 16:] = idx[0, :40, :1]            # looks padded after 16 samples
+    idx[0, 40:60, 20:] = idx[0, 40:60, :1]        # padded, but only from sample 20: needs both slots
+    idx[1, :10, :] = idx[1, :10, :1]              # a single neighbour
+    rad = (0.3 + rng.random((B, P))).astype(np.float32)
+    feat = rng.standard_normal((B, 128, N)).astype(np.float32)
+    layers = make_layers(rng, [131, 128, 128, 256])
+    mlp = M.prepare_layers([(cu(W), cu(b)) for W, b in layers])
+    outs = []
+    for dedup in (False, True):
+        monkeypatch.setattr(M, "DEDUP_SA", [dedup])
+        outs.append(M.sa_group_mlp(cu(xyz), cu(new_xyz), cu(feat), cu(idx), cu(rad), mlp).cpu().numpy().copy())
+    assert np.array_equal(outs[0], outs[1])
+    want = O.shared_mlp(O.query_and_group(xyz, new_xyz, feat, idx, rad, True, True), layers, pool=True)
+    close(torch.from_numpy(outs[1]), want, 2e-2)

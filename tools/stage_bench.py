@@ -88,20 +88,22 @@ def main():
         idx = ops.ball_query(0.2, 64, xyz, new_xyz, grid)
         m1 = layers([4, 64, 64, 128])
         hits = (idx != idx[:, :, :1]).sum(-1).float().mean().item() + 1
-        for mode in (False, True):
-            M.FAST_SA[0] = mode
+        for mode, dd in ((False, False), (True, False), (True, True)):
+            M.FAST_SA[0], M.DEDUP_SA[0] = mode, dd
             med, best = t(lambda: M.sa_group_mlp(xyz, new_xyz, feat, idx, 0.2, m1))
-            print({"stage": "sa1-real", "fast": mode, "us": round(med, 1), "mean_distinct_hits": round(hits, 1)}, flush=True)
+            print({"stage": "sa1-real", "fast": mode, "dedup": dd, "us": round(med, 1), "mean_distinct_hits": round(hits, 1)}, flush=True)
         M.FAST_SA[0] = True
         f1 = M.sa_group_mlp(xyz, new_xyz, feat, idx, 0.2, m1)
         inds2 = ops.furthest_point_sample(new_xyz, 1024)
         x2 = ops.gather_points(new_xyz, inds2)
         idx2 = ops.ball_query(0.4, 32, new_xyz, x2)
         m2 = layers([131, 128, 128, 256])
-        for mode in (False, "single", "pair"):
-            M.FAST_SA[0] = mode
+        hits2 = (idx2 != idx2[:, :, :1]).sum(-1).float().mean().item() + 1
+        for mode, dd in ((False, False), ("single", False), ("single", True), ("pair", False)):
+            M.FAST_SA[0], M.DEDUP_SA[0] = mode, dd
             med, best = t(lambda: M.sa_group_mlp(new_xyz, x2, f1, idx2, 0.4, m2))
-            print({"stage": "sa2-real", "fast": mode, "us": round(med, 1)}, flush=True)
+            print({"stage": "sa2-real", "fast": mode, "dedup": dd, "us": round(med, 1), "mean_distinct_hits": round(hits2, 1)}, flush=True)
+        M.DEDUP_SA[0] = True
         # same shapes, random neighbours
         ridx = torch.randint(0, 40000, (B, 2048, 64), device=dev, dtype=torch.int32)
         M.FAST_SA[0] = True
