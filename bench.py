@@ -473,7 +473,7 @@ def run_ours(args):
     set_bytes = sum(int(h.numel() * h.element_size()) for h in sets[0]["host"])
 
     eng = PipelinedHotPath(model, B_PER_GPU, N_POINTS, feat_dim=1, slots=args.slots, device=dev,
-                           fps_policy=args.fps_policy)
+                           fps_policy=args.fps_policy, mlp_tiles_per_cta=args.tpc)
     main = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -623,6 +623,7 @@ def main():
     ap.add_argument("--fps-policy", default="throughput", choices=["throughput", "throughput_paired", "latency"],
                     help="scheduling of the 40k-point FPS (same indices either way)")
     ap.add_argument("--sets", type=int, default=32, help="rotating input sets (32 x 5.1 MB > L2)")
+    ap.add_argument("--tpc", type=int, default=6, help="fused-MLP tiles per CTA under the pipelined executor (scheduling only)")
     ap.add_argument("--batch", type=int, default=8, help="scenes per GPU per step (default = configs[1]; other values = sweep points)")
     ap.add_argument("--points", type=int, default=40000, help="points per scene (default = configs[1])")
     ap.add_argument("--mlp-dtype", default="bf16", choices=["bf16", "tf32"],
