@@ -53,7 +53,7 @@ SIGNATURES = {
                        _c_int, _vp, _vp, _vp, _c_int, _vp],
     "sad_sa_mlp_dedup_workspace_bytes": [_c_int, _c_int],
     "sad_sa_mlp_dedup_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_float, _vp, _c_int, _vp, _c_int, _vp, _vp,
-                             _c_int, _vp, _vp, _vp, _vp, _c_int, _vp],
+                             _c_int, _vp, _vp, _vp, _vp, _c_int, _c_int, _vp],
     "sad_scatter_plan_build": [_c_int, _c_int, ctypes.c_longlong, _vp, _vp, _vp, _vp],
     "sad_interp_plan_build": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "sad_scatter_add_det": [_c_int, _c_int, _c_int, ctypes.c_longlong, _vp, _vp, _vp, _vp, _vp],

@@ -74,7 +74,7 @@ struct Cfg {
   static_assert(C3 % (128 * CG) == 0 && C3 <= 256, "output width");
   static_assert(HP % 64 == 0 && NQ % NP == 0 && NQP >= 1, "epilogue split");
   static_assert(NB >= G, "not enough tile buffers for the contexts");
-  static_assert(S == 16 || S == 32 || S == 64, "nsample");
+  static_assert(S == 8 || S == 16 || S == 32 || S == 64, "nsample");
   static_assert(WBYTES % 1024 == 0, "weight image alignment");
 };
 
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
   long long total_rows = p.total_rows;
   uint32_t total_points = p.total_points;
   int num_units = p.num_units;
-  constexpr bool kCanPlan = (CG == 1 && C::S == 16);      // only the 16-sample single-CTA instances run plans
+  constexpr bool kCanPlan = (CG == 1 && C::S <= 16);      // only the 8- / 16-sample single-CTA instances run plans
   const bool planned = kCanPlan && p.plan_counts != nullptr;
   uint32_t n4x = 0, n42x = 0;      // slots of the 4-runs, of the 4- and 2-runs
   if (planned) {
@@ -708,10 +708,15 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           if (g + 1 < 8) tmem_ld_x16(tctx + (uint32_t)(q * 128 + (g + 1) * 16), v[(g + 1) & 1]);
-          const float m = vmax_tree<16>(v[g & 1]);
-          constexpr int GP = C::S / 16;                 // 16-column groups per point
-          if (g % GP == 0) y[g / GP] = m;
-          else y[g / GP] = fmaxf(y[g / GP], m);
+          if constexpr (C::S == 8) {                   // two points per 16-column group
+            y[2 * g] = vmax_tree<8>(v[g & 1]);
+            y[2 * g + 1] = vmax_tree<8>(v[g & 1] + 8);
+          } else {
+            const float m = vmax_tree<16>(v[g & 1]);
+            constexpr int GP = C::S / 16;               // 16-column groups per point
+            if (g % GP == 0) y[g / GP] = m;
+            else y[g / GP] = fmaxf(y[g / GP], m);
+          }
           if (g + 1 < 8) tmem_ld_fence();
         }
         const uint32_t pt0 = (uint32_t)(tile * C::PTS);
@@ -725,40 +730,36 @@ __global__ void __launch_bounds__(kThreads, 1) sa_mlp_kernel(const __grid_consta
               if (id[i] == id[i - 1]) y[i] = fmaxf(y[i], y[i - 1]);
 #pragma unroll
             for (int i = 0; i < C::PTS; ++i) y[i] = fmaxf(y[i] + bias, 0.f);
-            bool seq = id[0] >= 0 && (id[0] & 3) == 0, pair = seq;
-            if constexpr (C::PTS == 8) {
+            bool seq = id[0] >= 0 && (id[0] & 3) == 0, pair = seq && C::PTS >= 8;
 #pragma unroll
-              for (int i = 1; i < 8; ++i) {
-                seq = seq && id[i] == id[0] + i;
-                pair = pair && id[i] == id[0] + (i >> 1);
-              }
-              seq = seq && (uint32_t)(id[0] & (p.P - 1)) + 8u <= (uint32_t)p.P;
-              pair = pair && (uint32_t)(id[0] & (p.P - 1)) + 4u <= (uint32_t)p.P;
-            } else {
-              seq = pair = false;
+            for (int i = 1; i < C::PTS; ++i) {
+              seq = seq && id[i] == id[0] + i;
+              pair = pair && id[i] == id[0] + (i >> 1);
             }
+            seq = seq && (uint32_t)(id[0] & (p.P - 1)) + (uint32_t)C::PTS <= (uint32_t)p.P;
+            pair = pair && (uint32_t)(id[0] & (p.P - 1)) + (uint32_t)(C::PTS / 2) <= (uint32_t)p.P;
             if (seq || pair) {
               const uint32_t rp = (uint32_t)id[0], bb = rp >> p.log2P, jj = rp - (bb << p.log2P);
               if (p.out_cf) {
                 float* o_cf = p.out_cf + ((size_t)bb * p.c3_real + ch) * p.P + jj;
-                if constexpr (C::PTS == 8) {
-                  if (seq) {
-                    *reinterpret_cast<float4*>(o_cf) = make_float4(y[0], y[1], y[2], y[3]);
-                    *reinterpret_cast<float4*>(o_cf + 4) = make_float4(y[4], y[5], y[6], y[7]);
-                  } else {
-                    *reinterpret_cast<float4*>(o_cf) = make_float4(y[1], y[3], y[5], y[7]);
+                if (seq) {
+#pragma unroll
+                  for (int i = 0; i < C::PTS; i += 4) *reinterpret_cast<float4*>(o_cf + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+                } else {
+                  if constexpr (C::PTS >= 8) {
+#pragma unroll
+                    for (int i = 0; i < C::PTS / 2; i += 4)
+                      *reinterpret_cast<float4*>(o_cf + i) = make_float4(y[2 * i + 1], y[2 * i + 3], y[2 * i + 5], y[2 * i + 7]);
                   }
                 }
               }
               if (p.out_cl) {
-                if constexpr (C::PTS == 8) {
-                  if (seq) {
+                if (seq) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) p.out_cl[(size_t)(rp + i) * p.c3_real + ch] = __float2bfloat16_rn(y[i]);
-                  } else {
+                  for (int i = 0; i < C::PTS; ++i) p.out_cl[(size_t)(rp + i) * p.c3_real + ch] = __float2bfloat16_rn(y[i]);
+                } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) p.out_cl[(size_t)(rp + i) * p.c3_real + ch] = __float2bfloat16_rn(y[2 * i + 1]);
-                  }
+                  for (int i = 0; i < C::PTS / 2; ++i) p.out_cl[(size_t)(rp + i) * p.c3_real + ch] = __float2bfloat16_rn(y[2 * i + 1]);
                 }
               }
             } else {
@@ -867,6 +868,8 @@ using CfgSA3 = Cfg<2, 4, 128, 256, 16>;     // SA3 / SA4 / vote aggregation (128
 using CfgSA2s = Cfg<1, 2, 128, 256, 32>;    // SA2 on one CTA (no cluster): bring-up / comparison
 using CfgSA1d = Cfg<1, 0, 64, 128, 16>;     // SA1 / SA2 on 16-sample slots: the duplicate-free mode (sad_sa_mlp_dedup_fwd)
 using CfgSA2d = Cfg<1, 2, 128, 256, 16>;
+// (An 8-sample-slot sibling <1, 2, 128, 256, 8> was built and measured for SA2: 61 % of the 16-slot rows, but 16 output
+// points per tile make its epilogue slower than the rows it saves -- 41 us against 38 us -- so it is not compiled in.)
 
 const Instance* instances(int* n) {
   // order = preference among instances that fit the same stage (SA2: the single-CTA instance measures 51 us against
@@ -1016,7 +1019,7 @@ extern "C" int sad_pack_xyzw(int B, int N, const float* xyz, const float* extra1
 // {x, y, z, radius} and the point id.  One warp per point, 32 points per block, one atomic per class and block.
 constexpr int kPlanWarps = 32;
 __global__ void __launch_bounds__(kPlanWarps * 32)
-sa_plan_kernel(uint32_t total_points, int N, int log2P, int S, const int32_t* __restrict__ idx,
+sa_plan_kernel(uint32_t total_points, int N, int log2P, int S, int SL, const int32_t* __restrict__ idx,
                const float* __restrict__ new_xyz, const float* __restrict__ radius_t, int* __restrict__ counts,
                int32_t* __restrict__ idxc, float4* __restrict__ q4, int32_t* __restrict__ pid) {
   __shared__ int s_cls[kPlanWarps], s_base[3];
@@ -1031,8 +1034,10 @@ sa_plan_kernel(uint32_t total_points, int N, int log2P, int S, const int32_t* __
     const int first = __shfl_sync(0xFFFFFFFFu, v0, 0);
     const unsigned e0 = __ballot_sync(0xFFFFFFFFu, v0 == first || lane >= S);
     const unsigned e1 = S > 32 ? __ballot_sync(0xFFFFFFFFu, v1 == first) : 0xFFFFFFFFu;
-    const bool d1 = (e0 >> 16) == 0xFFFFu, d23 = e1 == 0xFFFFFFFFu;
-    r = (S <= 16 || (d1 && d23)) ? 1 : ((S <= 32 || d23) ? 2 : 4);
+    // padding from sample SL on -> 1 slot, from 2 SL on -> 2 slots, else 4 (nsample / SL is 2 or 4)
+    const unsigned long long eq = ((unsigned long long)e1 << 32) | e0;      // bit j: sample j equals sample 0 (or is past nsample)
+    const bool from1 = (eq >> SL) == (~0ull >> SL), from2 = (eq >> (2 * SL)) == (~0ull >> (2 * SL));
+    r = from1 ? 1 : ((from2 || S <= 2 * SL) ? 2 : 4);
     cls = r == 4 ? 0 : (r == 2 ? 1 : 2);
   }
   if (lane == 0) s_cls[warp] = cls;
@@ -1057,8 +1062,8 @@ sa_plan_kernel(uint32_t total_points, int N, int log2P, int S, const int32_t* __
   const int src_base = (int)(pt >> log2P) * N;
   // samples 0 .. 16 r - 1 as global source rows; out-of-range neighbours are clamped like every other gather
   auto fix = [&](int v) { return src_base + (int)min((unsigned)v, (unsigned)(N - 1)); };
-  if (lane < 16 * r) idxc[(size_t)slot0 * 16 + lane] = fix(v0);
-  if (r == 4) idxc[(size_t)slot0 * 16 + 32 + lane] = fix(v1);
+  if (lane < SL * r) idxc[(size_t)slot0 * SL + lane] = fix(v0);
+  if (32 + lane < SL * r) idxc[(size_t)slot0 * SL + 32 + lane] = fix(v1);
   if (lane < r) {
     const float* q = new_xyz + (size_t)pt * 3;
     q4[slot0 + lane] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), radius_t ? __ldg(radius_t + pt) : 1.f);
@@ -1091,14 +1096,14 @@ extern "C" int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* fea
 }
 
 // Same stage, duplicate-free: `instance` is the stage's ordinary instance (nsample 32 or 64, single-CTA); the launch runs
-// its 16-sample sibling over the plan's slots.  workspace: sad_sa_mlp_dedup_workspace_bytes(B, P) bytes, 16-byte
+// its sibling with 8- or 16-sample slots (slot_samples; 0 = the smallest available) over the plan's slots.  workspace: sad_sa_mlp_dedup_workspace_bytes(B, P) bytes, 16-byte
 // aligned.  sched: 32 zero-initialised ints that the kernel re-zeroes ([0..1] scheduler, [16..18] the plan's counters).
 // Results are bit-identical to sad_sa_mlp_fwd.
 extern "C" int sad_sa_mlp_dedup_fwd(int instance, int B, int N, int P, const void* feat_cl, const float* xyz, const void* xyzw,
                                     const float* new_xyz, const int32_t* idx, float radius, const float* radius_t,
                                     int normalize_xyz, const float* extra, int E, const void* w_image, const float* bias3_padded,
                                     int c3, void* out_cl_bf16, float* out_cf_f32, int* sched, void* workspace,
-                                    int tiles_per_cta, sad_stream_t stream_) {
+                                    int slot_samples, int tiles_per_cta, sad_stream_t stream_) {
   const Instance* full = instance_by_id(instance);
   SAD_REQUIRE(full, "sa_mlp_dedup: unknown instance %d", instance);
   SAD_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "sa_mlp_dedup: workspace null / misaligned");
@@ -1106,9 +1111,11 @@ extern "C" int sad_sa_mlp_dedup_fwd(int instance, int B, int N, int P, const voi
   const Instance* t = instances(&n);
   const Instance* sib = nullptr;
   for (int i = 0; i < n; ++i)
-    if (t[i].CG == 1 && t[i].S == 16 && t[i].NF == full->NF && t[i].H == full->H && t[i].C3 == full->C3) sib = &t[i];
+    if (t[i].CG == 1 && t[i].S * 4 >= full->S && t[i].S * 2 <= full->S && t[i].NF == full->NF && t[i].H == full->H &&
+        t[i].C3 == full->C3 && (slot_samples ? t[i].S == slot_samples : (!sib || t[i].S < sib->S)))
+      sib = &t[i];      // the sibling with the smallest slot whose runs of 1 / 2 / 4 slots still cover nsample
   if (!sib || full->CG != 1 || (full->S != 32 && full->S != 64)) {
-    sad_set_error("sa_mlp_dedup: instance %d has no 16-sample sibling", instance);
+    sad_set_error("sa_mlp_dedup: instance %d has no sibling with %d-sample slots", instance, slot_samples);
     return SAD_EUNSUPPORTED;
   }
   return sa_mlp_launch(sib->id, B, N, P, feat_cl, xyz, xyzw, new_xyz, idx, radius, radius_t, normalize_xyz, extra, E, w_image,
@@ -1162,11 +1169,11 @@ int sa_mlp_launch(int instance, int B, int N, int P, const void* feat_cl, const 
     // workspace: idx rows (7 * points slots x 16) | q4 | pid
     const size_t slots = (size_t)B * P * 7;
     int32_t* idxc = static_cast<int32_t*>(plan.workspace);
-    float4* q4 = reinterpret_cast<float4*>(idxc + slots * 16);
+    float4* q4 = reinterpret_cast<float4*>(idxc + slots * 16);      // (sized for 16-sample slots; 8-sample slots use half)
     int32_t* pid = reinterpret_cast<int32_t*>(q4 + slots);
     int* counts = sched + 16;
     sa_plan_kernel<<<(unsigned)((p.total_points + kPlanWarps - 1) / kPlanWarps), kPlanWarps * 32, 0, stream>>>(
-        p.total_points, N, log2P, plan.s_full, idx, new_xyz, (normalize_xyz && radius_t) ? radius_t : nullptr, counts, idxc, q4, pid);
+        p.total_points, N, log2P, plan.s_full, in->S, idx, new_xyz, (normalize_xyz && radius_t) ? radius_t : nullptr, counts, idxc, q4, pid);
     SAD_LAUNCH_CHECK("sa_plan_kernel");
     p.idx = idxc;
     p.q4 = q4;

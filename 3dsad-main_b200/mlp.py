@@ -49,6 +49,7 @@ DEDUP_SA = [True]
 # 16-sample instance's higher cost per tile eats the saving; at nsample 32 (SA2: 7 of 32 distinct, half the rows remain)
 # it pays.  The C entry point accepts both.
 DEDUP_NSAMPLE = (32,)
+DEDUP_SLOT = [0]      # samples per slot: 0 = the smallest the library has for the stage (tools / tests: 8 or 16)
 FAST_SA = [True]
 # Scheduling hint for the fused-MLP launches issued from Python (never changes results): minimum 128-row tiles per
 # CTA.  engine.PipelinedHotPath raises it while it captures its graphs (narrower grids for the small stages).
@@ -285,7 +286,7 @@ def fused_sa_fast(mlp: "PreparedMLP", inst: int, layout: Layout, B, N, P, feat_c
         stream = _VP(torch.cuda.current_stream(dev).cuda_stream)
         if DEDUP_SA[0] and _dedup_ok(inst):
             ws = torch.empty(int(lib.sad_sa_mlp_dedup_workspace_bytes(B, P)), dtype=torch.uint8, device=dev)
-            rc = lib.sad_sa_mlp_dedup_fwd(*common, _ptr(ws), int(TILES_PER_CTA[0]), stream)
+            rc = lib.sad_sa_mlp_dedup_fwd(*common, _ptr(ws), int(DEDUP_SLOT[0]), int(TILES_PER_CTA[0]), stream)
         else:
             rc = lib.sad_sa_mlp_fwd(*common, int(TILES_PER_CTA[0]), stream)
     _lib.check(rc, "sa_mlp")

@@ -213,9 +213,10 @@ SAD_API int sad_sa_mlp_fwd(int instance, int B, int N, int P, const void* feat_c
 
 /* Same stage, DUPLICATE-FREE.  A ball query pads a neighbourhood that has fewer than nsample hits with copies of its first
  * hit, and a max-pool ignores copies: only the leading samples need to go through the MLP.  A small plan kernel turns
- * every point into a run of 1, 2 or 4 slots of 16 samples (the smallest run after which every remaining sample equals
- * sample 0 -- checked per point, so any idx is handled exactly) and the stage's 16-sample sibling instance runs over the
- * slots, max-combining the slots of a point in its epilogue.  Results are bit-identical to sad_sa_mlp_fwd.
+ * every point into a run of 1, 2 or 4 slots of 8 or 16 samples (the smallest run after which every remaining sample
+ * equals sample 0 -- checked per point, so any idx is handled exactly) and the stage's sibling instance with that nsample
+ * runs over the slots, max-combining the slots of a point in its epilogue.  slot_samples: 0 = the smallest
+ * slot the library has an instance for (16 today; an 8-sample variant measured slower and is not compiled in).  Results are bit-identical to sad_sa_mlp_fwd.
  * `instance`: the stage's ordinary single-CTA instance with nsample 32 or 64 (else SAD_EUNSUPPORTED); same weight image.
  * workspace: sad_sa_mlp_dedup_workspace_bytes(B, P) bytes, 16-byte aligned, caller-owned scratch.
  * sched: 32 zero-initialised ints that the kernel re-zeroes ([0..1] tile scheduler, [16..18] the plan's counters). */
@@ -224,7 +225,7 @@ SAD_API int sad_sa_mlp_dedup_fwd(int instance, int B, int N, int P, const void* 
                                  const float* new_xyz, const int32_t* idx, float radius, const float* radius_t,
                                  int normalize_xyz, const float* extra, int E, const void* w_image, const float* bias3_padded,
                                  int c3, void* out_cl_bf16, float* out_cf_f32, int* sched, void* workspace,
-                                 int tiles_per_cta, sad_stream_t stream);
+                                 int slot_samples, int tiles_per_cta, sad_stream_t stream);
 
 /* ---- a6 / a9, shape-specialised POINT-WISE fast path (csrc/mlp_pw.cu): nsample == 1 stages with 256-wide layers.
  *   kind 0  FP module: [three_interpolate(known) (256) | skip (256)] -> 256 -> c_last (<= 256), ReLU everywhere.  The

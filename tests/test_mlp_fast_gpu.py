@@ -160,20 +160,23 @@ def _ball_idx(rng, B, N, P, S, radius):
     return xyz, new_xyz, C.ball_query(radius, S, xyz, new_xyz)
 
 
-@pytest.mark.parametrize("which,B,N,P,radius,tpc", [
-    ("sa1", 2, 6000, 256, 0.2, 1),        # sparse balls: mostly 1- and 2-slot runs
-    ("sa1", 1, 6000, 128, 0.6, 1),        # dense balls: every point needs all 64 samples (4-slot runs)
-    ("sa1", 3, 9000, 512, 0.3, 6),        # mixed, narrow grid
-    ("sa2", 2, 2048, 256, 0.25, 1),       # nsample 32: 1- and 2-slot runs
-    ("sa2", 2, 2048, 128, 1.5, 1),        # all 2-slot runs
-    ("sa2", 1, 2048, 64, 0.02, 6),        # nearly empty balls: 1 slot per point, a single partial tile
+@pytest.mark.parametrize("which,B,N,P,radius,tpc,slot", [
+    ("sa1", 2, 6000, 256, 0.2, 1, 16),        # sparse balls: mostly 1- and 2-slot runs
+    ("sa1", 1, 6000, 128, 0.6, 1, 16),        # dense balls: every point needs all 64 samples (4-slot runs)
+    ("sa1", 3, 9000, 512, 0.3, 6, 0),         # mixed, narrow grid
+    ("sa2", 2, 2048, 256, 0.25, 1, 16),       # nsample 32, 16-sample slots: 1- and 2-slot runs
+    ("sa2", 2, 2048, 128, 1.5, 1, 16),        # all 2-slot runs
+    ("sa2", 1, 2048, 64, 0.02, 6, 16),        # nearly empty balls: 1 slot per point, a single partial tile
+    ("sa2", 1, 2048, 64, 0.02, 6, 0),         # 1 slot per point (automatic slot size), a single partial tile
+    ("sa2", 4, 2048, 1024, 0.4, 1, 0),        # the benchmark's shape and radius
 ])
-def test_duplicate_free_stage_is_bit_identical(which, B, N, P, radius, tpc, monkeypatch):
+def test_duplicate_free_stage_is_bit_identical(which, B, N, P, radius, tpc, slot, monkeypatch):
     """sad_sa_mlp_dedup_fwd (plan kernel + 16-sample sibling instance over slots) against the ordinary launch of the same
     stage: identical bits in both output layouts, and both within the bf16 bar of the oracle."""
     from sad_b200 import mlp as M
     monkeypatch.setattr(M, "TILES_PER_CTA", [tpc])
     monkeypatch.setattr(M, "DEDUP_NSAMPLE", (32, 64))      # (nsample 64 is off by default: it does not pay there)
+    monkeypatch.setattr(M, "DEDUP_SLOT", [slot])
     monkeypatch.setattr(M, "_DEDUP_OK", {})
     rng = np.random.default_rng(P + int(radius * 100))
     S, Cf, hidden = (64, 1, [64, 64, 128]) if which == "sa1" else (32, 128, [128, 128, 256])
