@@ -14,13 +14,16 @@
 //                   W ring  2-8 stages of one weight piece (<= 256 rows x 32 K values = 32 KB), one TMA bulk copy
 //                   each: the pieces are re-streamed from L2 for every tile, the ring depth is the prefetch distance
 //                   A ring  2-4 x 16 KB   layer-1 operand chunks (128 rows x 32 channels)
-//   TMEM            hidden accumulators in columns [0,256); last-layer blocks (128 channels x 128 rows) in 128-column
-//                   regions (columns 256.. when there are at most two blocks, so the next tile's first layers run under
-//                   the drain of this tile's last layer)
+//   TMEM            per tile context max(widest hidden layer, 128 x last-layer blocks) columns: hidden accumulators and
+//                   the last layer's 128-channel x 128-row blocks share them (a layer's accumulators are drained
+//                   before the next layer's MMAs are issued)
+//   contexts        TWO tiles in flight per CTA when two activation buffers and 2 x those columns fit (all SA stages):
+//                   the roles walk (layer, context) in the same order, so one context's epilogue runs under the other's
+//                   MMAs; the 256-wide point-wise stages (FP, voting) run one
 //   warps           0-15 epilogue (4 column groups x 4 TMEM lane quarters), 16-19 operand producers (thread = row),
 //                   20 MMA issue, 21 weight TMA
 //
-// One 128-row tile (row = (query point, sample)) is in flight per CTA; persistent CTAs take tiles round-robin.
+// Persistent CTAs take 128-row tiles (row = (query point, sample)) round-robin.
 // Roofline: tensor (kind::tf32 peak = half the bf16 peak); algorithmic flops = 2 * rows * sum(Cin*Cout).
 #include <string.h>
 
@@ -68,12 +71,14 @@ struct TfParams {
   float* out_cl;                     // (B, P, c_last) f32 or null
   // shared-memory carve-up
   int act_bytes, nsa, nsw, wstage;
+  // tile contexts in flight per CTA (1 or 2: own activation buffer and TMEM columns each) and TMEM columns of one
+  int nctx, ctx_cols;
 };
 
 struct Misc {
   uint64_t wfull[kMaxNSW], wfree[kMaxNSW], afull[kMaxNSA], afree[kMaxNSA];
-  uint64_t dfull[1 + 4];             // [0] hidden layers, [1 + blk] last-layer blocks
-  uint64_t actfull, tfree;
+  uint64_t dfull[2][1 + 4];          // per context: [0] hidden layers, [1 + blk] last-layer blocks
+  uint64_t actfull[2], tfree[2];
   uint32_t tmem_base;
 };
 
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* act = base;
   const int kNSA = p.nsa, kNSW = p.nsw, kWStage = p.wstage;
-  uint8_t* aring = act + p.act_bytes;
+  uint8_t* aring = act + p.nctx * p.act_bytes;
   uint8_t* wring = aring + kNSA * kChunk;
   Misc* ms = reinterpret_cast<Misc*>(wring + kNSW * kWStage);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -185,9 +190,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxNSW; ++i) { mbar_init(&ms->wfull[i], 1); mbar_init(&ms->wfree[i], 1); }
     for (int i = 0; i < kMaxNSA; ++i) { mbar_init(&ms->afull[i], 4); mbar_init(&ms->afree[i], 1); }
-    for (int i = 0; i < 5; ++i) mbar_init(&ms->dfull[i], 1);
-    mbar_init(&ms->actfull, kEpiWarps);
-    mbar_init(&ms->tfree, kEpiWarps);
+    for (int x = 0; x < 2; ++x) {
+      for (int i = 0; i < 5; ++i) mbar_init(&ms->dfull[x][i], 1);
+      mbar_init(&ms->actfull[x], kEpiWarps);
+      mbar_init(&ms->tfree[x], kEpiWarps);
+    }
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<1>(&ms->tmem_base, 512);
@@ -198,24 +205,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
   const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int kcI = (p.CI + 31) >> 5, kcF = (p.CF + 31) >> 5;
   const bool special = p.xyz != nullptr;
-  const uint32_t last_col0 = p.nblk <= 2 ? 256u : 0u;
+  // Tiles are taken in rounds of nctx: tile ordinal t = round * nctx + context.  Within a round the roles walk
+  // (layer 1, ctx 0), (layer 1, ctx 1), (layer 2, ctx 0), ... so one context's epilogue runs under the other's MMAs.
+  const int NX = p.nctx;
+  const int rounds = (my_tiles + NX - 1) / NX;
   TFP_DECL
 
   if (warp == kWarpTma) {
     // ============================================================ weight pieces through the W ring
     if (lane == 0) {
       uint32_t w = 0;
-      for (int t = 0; t < my_tiles; ++t) {
+      for (int r = 0; r < rounds; ++r) {
         for (int l = 0; l < NL; ++l) {
           const bool last = l == NL - 1;
           const int pieces = last ? p.nblk * p.kc[l] : p.kc[l];
           const uint32_t bytes = last ? 128u * 128u : (uint32_t)((p.c_out[l] + 15) & ~15) * 128u;
           const uint8_t* src = p.w_img[l];
-          for (int i = 0; i < pieces; ++i, ++w) {
-            const int st = w % kNSW;
-            TFP_WAIT(0, &ms->wfree[st], ((w / kNSW) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&ms->wfull[st], bytes);
-            tma_bulk_g2s(wring + st * kWStage, src + (size_t)i * bytes, bytes, &ms->wfull[st]);
+          for (int x = 0; x < NX; ++x) {
+            if (r * NX + x >= my_tiles) break;
+            for (int i = 0; i < pieces; ++i, ++w) {
+              const int st = w % kNSW;
+              TFP_WAIT(0, &ms->wfree[st], ((w / kNSW) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(&ms->wfull[st], bytes);
+              tma_bulk_g2s(wring + st * kWStage, src + (size_t)i * bytes, bytes, &ms->wfull[st]);
+            }
           }
         }
       }
@@ -223,47 +236,50 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
     }
   } else if (warp == kWarpMma) {
     // ============================================================ MMA issue
-    uint32_t w = 0, a = 0, n_act = 0;
-    const uint32_t act_addr = smem_u32(act);
-    for (int t = 0; t < my_tiles; ++t) {
-      if (t > 0 && p.nblk > 2) TFP_WAIT(3, &ms->tfree, (uint32_t)(t - 1) & 1u);      // last-layer blocks overlap the hidden columns
+    uint32_t w = 0, a = 0;
+    uint32_t n_act[2] = {0, 0};
+    for (int r = 0; r < rounds; ++r) {
       for (int l = 0; l < NL; ++l) {
         const bool last = l == NL - 1;
-        if (l > 0) {
-          TFP_WAIT(2, &ms->actfull, (n_act++) & 1u);
-          if (last && t > 0 && p.nblk <= 2) TFP_WAIT(3, &ms->tfree, (uint32_t)(t - 1) & 1u);
-        }
         const int KC = p.kc[l];
         const int nb = last ? p.nblk : 1;
         const uint32_t idesc = last ? uidesc_tf32(128, 128) : uidesc_tf32(128, (p.c_out[l] + 15) & ~15);
-        for (int blk = 0; blk < nb; ++blk) {
-          const uint32_t d = tmem + (last ? last_col0 + 128u * blk : 0u);
-          for (int c = 0; c < KC; ++c, ++w) {
-            const int ws = w % kNSW;
-            TFP_WAIT(0, &ms->wfull[ws], (w / kNSW) & 1u);
-            int as = 0;
-            int ksteps = 4;
-            if (l == 0) {
-              as = a % kNSA;
-              TFP_WAIT(1, &ms->afull[as], (a / kNSA) & 1u);
-              if (special && c == KC - 1) ksteps = 1;
-            }
-            tc_fence_after_sync();
-            if (elect_one()) {
-              const uint32_t wa = smem_u32(wring + ws * kWStage);
-              const uint32_t xa = l == 0 ? smem_u32(aring + as * kChunk) : act_addr + (uint32_t)c * kChunk;
-              const uint64_t dw = udesc_sw128(wa), dx = udesc_sw128(xa);
-              for (int k = 0; k < ksteps; ++k) {
-                // hidden: D[rows, cout] = X . W^T; last: D[cout, rows] = W . X^T
-                if (last) umma_tf32(d, dw + 2 * k, dx + 2 * k, idesc, (c | k) != 0);
-                else umma_tf32(d, dx + 2 * k, dw + 2 * k, idesc, (c | k) != 0);
+        for (int x = 0; x < NX; ++x) {
+          if (r * NX + x >= my_tiles) break;
+          const uint32_t act_addr = smem_u32(act) + (uint32_t)(x * p.act_bytes);
+          const uint32_t tctx = tmem + (uint32_t)(x * p.ctx_cols);
+          // the context's TMEM columns are reused by every layer: its previous tile must have been drained
+          if (l == 0 && r > 0) TFP_WAIT(3, &ms->tfree[x], (uint32_t)(r - 1) & 1u);
+          if (l > 0) TFP_WAIT(2, &ms->actfull[x], (n_act[x]++) & 1u);
+          for (int blk = 0; blk < nb; ++blk) {
+            const uint32_t d = tctx + (last ? 128u * blk : 0u);
+            for (int c = 0; c < KC; ++c, ++w) {
+              const int ws = w % kNSW;
+              TFP_WAIT(0, &ms->wfull[ws], (w / kNSW) & 1u);
+              int as = 0;
+              int ksteps = 4;
+              if (l == 0) {
+                as = a % kNSA;
+                TFP_WAIT(1, &ms->afull[as], (a / kNSA) & 1u);
+                if (special && c == KC - 1) ksteps = 1;
               }
-              umma_commit_to<1>(&ms->wfree[ws]);
-              if (l == 0) umma_commit_to<1>(&ms->afree[as]);
-              if (c == KC - 1) umma_commit_to<1>(&ms->dfull[last ? 1 + blk : 0]);
+              tc_fence_after_sync();
+              if (elect_one()) {
+                const uint32_t wa = smem_u32(wring + ws * kWStage);
+                const uint32_t xa = l == 0 ? smem_u32(aring + as * kChunk) : act_addr + (uint32_t)c * kChunk;
+                const uint64_t dw = udesc_sw128(wa), dx = udesc_sw128(xa);
+                for (int k = 0; k < ksteps; ++k) {
+                  // hidden: D[rows, cout] = X . W^T; last: D[cout, rows] = W . X^T
+                  if (last) umma_tf32(d, dw + 2 * k, dx + 2 * k, idesc, (c | k) != 0);
+                  else umma_tf32(d, dx + 2 * k, dw + 2 * k, idesc, (c | k) != 0);
+                }
+                umma_commit_to<1>(&ms->wfree[ws]);
+                if (l == 0) umma_commit_to<1>(&ms->afree[as]);
+                if (c == KC - 1) umma_commit_to<1>(&ms->dfull[x][last ? 1 + blk : 0]);
+              }
+              __syncwarp();
+              if (l == 0) ++a;
             }
-            __syncwarp();
-            if (l == 0) ++a;
           }
         }
       }
@@ -358,23 +374,26 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
     const int eg = warp >> 2, q = warp & 3;       // a warp may only read TMEM lanes 32 * (warp % 4) .. + 31
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     const int row = q * 32 + lane;
-    uint32_t n_d0 = 0;
+    uint32_t n_d0[2] = {0, 0};
     const int c_last = p.c_out[NL - 1];
     // last layer: a unit = the 32-column groups one max-pool window spans (1 for nsample <= 32, 2 for 64, 4 for 128)
     const int ug = p.S <= 32 ? 1 : p.S >> 5;
     const int upb = 4 / ug;
     const int items = p.nblk * upb;
-    for (int t = 0; t < my_tiles; ++t) {
-      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+    for (int r = 0; r < rounds; ++r) {
       for (int l = 0; l < NL - 1; ++l) {
-        TFP_WAIT(4, &ms->dfull[0], (n_d0++) & 1u);
+       for (int x = 0; x < NX; ++x) {
+        if (r * NX + x >= my_tiles) break;
+        const uint32_t lane_x = lane_addr + (uint32_t)(x * p.ctx_cols);
+        const uint32_t act_x = smem_u32(act) + (uint32_t)(x * p.act_bytes);
+        TFP_WAIT(4, &ms->dfull[x][0], (n_d0[x]++) & 1u);
         tc_fence_after_sync();
         const int groups = p.c_out[l] >> 5;
         const float* bias = p.bias[l];
         for (int g = eg; g < groups; g += 4) {
           uint32_t v[32];
           TFP_T(e0);
-          tmem_ld_x32(lane_addr + (uint32_t)(g * 32), v);
+          tmem_ld_x32(lane_x + (uint32_t)(g * 32), v);
           float bv[32];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
@@ -384,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
           tmem_ld_fence();
           TFP_T(e1);
           TFP_ADD(0, e0, e1);
-          const uint32_t dst = smem_u32(act) + (uint32_t)g * kChunk;
+          const uint32_t dst = act_x + (uint32_t)g * kChunk;
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             uint32_t o[4];
@@ -400,14 +419,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ms->actfull);
+        if (lane == 0) mbar_arrive(&ms->actfull[x]);
         TFP_T(e4);
         TFP_ADD(2, e3, e4);
+       }
       }
       // last layer, transposed: lane = output channel, TMEM column = row of the tile
+     for (int x = 0; x < NX; ++x) {
+      const int t = r * NX + x;
+      if (t >= my_tiles) break;
+      const uint32_t lane_x = lane_addr + (uint32_t)(x * p.ctx_cols);
+      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
       const long long pt0 = (tile * 128) >> p.log2S;       // first point of the tile (128 % S == 0)
       for (int blk = 0; blk < p.nblk; ++blk) {
-        TFP_WAIT(5, &ms->dfull[1 + blk], (uint32_t)t & 1u);
+        TFP_WAIT(5, &ms->dfull[x][1 + blk], (uint32_t)r & 1u);
       }
       tc_fence_after_sync();
       TFP_T(e5);
@@ -437,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
         for (int g = g0; g < g0 + ug; ++g) {
           uint32_t v[32];
           TFP_T(f2);
-          tmem_ld_x32(lane_addr + last_col0 + (uint32_t)(blk * 128 + g * 32), v);
+          tmem_ld_x32(lane_x + (uint32_t)(blk * 128 + g * 32), v);
           tmem_ld_fence();
           TFP_T(f3);
           TFP_ADD(7, f2, f3);
@@ -457,7 +482,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tf32_kernel(const TfParams p)
       TFP_ADD(3, e5, e6);
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ms->tfree);
+      if (lane == 0) mbar_arrive(&ms->tfree[x]);
+     }
     }
     if (warp == 0) TFP_REPORT("epilogue");
   }
@@ -570,12 +596,18 @@ extern "C" int sad_mlp_tf32_fwd(int B, int N, int P, int S, const float* known_c
   p.act_bytes = (max_h / 32) * kChunk;
   p.wstage = (piece + 1023) & ~1023;
   const int usable = kSmemMax - 1024 - kMisc;
-  p.nsw = (usable - p.act_bytes - 2 * kChunk) / p.wstage;
+  // two tile contexts when two activation buffers leave room for the rings and both fit the 512 TMEM columns: one
+  // context's epilogue then runs under the other's MMAs
+  p.ctx_cols = max_h > 128 * p.nblk ? max_h : 128 * p.nblk;
+  p.nctx = (2 * p.ctx_cols <= 512 && usable - 2 * p.act_bytes - 2 * kChunk >= 3 * p.wstage && p.num_tiles > 1) ? 2 : 1;
+  if (p.ctx_cols > 512) return fail(SAD_EUNSUPPORTED, "mlp_tf32: last layer too wide for TMEM");
+  const int act_total = p.nctx * p.act_bytes;
+  p.nsw = (usable - act_total - 2 * kChunk) / p.wstage;
   if (p.nsw > kMaxNSW) p.nsw = kMaxNSW;
   if (p.nsw < 2) return fail(SAD_EUNSUPPORTED, "mlp_tf32: layers too wide for shared memory");
-  p.nsa = 2 + (usable - p.act_bytes - p.nsw * p.wstage - 2 * kChunk) / kChunk;
+  p.nsa = 2 + (usable - act_total - p.nsw * p.wstage - 2 * kChunk) / kChunk;
   if (p.nsa > kMaxNSA) p.nsa = kMaxNSA;
-  const int kSmem = 1024 + p.act_bytes + p.nsa * kChunk + p.nsw * p.wstage + kMisc;
+  const int kSmem = 1024 + act_total + p.nsa * kChunk + p.nsw * p.wstage + kMisc;
   static bool configured = false;
   if (!configured) {
     SAD_CUDA_OK(cudaFuncSetAttribute(mlp_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
