@@ -68,11 +68,25 @@ SIGNATURES = {
                        _c_int, _vp],
     "sad_three_interpolate_cl_fwd": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "sad_cf_to_cl_bf16": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
+    "sad_engine_submit": [_vp, _vp],
 }
 _RESTYPES = {"sad_last_error_string": ctypes.c_char_p,
              "sad_launch_count": ctypes.c_ulonglong, "sad_scene_grid_workspace_bytes": ctypes.c_longlong, "sad_mlp_weight_image_bytes": ctypes.c_longlong,
              "sad_sa_mlp_image_bytes": ctypes.c_longlong, "sad_pw_mlp_image_bytes": ctypes.c_longlong,
              "sad_mlp_tf32_image_bytes": ctypes.c_longlong, "sad_sa_mlp_dedup_workspace_bytes": ctypes.c_longlong}
+
+SUBMIT_MAX_COPIES = 4
+
+
+class SubmitDesc(ctypes.Structure):
+    """include/sad_ops.h sad_submit_desc"""
+    _fields_ = [("graph_exec", _vp), ("wait_event", _vp), ("done_event", _vp),
+                ("n_in", _c_int), ("n_out", _c_int),
+                ("in_dst", _vp * SUBMIT_MAX_COPIES), ("in_src", _vp * SUBMIT_MAX_COPIES),
+                ("in_bytes", ctypes.c_size_t * SUBMIT_MAX_COPIES),
+                ("out_dst", _vp * SUBMIT_MAX_COPIES), ("out_src", _vp * SUBMIT_MAX_COPIES),
+                ("out_bytes", ctypes.c_size_t * SUBMIT_MAX_COPIES)]
+
 
 class MlpOpts(ctypes.Structure):
     """include/sad_ops.h sad_mlp_opts"""

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(PKG)
 LIB_DIR = os.path.join(PKG, "lib")
 OBJ_DIR = os.path.join(PKG, "build")
 SO = os.path.join(LIB_DIR, "libsad_b200.so")
-SOURCES = ["capi.cu", "fps.cu", "fps_cull.cu", "grid.cu", "search.cu", "gather.cu", "interp.cu", "mlp.cu", "mlp_sa.cu", "mlp_pw.cu", "mlp_tf32.cu", "scatter.cu"]
+SOURCES = ["capi.cu", "fps.cu", "fps_cull.cu", "grid.cu", "search.cu", "gather.cu", "interp.cu", "mlp.cu", "mlp_sa.cu", "mlp_pw.cu", "mlp_tf32.cu", "scatter.cu", "engine.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

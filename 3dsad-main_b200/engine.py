@@ -26,7 +26,7 @@ from . import _lib
 
 
 class _Slot:
-    __slots__ = ("stream", "xyz", "feat", "size", "graph", "end", "out_host", "done", "busy", "launches")
+    __slots__ = ("stream", "xyz", "feat", "size", "graph", "end", "out_host", "done", "busy", "launches", "desc", "ready")
 
 
 class PipelinedHotPath:
@@ -39,8 +39,16 @@ class PipelinedHotPath:
 
     def __init__(self, model, batch: int, n_points: int, feat_dim: int = 1, slots: int = 3,
                  device: Optional[torch.device] = None, warmup: int = 2, fps_policy: str = "throughput",
-                 mlp_tiles_per_cta: int = 6):
-        """`fps_policy`: "throughput" (default) captures the one-SM-per-scene FPS kernel -- longer per batch, but
+                 mlp_tiles_per_cta: int = 6, native_submit: bool = True, linear_graph: bool = True):
+        """`linear_graph`: capture the batch on ONE stream (no side-stream fork / join of the coordinate-only chain), so
+        the graph is a straight line of kernel nodes: the driver launches those in near-constant time, a forked graph
+        costs ~100 us of host time per launch -- more than the GPU needs to start the batch.  With several batches in
+        flight the intra-batch overlap the fork buys is provided by the other batches anyway; for 1-2 slots pass False
+        (shorter single-batch latency).
+        `native_submit`: queue a batch (event wait, input copies, graph launch, result copies, completion event)
+        with ONE call into libsad_b200 (`sad_engine_submit`) instead of ~10 PyTorch calls; inputs whose shape / dtype /
+        layout differ from the slot's static buffers take the PyTorch path (copy_ converts).
+        `fps_policy`: "throughput" (default) captures the one-SM-per-scene FPS kernel -- longer per batch, but
         about half the SM-time, which is what bounds a pipeline with several batches in flight; "latency" captures the
         cluster kernel (shortest time per batch; right for 1-2 slots)."""
         self.model = model
@@ -58,12 +66,63 @@ class PipelinedHotPath:
         saved_policy = _modules.FPS_POLICY[0]
         _modules.FPS_POLICY[0] = fps_policy
         _mlp.TILES_PER_CTA[0] = int(mlp_tiles_per_cta)
+        self.linear_graph = bool(linear_graph)
+        backbone = getattr(model, "backbone", None)
+        saved_overlap = getattr(backbone, "overlap_geometry", None)
+        if self.linear_graph and saved_overlap is not None:
+            backbone.overlap_geometry = False
         try:
             self._capture(model, batch, n_points, feat_dim, slots, dev, warmup, lib)
         finally:
             _modules.FPS_POLICY[0] = saved_policy
             _mlp.TILES_PER_CTA[0] = 1
+            if saved_overlap is not None:
+                backbone.overlap_geometry = saved_overlap
         self.launches_per_batch = self._slots[0].launches
+        self._lib = lib
+        self.native_submit = bool(native_submit)
+        if self.native_submit:
+            self._prepare_native()
+
+    def _prepare_native(self):
+        """Per slot: the constant part of its sad_submit_desc (graph, destinations, sizes, result copies, completion
+        event).  torch creates an Event's cudaEvent_t on its first record, so every event is recorded once here."""
+        import ctypes
+        with torch.cuda.device(self.device):
+            for s in self._slots:
+                s.done.record(s.stream)
+                s.ready = torch.cuda.Event()
+                s.ready.record(s.stream)
+                d = _lib.SubmitDesc()
+                d.graph_exec = int(s.graph.raw_cuda_graph_exec())
+                d.done_event = int(s.done.cuda_event)
+                d.n_in = 3
+                for i, t in enumerate((s.xyz, s.feat, s.size)):
+                    d.in_dst[i] = t.data_ptr()
+                    d.in_bytes[i] = t.numel() * t.element_size()
+                outs = (s.end["cluster_xyz"], s.end["cluster_features"])
+                for i, (h, t) in enumerate(zip(s.out_host, outs)):
+                    if not (t.is_contiguous() and h.is_contiguous() and h.shape == t.shape and h.dtype == t.dtype):
+                        self.native_submit = False       # results need a converting copy: PyTorch path
+                        return
+                    d.out_dst[i] = h.data_ptr()
+                    d.out_src[i] = t.data_ptr()
+                    d.out_bytes[i] = t.numel() * t.element_size()
+                s.desc = d
+            torch.cuda.synchronize(self.device)
+        self._byref = ctypes.byref
+
+    def _native_ok(self, s, xyz, feat, size) -> bool:
+        return (self.native_submit and xyz.shape == s.xyz.shape and feat.shape == s.feat.shape and size.shape == s.size.shape
+                and xyz.dtype == feat.dtype == size.dtype == torch.float32
+                and xyz.is_contiguous() and feat.is_contiguous() and size.is_contiguous())
+
+    def _submit_native(self, s, xyz, feat, size, wait_event, to_host: bool):
+        d = s.desc
+        d.in_src[0], d.in_src[1], d.in_src[2] = xyz.data_ptr(), feat.data_ptr(), size.data_ptr()
+        d.wait_event = int(wait_event.cuda_event) if wait_event is not None else None
+        d.n_out = 2 if to_host else 0
+        _lib.check(self._lib.sad_engine_submit(self._byref(d), s.stream.cuda_stream), "sad_engine_submit")
 
     def _capture(self, model, batch, n_points, feat_dim, slots, dev, warmup, lib):
         with torch.cuda.device(dev), torch.no_grad():
@@ -118,11 +177,14 @@ class PipelinedHotPath:
         or dropped right after it are safe."""
         i, s = self._acquire()
         if after is None:
-            after = torch.cuda.Event()
+            after = s.ready if self.native_submit else torch.cuda.Event()
             after.record(torch.cuda.current_stream(self.device))
         for t in (xyz, feat, size):
             if t.is_cuda:
                 t.record_stream(s.stream)
+        if self._native_ok(s, xyz, feat, size):
+            self._submit_native(s, xyz, feat, size, after, to_host)
+            return i
         with torch.cuda.stream(s.stream):
             s.stream.wait_event(after)
             s.xyz.copy_(xyz, non_blocking=True)
@@ -139,6 +201,9 @@ class PipelinedHotPath:
     def submit_host(self, xyz_host, feat_host, size_host, after: Optional[torch.cuda.Event] = None) -> int:
         """Host (pinned) buffers in, pinned host results out; everything queued on the slot's stream."""
         i, s = self._acquire()
+        if self._native_ok(s, xyz_host, feat_host, size_host):
+            self._submit_native(s, xyz_host, feat_host, size_host, after, True)
+            return i
         with torch.cuda.stream(s.stream):
             if after is not None:
                 s.stream.wait_event(after)

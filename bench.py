@@ -473,7 +473,8 @@ def run_ours(args):
     set_bytes = sum(int(h.numel() * h.element_size()) for h in sets[0]["host"])
 
     eng = PipelinedHotPath(model, B_PER_GPU, N_POINTS, feat_dim=1, slots=args.slots, device=dev,
-                           fps_policy=args.fps_policy, mlp_tiles_per_cta=args.tpc)
+                           fps_policy=args.fps_policy, mlp_tiles_per_cta=args.tpc, native_submit=not args.py_submit,
+                           linear_graph=not args.forked_graph)
     main = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -489,8 +490,10 @@ def run_ours(args):
     t_wall0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(main)
+    t_sub0 = time.perf_counter()
     for k in range(args.steps):
         eng.submit_device(*sets[(args.warmup + k) % NSETS]["dev"], after=ev0 if k < eng.slots else None)
+    host_submit_us = (time.perf_counter() - t_sub0) * 1e6 / args.steps      # includes back-pressure waits once steps > slots
     eng.join(main)
     ev1.record(main)
     barrier()
@@ -572,6 +575,9 @@ def run_ours(args):
                                          "sustained rate (python bench.py without flags runs 200 steps)",
                     "fps_policy": f"{args.fps_policy} (throughput = one SM per scene for the 40k-point FPS, latency = "
                                   "4-SM cluster per scene; identical indices)",
+                    "submit": ("one sad_engine_submit call per batch (C ABI)" if eng.native_submit else "PyTorch calls"),
+                    "graph": ("straight-line (one stream per batch)" if eng.linear_graph else "forked (side streams inside the batch)"),
+                    "host_submit_us_per_step": round(host_submit_us, 1),
                     "batch_latency_loaded_ms": round(eng.slots * (total_ms / args.steps), 4),
                     "batch_latency_ms": round(lat[len(lat) // 2], 4),
                     "search_dtype": "f32 (bit-exact indices)", "mlp_dtype": f"{args.mlp_dtype} in / f32 accumulate"},
@@ -628,6 +634,8 @@ def main():
     ap.add_argument("--points", type=int, default=40000, help="points per scene (default = configs[1])")
     ap.add_argument("--mlp-dtype", default="bf16", choices=["bf16", "tf32"],
                     help="operand precision of the fused MLP stages (tf32: fp32 activations, csrc/mlp_tf32.cu)")
+    ap.add_argument("--forked-graph", action="store_true", help="capture the coordinate-only chain on side streams (forked graph; comparison)")
+    ap.add_argument("--py-submit", action="store_true", help="queue batches through PyTorch calls instead of sad_engine_submit (comparison)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-hbm", action="store_true", help="skip the hbm_kernels micro-benchmark block")
     args = ap.parse_args()

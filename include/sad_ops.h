@@ -316,6 +316,27 @@ SAD_API int sad_cf_to_cl_bf16(int B, int C, int N, const float* in_cf, void* out
 /* Number of kernels this library has launched in this process (all threads, monotonic). */
 SAD_API unsigned long long sad_launch_count(void);
 
+/* ---- pipelined executor, host side (engine.PipelinedHotPath) ------------------------------------------------------
+ * One batch = [stream waits for `wait_event`] -> n_in async copies (host-pinned or device sources; the direction is
+ * inferred from the pointers) -> launch of the slot's instantiated CUDA graph -> n_out async copies of the results
+ * -> `done_event` recorded, all queued on `stream` by ONE call (no Python between the driver calls: the per-batch
+ * host cost is what bounds how fast a pipeline of `slots` batches fills).  Handles are the CUDA runtime's
+ * (cudaGraphExec_t / cudaEvent_t); NULL wait_event / done_event are skipped.  Launches no kernel of its own. */
+#define SAD_SUBMIT_MAX_COPIES 4
+typedef struct {
+  void* graph_exec;                            /* cudaGraphExec_t */
+  void* wait_event;                            /* cudaEvent_t or NULL */
+  void* done_event;                            /* cudaEvent_t or NULL */
+  int n_in, n_out;
+  void* in_dst[SAD_SUBMIT_MAX_COPIES];
+  const void* in_src[SAD_SUBMIT_MAX_COPIES];
+  size_t in_bytes[SAD_SUBMIT_MAX_COPIES];
+  void* out_dst[SAD_SUBMIT_MAX_COPIES];
+  const void* out_src[SAD_SUBMIT_MAX_COPIES];
+  size_t out_bytes[SAD_SUBMIT_MAX_COPIES];
+} sad_submit_desc;
+SAD_API int sad_engine_submit(const sad_submit_desc* desc, sad_stream_t stream);
+
 /* a1 with an explicit thread-block-cluster size (tests / tools: 1,2,4,8,16; 0 = the built-in heuristic, i.e.
  * sad_furthest_point_sample_fwd).  Results never depend on it. */
 SAD_API int sad_furthest_point_sample_cs_fwd(int B, int N, int npoint, const float* xyz, int32_t* idx, int cluster_size,
