@@ -94,7 +94,11 @@ class PipelinedHotPath:
                 s.ready = torch.cuda.Event()
                 s.ready.record(s.stream)
                 d = _lib.SubmitDesc()
-                d.graph_exec = int(s.graph.raw_cuda_graph_exec())
+                try:
+                    d.graph_exec = int(s.graph.raw_cuda_graph_exec())
+                except RuntimeError:                      # a keep_graph=True capture is instantiated on demand
+                    s.graph.instantiate()
+                    d.graph_exec = int(s.graph.raw_cuda_graph_exec())
                 d.done_event = int(s.done.cuda_event)
                 d.n_in = 3
                 for i, t in enumerate((s.xyz, s.feat, s.size)):
@@ -153,6 +157,11 @@ class PipelinedHotPath:
                     s.end = model(s.xyz, s.feat, s.size)
                 s.launches = int(lib.sad_launch_count() - l0)
                 s.out_host = model.make_host_outputs(batch)
+            # the first launch of an instantiated graph uploads it to the device (~60 us of host time per graph,
+            # measured): pay that here, once per slot, not inside the caller's first `slots` submissions
+            for s in self._slots:
+                with torch.cuda.stream(s.stream):
+                    s.graph.replay()
             torch.cuda.synchronize(dev)
 
     # ------------------------------------------------------------------ submission
@@ -190,6 +199,43 @@ class PipelinedHotPath:
             s.xyz.copy_(xyz, non_blocking=True)
             s.feat.copy_(feat, non_blocking=True)
             s.size.copy_(size, non_blocking=True)
+            s.graph.replay()
+            if to_host:
+                s.out_host[0].copy_(s.end["cluster_xyz"], non_blocking=True)
+                s.out_host[1].copy_(s.end["cluster_features"], non_blocking=True)
+            s.done.record(s.stream)
+        return i
+
+    def slot_inputs(self, index: int):
+        """The static device input buffers (xyz, feat, size) of slot `index`: a producer that can write a batch
+        straight into them (a decoder, a previous pipeline stage) skips the copy of submit_device; `next_slot` is the
+        slot the next submit_* call takes."""
+        s = self._slots[index]
+        return s.xyz, s.feat, s.size
+
+    @property
+    def next_slot(self) -> int:
+        return self._next
+
+    @torch.no_grad()
+    def submit_resident(self, after: Optional[torch.cuda.Event] = None, to_host: bool = False) -> int:
+        """Zero-copy submission: run the next slot's graph on what its input buffers (slot_inputs) hold.  The buffers
+        must have been written on a stream the slot's stream is ordered after: pass the event recorded after the
+        writes as `after` (None: the caller guarantees they completed, e.g. they were filled before a synchronize)."""
+        i, s = self._acquire()
+        if self.native_submit:
+            d = s.desc
+            d.n_in = 0
+            try:
+                d.wait_event = int(after.cuda_event) if after is not None else None
+                d.n_out = 2 if to_host else 0
+                _lib.check(self._lib.sad_engine_submit(self._byref(d), s.stream.cuda_stream), "sad_engine_submit")
+            finally:
+                d.n_in = 3
+            return i
+        with torch.cuda.stream(s.stream):
+            if after is not None:
+                s.stream.wait_event(after)
             s.graph.replay()
             if to_host:
                 s.out_host[0].copy_(s.end["cluster_xyz"], non_blocking=True)

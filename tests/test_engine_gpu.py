@@ -64,6 +64,35 @@ def test_device_submission_and_launch_count(setup):
     assert eng.launches_per_batch >= 20      # kernels of libsad_b200 captured per batch
 
 
+def test_resident_submission_and_forked_pytorch_path(setup):
+    """submit_resident (zero-copy: the batch is written straight into the slot's input buffers) and the executor's other
+    configuration (forked graph, PyTorch-call submission) return exactly what the default one does."""
+    from sad_b200.engine import PipelinedHotPath
+    model, eng, batches = setup
+    dev_in = tuple(t.to(DEV) for t in batches[1])
+    t = eng.submit_device(*dev_in, to_host=True)
+    cx, cf = eng.result(t)
+    want_x, want_f = cx.numpy().copy(), cf.numpy().copy()
+    for dst, src in zip(eng.slot_inputs(eng.next_slot), dev_in):
+        dst.copy_(src)
+    ev = torch.cuda.Event()
+    ev.record()
+    t = eng.submit_resident(after=ev, to_host=True)
+    cx, cf = eng.result(t)
+    assert np.array_equal(cx.numpy(), want_x) and np.array_equal(cf.numpy(), want_f)
+    other = PipelinedHotPath(model, eng.batch, eng.n_points, slots=2, device=torch.device(DEV), native_submit=False,
+                             linear_graph=False)
+    assert not other.native_submit and not other.linear_graph and eng.native_submit and eng.linear_graph
+    for submit in (lambda: other.submit_host(*batches[1]), lambda: other.submit_device(*dev_in, to_host=True)):
+        cx, cf = other.result(submit())
+        assert np.array_equal(cx.numpy(), want_x) and np.array_equal(cf.numpy(), want_f)
+    for dst, src in zip(other.slot_inputs(other.next_slot), dev_in):
+        dst.copy_(src)
+    torch.cuda.synchronize()
+    cx, cf = other.result(other.submit_resident(to_host=True))
+    assert np.array_equal(cx.numpy(), want_x) and np.array_equal(cf.numpy(), want_f)
+
+
 def _close_elementwise(got, want, tol, rel, floor_frac=0.25, what=""):
     """Norm-wise bar (max |err| <= tol * max |want|) plus an element-wise relative bar above a magnitude floor."""
     scale = max(1e-6, float(np.abs(want).max()))

@@ -1,20 +1,17 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out/sub
-timeout 600 python -m pytest tests/test_engine_gpu.py -x -q -m gpu > gpurun_out/sub/tests.log 2>&1; echo "engine tests exit $?"; tail -3 gpurun_out/sub/tests.log
 run() { n=$1; shift
   timeout 300 "$@" > gpurun_out/sub/$n.json 2> gpurun_out/sub/$n.err
   python - <<P
 import json
 try:
     d=json.load(open("gpurun_out/sub/$n.json"))
-    print("$n", d["value"], d["e2e"]["value"], d["ms_per_step"], d["run"].get("host_submit_us_per_step"), d["run"].get("batch_latency_ms"), d["gpu_launches_per_step"], flush=True)
+    print("$n", d["value"], d["e2e"]["value"], d["ms_per_step"], d["run"].get("host_submit_us_per_step"), d["run"].get("host_submit_us_first_calls")[:8], flush=True)
 except Exception as e:
     print("$n failed", e); print(open("gpurun_out/sub/$n.err").read()[-1500:])
 P
 }
-run linear20 python bench.py --steps 20 --warmup 3 --no-hbm --no-cpu
-run forked20 python bench.py --steps 20 --warmup 3 --no-hbm --no-cpu --forked-graph
-run linear20b python bench.py --steps 20 --warmup 3 --no-hbm --no-cpu
-run linear200 python bench.py --steps 200 --no-hbm --no-cpu
-run forked200 python bench.py --steps 200 --no-hbm --no-cpu --forked-graph
+run res20 python bench.py --steps 20 --warmup 3 --no-hbm --no-cpu
+run res20b python bench.py --steps 20 --warmup 3 --no-hbm --no-cpu
+run res200 python bench.py --steps 200 --no-hbm --no-cpu
