@@ -51,6 +51,15 @@ def test_argument_validation_returns_codes_without_a_gpu(lib):
     assert b"m >= 3" in lib.sad_last_error_string()
     assert lib.sad_ball_query_fwd(1, 16, 4, 0.5, 0, None, None, None, None) == -1
     assert lib.sad_furthest_point_sample_fwd(1, 300000, 4, ctypes.c_void_p(16), ctypes.c_void_p(16), None) == -3
+    # the executor's submit call validates its descriptor before touching the CUDA runtime
+    from sad_b200 import _lib
+    assert lib.sad_engine_submit(None, None) == -1
+    assert b"null descriptor" in lib.sad_last_error_string()
+    d = _lib.SubmitDesc()
+    d.graph_exec, d.n_in = 16, _lib.SUBMIT_MAX_COPIES + 1
+    assert lib.sad_engine_submit(ctypes.byref(d), None) == -1
+    assert b"bad copy counts" in lib.sad_last_error_string()
+    assert ctypes.sizeof(_lib.SubmitDesc) == 3 * 8 + 2 * 4 + 6 * _lib.SUBMIT_MAX_COPIES * 8      # layout of sad_submit_desc
     # empty batches are a no-op success
     assert lib.sad_furthest_point_sample_fwd(0, 16, 4, None, None, None) == 0
     assert lib.sad_grouping_operation_fwd(0, 4, 16, 4, 4, None, None, None, None) == 0
