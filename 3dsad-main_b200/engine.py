@@ -26,7 +26,7 @@ from . import _lib
 
 
 class _Slot:
-    __slots__ = ("stream", "xyz", "feat", "size", "graph", "end", "out_host", "done", "busy", "launches", "desc", "ready")
+    __slots__ = ("stream", "xyz", "feat", "size", "graph", "end", "out_host", "done", "busy", "launches", "desc", "ready", "hold")
 
 
 class PipelinedHotPath:
@@ -122,6 +122,9 @@ class PipelinedHotPath:
                 and xyz.is_contiguous() and feat.is_contiguous() and size.is_contiguous())
 
     def _submit_native(self, s, xyz, feat, size, wait_event, to_host: bool):
+        # the copies are raw cudaMemcpyAsync calls: nothing tells PyTorch's pinned-host / device allocators that the
+        # sources are in use, so the slot keeps them alive until its batch has left the GPU (result / reuse / drain)
+        s.hold = (xyz, feat, size)
         d = s.desc
         d.in_src[0], d.in_src[1], d.in_src[2] = xyz.data_ptr(), feat.data_ptr(), size.data_ptr()
         d.wait_event = int(wait_event.cuda_event) if wait_event is not None else None
@@ -137,6 +140,7 @@ class PipelinedHotPath:
                 s.feat = torch.zeros((batch, feat_dim, n_points), dtype=torch.float32, device=dev)
                 s.size = torch.ones((batch, self.n_clusters, 3), dtype=torch.float32, device=dev)
                 s.busy = False
+                s.hold = None
                 s.done = torch.cuda.Event()
                 self._slots.append(s)
             # well-formed warm-up input (weights get packed, kernels configured) before capture
@@ -175,6 +179,7 @@ class PipelinedHotPath:
         s = self._slots[i]
         if s.busy:
             s.done.synchronize()      # back-pressure: the slot's previous batch must have left the GPU
+        s.hold = None
         s.busy = True
         return i, s
 
@@ -267,6 +272,7 @@ class PipelinedHotPath:
         s = self._slots[ticket]
         s.done.synchronize()
         s.busy = False
+        s.hold = None
         return s.out_host
 
     def outputs(self, ticket: int) -> dict:
@@ -285,6 +291,7 @@ class PipelinedHotPath:
             if s.busy:
                 s.done.synchronize()
                 s.busy = False
+                s.hold = None
 
 
 class ShardedHotPath:
