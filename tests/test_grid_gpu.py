@@ -176,3 +176,30 @@ def test_fps_scheduling_policy_never_changes_the_result(ops, N, npoint):
         assert np.array_equal(got.cpu().numpy(), want), policy
     with pytest.raises(KeyError):
         ops.furthest_point_sample(x, npoint, grid, "fastest")
+
+
+@pytest.mark.parametrize("B,N,npoint,quant,kind", [
+    (1, 1, 1, None, "uniform"), (2, 5, 9, None, "uniform"), (3, 33, 2, None, "uniform"), (2, 64, 3, None, "uniform"),
+    (2, 255, 64, 0.5, "uniform"),                        # lattice: many exact ties, most picks duplicates at the end
+    (2, 1000, 300, None, "blobs"), (4, 2048, 1024, None, "surface"),
+    (2, 4097, 200, 0.25, "uniform"),                     # lattice
+    (2, 20000, 512, 0.25, "uniform"),                    # two register sets of bucket state, ties
+    (8, 40000, 2048, None, "surface"),                   # the benchmark's sampling (three register sets)
+    (2, 40000, 2500, 0.05, "surface"),                   # more picks than the output ring holds, ties
+    (1, 46000, 300, None, "blobs"),                      # the largest scene whose min-distances fit shared memory
+])
+def test_throughput_fps_matches_oracle(ops, B, N, npoint, quant, kind):
+    """The one-SM-per-scene kernel (throughput policy) over its whole range of shapes: one to three register sets of
+    bucket state, ties, more picks than points, more picks than the output ring holds."""
+    rng = np.random.default_rng(N * 11 + npoint)
+    xyz = scene(rng, B, N, quant, kind)
+    want = C.furthest_point_sample(xyz, npoint)
+    x = cu(xyz)
+    got = ops.furthest_point_sample(x, npoint, ops.build_scene_grid(x), "throughput")
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_throughput_fps_all_points_equal(ops):
+    p = np.ones((2, 300, 3), np.float32)
+    x = cu(p)
+    assert ops.furthest_point_sample(x, 5, ops.build_scene_grid(x), "throughput").cpu().tolist() == [[0] * 5] * 2

@@ -13,9 +13,10 @@ pol = sys.argv[2] if len(sys.argv) > 2 else "throughput"
 x = torch.from_numpy(make_scenes(B, 40000, "surface")[0]).cuda()
 g = ops.build_scene_grid(x)
 ref = ops.furthest_point_sample(x, 2048, g)
-ts = []
-for _ in range(4):
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); got = ops.furthest_point_sample(x, 2048, g, pol); b.record(); torch.cuda.synchronize()
-    ts.append(a.elapsed_time(b))
-print(f"B={B} {pol}: {min(ts):.3f} ms  ({1e3 * min(ts) / 2047:.3f} us per pick)  equal to the cluster kernel: {bool((got == ref).all())}", flush=True)
+for variant in (0,):
+    ts = []
+    for _ in range(4):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); got = ops.furthest_point_sample(x, 2048, g, pol, False, variant); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    print(f"B={B} {pol} variant {variant}: {min(ts):.3f} ms  ({1e3 * min(ts) / 2047:.3f} us per pick)  equal to the cluster kernel: {bool((got == ref).all())}", flush=True)
