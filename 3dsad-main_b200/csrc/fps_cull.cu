@@ -567,9 +567,9 @@ extern "C" int sad_furthest_point_sample_grid_policy_fwd(int B, int N, int npoin
   cudaStream_t stream = (cudaStream_t)stream_;
   SAD_REQUIRE(policy == SAD_FPS_LATENCY || policy == SAD_FPS_THROUGHPUT || policy == SAD_FPS_THROUGHPUT_PAIRED,
               "furthest_point_sample_grid: bad policy %d", policy);
-  SAD_REQUIRE(variant == 0 || variant == -1 || variant == 1 || variant == 2 || variant == 4 || variant == 8 || variant == 16,
+  SAD_REQUIRE(variant == 0 || variant == -1 || variant == -2 || variant == 1 || variant == 2 || variant == 4 || variant == 8 || variant == 16,
               "furthest_point_sample_grid: bad variant %d", variant);
-  const int force = variant != 0 ? variant : (policy == SAD_FPS_LATENCY ? 0 : -1);
+  const int force = variant != 0 ? (variant == -2 ? -1 : variant) : (policy == SAD_FPS_LATENCY ? 0 : -1);
   SAD_REQUIRE(B >= 0 && N >= 1 && npoint >= 1, "furthest_point_sample_grid: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
   if (B == 0) return SAD_OK;
   SAD_REQUIRE(xyz && grid_ws && idx, "furthest_point_sample_grid: null pointer");
@@ -613,9 +613,16 @@ extern "C" int sad_furthest_point_sample_grid_policy_fwd(int B, int N, int npoin
     }
     const char* e_nw = sad_tool_env("SAD_FPS1_NW");                                      // tools: warps per scene
     if (!e_nw || atoi(e_nw) != 32) {
-      const int pl = sad_ceil_div(sad_ceil_div(nbk, 16), 32);
-      if (pl <= 1) return launch_cull1<1, 16, true>(B, N, npoint, xyz, grid_ws, idx, stream);
-      if (pl <= 2) return launch_cull1<2, 16, true>(B, N, npoint, xyz, grid_ws, idx, stream);
+      // (register sets R, warps NW) with the fewest lane-rounds of box tests per pick (R x NW) that holds the scene's
+      // buckets: a partly filled last register set costs a full round, so 20 / 24 warps with full sets beat 16 warps
+      // with one more set (40k points: <2,20> 1.10 us per pick, <2,28> 1.11, <2,24> 1.22, <3,16> 1.26, <2,32> 1.34).
+      // variant -2 (tests / tools) keeps to the 16-warp instances.
+      const bool wide = variant != -2;
+      if (nbk <= 16 * 32) return launch_cull1<1, 16, true>(B, N, npoint, xyz, grid_ws, idx, stream);
+      if (wide && nbk <= 20 * 32) return launch_cull1<1, 20, true>(B, N, npoint, xyz, grid_ws, idx, stream);
+      if (nbk <= 16 * 64) return launch_cull1<2, 16, true>(B, N, npoint, xyz, grid_ws, idx, stream);
+      if (wide && nbk <= 20 * 64) return launch_cull1<2, 20, true>(B, N, npoint, xyz, grid_ws, idx, stream);
+      if (wide && nbk <= 24 * 64) return launch_cull1<2, 24, true>(B, N, npoint, xyz, grid_ws, idx, stream);
       return launch_cull1<3, 16, true>(B, N, npoint, xyz, grid_ws, idx, stream);
     }
     if (per_lane32 <= 1) return launch_cull1<1, 32, true>(B, N, npoint, xyz, grid_ws, idx, stream);

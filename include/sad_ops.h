@@ -79,12 +79,13 @@ SAD_API int sad_furthest_point_sample_grid_fwd(int B, int N, int npoint, const f
                                                void* grid_workspace, int32_t* idx, sad_stream_t stream);
 /* Same result, explicit scheduling policy.  SAD_FPS_LATENCY (what sad_furthest_point_sample_grid_fwd uses): the
  * fewest-CTA cluster whose shared memory holds the scene -- shortest time per scene (40k points: 4 SMs, 0.70 us per
- * pick).  SAD_FPS_THROUGHPUT: ONE SM per scene over the L2-resident sorted array (1.5 us per pick, i.e. about half
+ * pick).  SAD_FPS_THROUGHPUT: ONE SM per scene over the L2-resident sorted array (1.1 us per pick, i.e. about 0.4 of
  * the SM-time per scene): what a pipelined caller with other kernels to overlap wants (writes the workspace's
  * min-distance scratch, so two calls must not share a workspace).
  * SAD_FPS_THROUGHPUT_PAIRED: two scenes share one SM (16 warps each): ~30 % less SM-time again, longer per scene.
  * `variant` (tests / tools; results never depend on it): 0 = the policy's kernel; 1,2,4,8,16 = the cluster kernel with
- * at least that many CTAs per scene; -1 = the single-SM kernel. */
+ * at least that many CTAs per scene; -1 = the single-SM kernel; -2 = the single-SM kernel restricted to its 16-warp
+ * instances. */
 #define SAD_FPS_LATENCY 0
 #define SAD_FPS_THROUGHPUT 1
 #define SAD_FPS_THROUGHPUT_PAIRED 2

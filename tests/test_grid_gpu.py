@@ -189,14 +189,17 @@ def test_fps_scheduling_policy_never_changes_the_result(ops, N, npoint):
     (1, 46000, 300, None, "blobs"),                      # the largest scene whose min-distances fit shared memory
 ])
 def test_throughput_fps_matches_oracle(ops, B, N, npoint, quant, kind):
-    """The one-SM-per-scene kernel (throughput policy) over its whole range of shapes: one to three register sets of
-    bucket state, ties, more picks than points, more picks than the output ring holds."""
+    """The one-SM-per-scene kernel (throughput policy) over its whole range of shapes and instances (<R register sets,
+    NW warps>: <1,16> <1,20> <2,16> <2,20> <2,24> <3,16>), ties, more picks than points, more picks than the output
+    ring holds."""
     rng = np.random.default_rng(N * 11 + npoint)
     xyz = scene(rng, B, N, quant, kind)
     want = C.furthest_point_sample(xyz, npoint)
     x = cu(xyz)
-    got = ops.furthest_point_sample(x, npoint, ops.build_scene_grid(x), "throughput")
-    assert np.array_equal(got.cpu().numpy(), want)
+    grid = ops.build_scene_grid(x)
+    for variant in (0, -2):           # 0: the instance with the fewest box-test rounds (16 / 20 / 24 warps); -2: 16 warps only
+        got = ops.furthest_point_sample(x, npoint, grid, "throughput", False, variant)
+        assert np.array_equal(got.cpu().numpy(), want), f"variant {variant}"
 
 
 def test_throughput_fps_all_points_equal(ops):

@@ -13,7 +13,7 @@ pol = sys.argv[2] if len(sys.argv) > 2 else "throughput"
 x = torch.from_numpy(make_scenes(B, 40000, "surface")[0]).cuda()
 g = ops.build_scene_grid(x)
 ref = ops.furthest_point_sample(x, 2048, g)
-for variant in (0,):
+for variant in (0, -2):      # 0 = the policy's kernel, -2 = the 16-warp / three-register-set instance
     ts = []
     for _ in range(4):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
