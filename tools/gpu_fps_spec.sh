@@ -1,11 +1,12 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out/spec
-for d in 3 5 6; do echo "DEPTH=$d"; SAD_B200_LIB=3dsad-main_b200/lib/libsad_d$d.so timeout 100 python tools/fps1_probe.py 8 2>&1 | grep "variant 0"; done
-for t in 3 4 8 12; do
-timeout 300 python bench.py --no-hbm --no-cpu --tpc $t > gpurun_out/spec/tpc$t.json 2>/dev/null
+timeout 100 python tools/fps1_probe.py 8 2>&1 | tail -2
+timeout 300 python -m pytest tests/test_grid_gpu.py -x -q -m gpu -k "fps" > gpurun_out/spec/tests.log 2>&1; echo "fps tests exit $?"; tail -3 gpurun_out/spec/tests.log
+for st in 200 20; do
+timeout 300 python bench.py --no-hbm --no-cpu --steps $st --warmup 3 > gpurun_out/spec/b$st.json 2>/dev/null
 python - <<P
 import json
-d=json.load(open("gpurun_out/spec/tpc$t.json")); print("tpc $t", d["value"], d["e2e"]["value"], d["ms_per_step"])
+d=json.load(open("gpurun_out/spec/b$st.json")); print($st, d["value"], d["e2e"]["value"], d["ms_per_step"], d["run"]["batch_latency_ms"])
 P
 done
