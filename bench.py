@@ -519,6 +519,8 @@ def run_ours(args):
     eng.drain()
     t_wall1 = time.perf_counter()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    if clocks is None and rank == 0:
+        clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled (--no-clocks: tools only, not a bench value)"]}
     total_ms = ev0.elapsed_time(ev1)
 
     # ---- latency of ONE batch in isolation (nothing else in flight), device-timed
