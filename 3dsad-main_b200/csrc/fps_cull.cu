@@ -277,6 +277,13 @@ fps_cull1_kernel(int B, int N, int npoint, const float* __restrict__ xyz, uint8_
   __shared__ __align__(16) float4 s_wrec_[SC][NW];      // per warp: best point {x,y,z,bits(idx)}
   __shared__ uint32_t s_wval_[SC][NW];                  // per warp: its min-dist bits
   __shared__ __align__(16) float4 s_pick_[SC];          // the pick of this round {x,y,z,bits(idx)}, written by warp 0
+  // SC == 1: ONE barrier per pick.  Every warp merges {min-dist bits | inverted original index | warp} into a packed
+  // 64-bit key with a shared-memory max before the barrier; after it every thread reads the winning key and the winning
+  // warp's record itself -- no reduce by warp 0 and no second barrier (ncu: 4 of 20 warps sat at those barriers per
+  // issued instruction).  Keys are triple-buffered (the key of pick j+2 is cleared after pick j's barrier), records
+  // double-buffered (a slow warp may still read pick j's while a fast one writes pick j+1's).
+  __shared__ unsigned long long s_key[3];
+  __shared__ __align__(16) float4 s_wrec2[2][NW];
   static_assert(!(MDS && SC > 1), "two scenes per CTA keep the min-distances in global memory");
 
   const int half = SC > 1 ? (int)threadIdx.x / (NW * 32) : 0;
@@ -346,6 +353,12 @@ fps_cull1_kernel(int B, int N, int npoint, const float* __restrict__ xyz, uint8_
     }
   }
   bool changed = true;
+  unsigned long long ckey = 0ull;                       // this warp's key (warp-uniform), kept while its buckets do not change
+  int k3 = 1;                                           // j % 3
+  if (SC == 1) {
+    if (tid < 3) s_key[tid] = 0ull;
+    cta_sync();
+  }
 #ifdef SAD_FPS_PROFILE
   long long ph[5] = {0, 0, 0, 0, 0}, nupd = 0, nround = 0, tprev = clock64();
 #define SAD_MARK1(i) { const long long tn = clock64(); ph[i] += tn - tprev; tprev = tn; }
@@ -354,66 +367,118 @@ fps_cull1_kernel(int B, int N, int npoint, const float* __restrict__ xyz, uint8_
 #endif
 
   for (int j = 1; j < npoint; ++j) {
-    // ---- this warp's record: its best bucket (rewritten only when one of its buckets changed; records are read
-    // by warp 0 alone, between the two barriers, so one buffer suffices and an unchanged warp does nothing)
-    __syncwarp();
-    if (changed) {
-      uint32_t v = 0u, vi = kInf;
-      int vr = 0;
+    if constexpr (SC == 1) {
+      // ---- this warp's record and key (recomputed only when one of its buckets changed)
+      __syncwarp();
+      const int p = j & 1;
+      if (changed) {
+        uint32_t v = 0u, vi = kInf;
+        int vr = 0;
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const bool valid = (r * 32 + lane) < nslots;
-        const uint32_t x = valid ? __float_as_uint(bmax[r]) : 0u;
-        const uint32_t id = valid ? bidx[r] : kInf;
-        // branch-free on purpose: a divergent compare chain leaves the warp unconverged at the redux below, which
-        // then takes its slow collective path (measured: ~900 instead of ~150 cycles for this block)
-        const bool take = (x > v) | ((x == v) & (id < vi));
-        v = take ? x : v;
-        vi = take ? id : vi;
-        vr = take ? r : vr;
-      }
-      const uint32_t wmax = __reduce_max_sync(FULL, v);
-      const uint32_t widx = __reduce_min_sync(FULL, v == wmax ? vi : kInf);
-      if (widx == kInf) {
-        if (lane == 0) {
-          s_wval[warp] = 0u;
-          s_wrec[warp] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInf));
+        for (int r = 0; r < R; ++r) {
+          const bool valid = (r * 32 + lane) < nslots;
+          const uint32_t x = valid ? __float_as_uint(bmax[r]) : 0u;
+          const uint32_t id = valid ? bidx[r] : kInf;
+          // branch-free on purpose: a divergent compare chain leaves the warp unconverged at the redux below, which
+          // then takes its slow collective path (measured: ~900 instead of ~150 cycles for this block)
+          const bool take = (x > v) | ((x == v) & (id < vi));
+          v = take ? x : v;
+          vi = take ? id : vi;
+          vr = take ? r : vr;
         }
-      } else if (v == wmax && vi == widx) {
-        s_wval[warp] = wmax;
-        s_wrec[warp] = s_best[(vr * 32 + lane) * NW + warp];
+        const uint32_t wmax = __reduce_max_sync(FULL, v);
+        const uint32_t widx = __reduce_min_sync(FULL, v == wmax ? vi : kInf);
+        if (widx == kInf) {                               // no bucket: loses against every real record (key < 32)
+          ckey = (unsigned long long)warp;
+          if (lane == 0) s_wrec2[p][warp] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInf));
+        } else {                                          // max min-dist, ties -> lowest original index (< 2^19)
+          ckey = ((unsigned long long)wmax << 32) | ((unsigned long long)(0x7FFFFu - widx) << 5) | (unsigned long long)warp;
+          if (v == wmax && vi == widx) s_wrec2[p][warp] = s_best[(vr * 32 + lane) * NW + warp];
+        }
+      } else if (lane == 0) {
+        s_wrec2[p][warp] = s_wrec2[p ^ 1][warp];
       }
-    }
-    SAD_MARK1(0)
-    cta_sync();
-    SAD_MARK1(1)
-
-    // ---- warp 0 reduces the NW records (max value, ties -> lowest original index) and publishes the pick: one
-    // warp's two redux instead of every warp's (the redux unit is shared; NW redundant reductions queue on it)
-#if defined(SAD_FPS_ABLATE) && SAD_FPS_ABLATE >= 4
-    if (false) {
-#else
-    if (warp == 0) {
-#endif
-      const uint32_t x = lane < NW ? s_wval[lane] : 0u;
-      const uint32_t id = lane < NW ? __float_as_uint(s_wrec[lane].w) : kInf;
-      const uint32_t gmax = __reduce_max_sync(FULL, x);
-      const uint32_t gidx = __reduce_min_sync(FULL, x == gmax ? id : kInf);
-      if (x == gmax && id == gidx && lane < NW) {
-        s_pick = s_wrec[lane];
-        s_out[j & (FC1_OUT - 1)] = (int32_t)gidx;
-      }
-    }
-    cta_sync();
-    if (((j + 1) & (FC1_OUT - 1)) == 0 || j == npoint - 1) {     // flush the buffered picks (coalesced, rare)
-      const int j0 = j & ~(FC1_OUT - 1);
-      for (int i = tid; j0 + i <= j; i += NW * 32) o[j0 + i] = s_out[i];
-    }
-    {
-      const float4 w = s_pick;
+      if (lane == 0) atomicMax(&s_key[k3], ckey);
+      SAD_MARK1(0)
+      cta_sync();
+      SAD_MARK1(1)
+      const unsigned long long key = s_key[k3];
+      const float4 w = s_wrec2[p][(int)(key & 31ull)];
       qx = w.x;
       qy = w.y;
       qz = w.z;
+      if (tid == 0) {
+        s_out[j & (FC1_OUT - 1)] = (int32_t)__float_as_uint(w.w);
+        s_key[k3 == 0 ? 2 : k3 - 1] = 0ull;               // the key of pick j + 2
+      }
+      k3 = k3 == 2 ? 0 : k3 + 1;
+      if (((j + 1) & (FC1_OUT - 1)) == 0 || j == npoint - 1) {     // flush the buffered picks (coalesced, rare)
+        cta_sync();
+        const int j0 = j & ~(FC1_OUT - 1);
+        for (int i = tid; j0 + i <= j; i += NW * 32) o[j0 + i] = s_out[i];
+      }
+    } else {
+      // ---- this warp's record: its best bucket (rewritten only when one of its buckets changed; records are read
+      // by warp 0 alone, between the two barriers, so one buffer suffices and an unchanged warp does nothing)
+      __syncwarp();
+      if (changed) {
+        uint32_t v = 0u, vi = kInf;
+        int vr = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const bool valid = (r * 32 + lane) < nslots;
+          const uint32_t x = valid ? __float_as_uint(bmax[r]) : 0u;
+          const uint32_t id = valid ? bidx[r] : kInf;
+          // branch-free on purpose: a divergent compare chain leaves the warp unconverged at the redux below, which
+          // then takes its slow collective path (measured: ~900 instead of ~150 cycles for this block)
+          const bool take = (x > v) | ((x == v) & (id < vi));
+          v = take ? x : v;
+          vi = take ? id : vi;
+          vr = take ? r : vr;
+        }
+        const uint32_t wmax = __reduce_max_sync(FULL, v);
+        const uint32_t widx = __reduce_min_sync(FULL, v == wmax ? vi : kInf);
+        if (widx == kInf) {
+          if (lane == 0) {
+            s_wval[warp] = 0u;
+            s_wrec[warp] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInf));
+          }
+        } else if (v == wmax && vi == widx) {
+          s_wval[warp] = wmax;
+          s_wrec[warp] = s_best[(vr * 32 + lane) * NW + warp];
+        }
+      }
+      SAD_MARK1(0)
+      cta_sync();
+      SAD_MARK1(1)
+
+      // ---- warp 0 reduces the NW records (max value, ties -> lowest original index) and publishes the pick: one
+      // warp's two redux instead of every warp's (the redux unit is shared; NW redundant reductions queue on it)
+#if defined(SAD_FPS_ABLATE) && SAD_FPS_ABLATE >= 4
+      if (false) {
+#else
+      if (warp == 0) {
+#endif
+        const uint32_t x = lane < NW ? s_wval[lane] : 0u;
+        const uint32_t id = lane < NW ? __float_as_uint(s_wrec[lane].w) : kInf;
+        const uint32_t gmax = __reduce_max_sync(FULL, x);
+        const uint32_t gidx = __reduce_min_sync(FULL, x == gmax ? id : kInf);
+        if (x == gmax && id == gidx && lane < NW) {
+          s_pick = s_wrec[lane];
+          s_out[j & (FC1_OUT - 1)] = (int32_t)gidx;
+        }
+      }
+      cta_sync();
+      if (((j + 1) & (FC1_OUT - 1)) == 0 || j == npoint - 1) {     // flush the buffered picks (coalesced, rare)
+        const int j0 = j & ~(FC1_OUT - 1);
+        for (int i = tid; j0 + i <= j; i += NW * 32) o[j0 + i] = s_out[i];
+      }
+      {
+        const float4 w = s_pick;
+        qx = w.x;
+        qy = w.y;
+        qz = w.z;
+      }
     }
     if (j == npoint - 1) break;
     SAD_MARK1(2)

@@ -133,7 +133,7 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples SM clock + throttle reasons through NVML every ~5 ms on a side thread
+    """Samples SM clock + throttle reasons through NVML every ~2 ms on a side thread
     (the recipe's nvidia-smi line, without its start-up latency)."""
 
     def __init__(self, index):
@@ -159,7 +159,7 @@ class ClockSampler:
                 self.rows.append((time.perf_counter(), sm, rs))
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.004)
+            time.sleep(0.002)
 
     def stop(self, t0, t1):
         if not self.ok:
@@ -172,12 +172,15 @@ class ClockSampler:
                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
                 "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
         sm, reasons = [], set()
-        for (t, c, rs) in self.rows:
-            if t0 <= t <= t1:
-                sm.append(c)
-                for name, bit in bits.items():
-                    if rs & bit:
-                        reasons.add(name)
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        if not rows and self.rows:      # a window shorter than one polling period: the sample nearest to it
+            mid = 0.5 * (t0 + t1)
+            rows = [min(self.rows, key=lambda r: abs(r[0] - mid))]
+        for (t, c, rs) in rows:
+            sm.append(c)
+            for name, bit in bits.items():
+                if rs & bit:
+                    reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(reasons),
                 "samples": len(sm)}
