@@ -252,9 +252,11 @@ fps_cull_kernel(int N, int npoint, const float* __restrict__ xyz, const uint8_t*
 // Single-CTA variant: one SM per scene, any N.  The points stay in the (L2-resident) sorted array and
 // the min-distances in the workspace scratch; the CTA keeps only per-bucket state on chip: box / bmax /
 // bidx in registers (slot s of a warp lives in lane s % 32, register set s / 32) and each bucket's
-// best point in shared memory.  A pick costs: one block barrier, a 16-record reduce, the lane-parallel
-// box test, and an L2 round trip for the handful of buckets that survive it (two at a time per warp for
-// latency overlap) -- no cluster, no DSMEM exchange, and 1/4 .. 1/16 of the SMs of the other kernels.
+// best point in shared memory.  A pick costs: each warp's record merged into a packed 64-bit key (shared-memory
+// max), ONE block barrier, the winner's record read by every thread, the lane-parallel box test, and an L2 round
+// trip for the handful of buckets that survive it (four at a time per warp for latency overlap) -- no cluster, no
+// DSMEM exchange, and 1/4 .. 1/16 of the SMs of the other kernels.  (Two scenes per CTA, SC == 2, keep the earlier
+// barrier -> warp-0 reduce -> barrier sequence on a named barrier per scene.)
 constexpr int FC1_NW = 16;                // warps of the capacity bound (sad_fps_grid_max_points)
 constexpr int FC1_DEPTH = 4;              // bucket updates (independent L2 round trips) in flight per warp
 constexpr int FC1_OUT = 2048;             // picks buffered in shared memory between flushes to the output
