@@ -34,3 +34,30 @@ def test_our_arm_refuses_to_run_without_a_gpu():
     assert r.returncode != 0
     assert "CUDA" in (r.stderr + r.stdout)
     assert not [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
+
+
+def test_clock_sampler_window_selection():
+    """The `clocks` block: median SM clock and throttle reasons of the samples inside the timed window; a window shorter
+    than one polling period (the driver's 20-step run is ~7 ms) takes the nearest sample instead of reporting nothing."""
+    import threading
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class NV:
+        nvmlClocksEventReasonHwSlowdown, nvmlClocksEventReasonHwThermalSlowdown = 1, 2
+        nvmlClocksEventReasonSwThermalSlowdown, nvmlClocksEventReasonSwPowerCap = 4, 8
+
+    def sampler(rows):
+        s = bench.ClockSampler.__new__(bench.ClockSampler)
+        s.ok, s._stop, s.nv, s.smax, s.rows = True, False, NV, 1965.0, list(rows)
+        s.th = threading.Thread(target=lambda: None)
+        s.th.start()
+        return s
+
+    rows = [(1.0, 1900.0, 0), (2.0, 1965.0, 8), (3.0, 1950.0, 2)]
+    inside = sampler(rows).stop(0.5, 2.5)
+    assert inside == {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 2}
+    short = sampler(rows).stop(2.8, 2.9)                       # no sample inside: the nearest one (t = 3.0)
+    assert short["samples"] == 1 and short["sm_mhz"] == 1950.0 and short["reasons"] == ["hw_thermal_slowdown"]
+    none = sampler([]).stop(0.0, 1.0)
+    assert none["sm_mhz"] is None and none["samples"] == 0
